@@ -1,0 +1,57 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY -- builds oracle/_ref/: the reference's own C++ solver stack
+# (PoissonOp / MGSolver / LevelHybridSolver / Chombo containers), compiled UNMODIFIED from the
+# sources where they lie under /root/reference (serial, no Python, no MPI), linked against
+# oracle/fort_leaves.cpp (our C++ restatement of the Chombo-Fortran leaf kernels + dgtsv; this
+# image has no gfortran / LAPACK) and oracle/ref_driver.cpp (a small driver standing in for
+# AMRNSLevel::projectCorrect).  Outputs go ONLY into oracle/_ref/ (git-ignored).
+#
+# Usage: oracle/build_ref.sh [2|3]       (space dimension; default 3)
+set -euo pipefail
+DIM="${1:-3}"
+REF="${SOMAR_REFERENCE:-/root/reference}"
+HERE="$(cd "$(dirname "$0")" && pwd)"
+OUT="$HERE/_ref/d$DIM"
+GEN="$OUT/gen"
+OBJ="$OUT/obj"
+JOBS="${JOBS:-$(nproc)}"
+if [ ! -d "$REF/src" ]; then echo "reference tree not found at $REF -- nothing to build"; exit 0; fi
+mkdir -p "$GEN" "$OBJ"
+
+# 1. ChF -> _F.H prototypes with the vendored perl preprocessor (site_scons/site_init.py:58-66).
+for f in $(find "$REF/src" -name '*.ChF'); do
+  b="$(basename "$f" .ChF)"
+  if [ ! -s "$GEN/${b}_F.H" ]; then
+    (cd "$GEN" && perl -I "$REF/compileUtils/chfpp" "$REF/compileUtils/chfpp/uber.pl" -f "$f" -p /dev/null -c "$GEN/${b}_F.H" -D"$DIM")
+  fi
+done
+
+# 2. include path = every directory under src (PyGlue excluded), as site_init.py:285-296 does.
+INC="-I$GEN -I$HERE"
+for d in $(find "$REF/src" -type d | grep -v PyGlue); do INC="$INC -I$d"; done
+DEFS="-DCH_SPACEDIM=$DIM -DCH_Linux -DCH_USE_64 -DCH_USE_DOUBLE -DCH_FORT_UNDERSCORE -DCH_LANG_CC -DCH_NTIMER -DNDEBUG -DCH_USE_COMPLEX"
+CXXFLAGS="-std=c++17 -O3 -funroll-loops -ffp-contract=off -fPIC -w $DEFS"
+
+# 3. compile the reference sources (object names flattened).
+# Grade5 (the Navier-Stokes physics) is out of scope: only the parameter singleton the solvers read.
+SRCS=$(find "$REF/src" -name '*.cpp' | grep -v PyGlue | grep -v Grade5_SOMAR;
+       ls "$REF"/src/Grade5_SOMAR/{ProblemContext,ProjectorParameters,RHSParameters}.cpp)
+echo "$SRCS" | xargs -P "$JOBS" -I{} bash -c '
+  s="{}"; o="'"$OBJ"'/$(basename "$s" .cpp).o"
+  if [ ! -s "$o" ] || [ "$s" -nt "$o" ]; then g++ '"$CXXFLAGS $INC"' -c "$s" -o "$o" || { echo "FAILED: $s"; exit 255; }; fi'
+
+# 4. our pieces.
+g++ $CXXFLAGS $INC -c "$HERE/fort_leaves.cpp" -o "$OBJ/_fort_leaves.o"
+g++ $CXXFLAGS $INC -c "$HERE/ref_driver.cpp" -o "$OBJ/_ref_driver.o"
+
+# 5. link; any Fortran leaf the driver never reaches becomes an aborting stub.
+OBJS=$(for s in $SRCS; do echo "$OBJ/$(basename "$s" .cpp).o"; done)
+link() { g++ -o "$OUT/somar_ref" $OBJS "$OBJ/_fort_leaves.o" "$OBJ/_ref_driver.o" $1 -lpthread 2>&1; }
+if ! link "" > "$OUT/link1.log"; then
+  grep -o "undefined reference to \`[A-Za-z0-9_]*'" "$OUT/link1.log" | sed "s/.*\`//; s/'//" | sort -u > "$OUT/undefined.txt"
+  { echo '#include <stdio.h>'; echo '#include <stdlib.h>';
+    while read -r s; do echo "void $s(void){fprintf(stderr,\"oracle/_ref: unreached Fortran leaf $s was called\\n\");abort();}"; done < "$OUT/undefined.txt"; } > "$GEN/fort_stubs.c"
+  gcc -fPIC -c "$GEN/fort_stubs.c" -o "$OBJ/_fort_stubs.o"
+  link "$OBJ/_fort_stubs.o" > "$OUT/link2.log" || { cat "$OUT/link2.log" | head -50; exit 1; }
+fi
+echo "built $OUT/somar_ref"

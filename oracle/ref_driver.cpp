@@ -1,0 +1,433 @@
+// TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Nothing in somar_b200/ may call this.
+//
+// ref_driver: stands in for AMRNSLevel::projectCorrect (reference
+// src/Grade5_SOMAR/AMRNSLevelProject.cpp:247-373) and AMRNSLevel::validateOpsAndSolvers
+// (src/Grade5_SOMAR/AMRNSLevelInit.cpp:590-690) so that the reference's OWN, UNMODIFIED
+// Elliptic::PoissonOp / MGSolver / BiCGStabSolver / LevelHybridSolver classes (compiled from
+// /root/reference by oracle/build_ref.sh) can be run on inputs prepared by the tests.
+//
+// It only (a) builds the single-level grids the way AnisotropicAMR::makeBaseLevelMesh does
+// (src/Grade2_AnisotropicChombo/AnisotropicAMR.cpp:1461-1580), (b) constructs LevelGeometry,
+// PoissonOp and LevelHybridSolver with the same arguments AMRNSLevel uses, (c) taps the
+// depth-0 operator's virtual norm() so that the per-cycle residual norms are available in full
+// precision (the reference only prints 7 digits), and (d) reads / writes flat binary files.
+//
+// Usage: somar_ref <deck> [key=value ...]
+//   drv.mode  = solve | project | applyop | relax
+//   drv.map   = cartesian | stretched        drv.ampl = ax ay az (StretchedMap amplitudes)
+//   drv.in    = <file>    raw little-endian doubles, global Fortran order over the domain box:
+//                  solve:   rhs[nx*ny*nz]
+//                  project: U0[(nx+1)*ny*nz] U1[nx*(ny+1)*nz] U2[nx*ny*(nz+1)]  (advecting velocity)
+//                  applyop: phi[nx*ny*nz]
+//                  relax:   phi[nx*ny*nz] rhs[nx*ny*nz]
+//   drv.out   = <prefix>  writes <prefix>.bin (doubles) and <prefix>.txt (key = value lines)
+//   drv.relaxIters = n (relax mode)
+//   drv.reps = n          repeat the solve n times for timing (first result is dumped)
+//   drv.useMGSolver = 1   call MGSolver directly instead of LevelHybridSolver (always MG mode)
+//   drv.refSchedule = r0x r0y r0z r1x ... explicit MG refinement schedule (drv.useMGSolver=1)
+#include <chrono>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+#include <vector>
+
+#include "BCTools.H"
+#include "CartesianMap.H"
+#include "DisjointBoxLayout.H"
+#include "FluxBox.H"
+#include "LevelData.H"
+#include "LevelGeometry.H"
+#include "LevelHybridSolver.H"
+#include "MGSolver.H"
+#include "ParmParse.H"
+#include "PoissonOp.H"
+#include "ProblemContext.H"
+#include "StretchedMap.H"
+
+using Elliptic::PoissonOp;
+typedef LevelData<FArrayBox> LDFAB;
+
+static std::vector<double> g_norms;  // every depth-0 norm() result, in call order
+static long g_relaxCalls = 0, g_relaxIters = 0, g_residualCalls = 0;
+
+// Depth-0 tap.  MGSolver::define clones its top operator with newMGOperator(Unit)
+// (MGSolverI.H:188), so the clone must be a TapOp too.
+class TapOp : public PoissonOp
+{
+public:
+    using PoissonOp::PoissonOp;
+    TapOp(const PoissonOp& a_src) : PoissonOp(a_src) {}
+
+    Real
+    norm(const LDFAB& a_x, const int a_p, const Real a_powScale = 1.0) const override
+    {
+        const Real v = PoissonOp::norm(a_x, a_p, a_powScale);
+        g_norms.push_back(v);
+        return v;
+    }
+
+    void
+    relax(LDFAB& a_cor, const LDFAB& a_res, const Real a_time, const int a_iters) const override
+    {
+        ++g_relaxCalls;
+        g_relaxIters += a_iters;
+        PoissonOp::relax(a_cor, a_res, a_time, a_iters);
+    }
+
+    Elliptic::MGOperator<LDFAB>*
+    newMGOperator(const IntVect& a_refRatio) const override
+    {
+        if (a_refRatio == IntVect::Unit) return new TapOp(*this);
+        return PoissonOp::newMGOperator(a_refRatio);
+    }
+
+    const LDFAB&   J() const { return m_J; }
+    const LDFAB&   Dinv() const { return m_Dinv; }
+    const FArrayBox& M(int d) const { return m_M[d]; }
+    bool           hasNullSpace() const { return m_hasNullSpace; }
+};
+
+
+static void
+makeBaseGrids(Vector<Box>& a_grids, const ProblemDomain& a_domain, const IntVect& a_maxBGS,
+              const IntVect& a_splitDirs, const int a_blockFactor)
+{
+    // Same arithmetic as AnisotropicAMR::makeBaseLevelMesh.
+    const IntVect unsplit = IntVect::Unit - a_splitDirs;
+    const IntVect bf      = a_blockFactor * a_splitDirs + unsplit;
+    IntVect       maxBGS  = a_maxBGS;
+    for (int d = 0; d < SpaceDim; ++d) {
+        if (maxBGS[d] == 0 || maxBGS[d] > a_domain.size(d) || a_splitDirs[d] == 0)
+            maxBGS[d] = a_domain.size(d);
+    }
+    Box blk = coarsen(a_domain.domainBox(), bf);
+    if (refine(blk, bf) != a_domain.domainBox()) MayDay::Error("domain not coarsenable by blockFactor");
+    for (int d = 0; d < SpaceDim; ++d) {
+        if (a_splitDirs[d] == 1) continue;
+        blk.shift(d, -blk.smallEnd(d));
+        blk.setBig(d, blk.smallEnd(d));
+    }
+    IntVect num, base;
+    for (int d = 0; d < SpaceDim; ++d) {
+        int       nd = 1;
+        const int sz = blk.size(d);
+        if (a_splitDirs[d] == 0) {
+            num[d] = 1; base[d] = sz;
+        } else {
+            const int bmax = maxBGS[d] / a_blockFactor;
+            if (bmax <= 0) MayDay::Error("maxBaseGridSize < blockFactor");
+            while (nd * bmax < sz) ++nd;
+            num[d] = nd; base[d] = (sz + nd - 1) / nd;
+        }
+    }
+    const Box b(IntVect::Zero, num - IntVect::Unit);
+    for (BoxIterator bit(b); bit.ok(); ++bit) {
+        const IntVect slo = a_splitDirs * (blk.smallEnd() + bit() * base);
+        const IntVect shi = a_splitDirs * min(slo + base - IntVect::Unit, blk.bigEnd());
+        const IntVect lo  = slo + unsplit * a_domain.domainBox().smallEnd();
+        const IntVect hi  = shi + unsplit * a_domain.domainBox().bigEnd();
+        Box g(lo, hi);
+        g.refine(bf);
+        a_grids.push_back(g);
+    }
+}
+
+
+// global flat array (Fortran order over a_region) <-> LevelData
+static void
+scatter(LDFAB& a_dst, const double* a_src, const Box& a_region)
+{
+    const IntVect lo = a_region.smallEnd();
+    const IntVect sz = a_region.size();
+    for (DataIterator dit = a_dst.dataIterator(); dit.ok(); ++dit) {
+        Box bx = a_dst.getBoxes()[dit];
+        bx.convert(a_region.type());
+        bx &= a_dst[dit].box();
+        for (BoxIterator bit(bx); bit.ok(); ++bit) {
+            const IntVect iv = bit() - lo;
+            size_t idx = iv[0] + sz[0] * (size_t)(iv[1] D_TERM(, , +sz[1] * (size_t)iv[2]));
+            a_dst[dit](bit(), 0) = a_src[idx];
+        }
+    }
+}
+static void
+scatterFAB(FArrayBox& a_dst, const Box& a_valid, const double* a_src, const Box& a_region)
+{
+    const IntVect lo = a_region.smallEnd();
+    const IntVect sz = a_region.size();
+    Box bx = a_valid;
+    bx.convert(a_region.type());
+    bx &= a_dst.box();
+    for (BoxIterator bit(bx); bit.ok(); ++bit) {
+        const IntVect iv = bit() - lo;
+        size_t idx = iv[0] + sz[0] * (size_t)(iv[1] D_TERM(, , +sz[1] * (size_t)iv[2]));
+        a_dst(bit(), 0) = a_src[idx];
+    }
+}
+static void
+gatherFAB(std::vector<double>& a_dst, const FArrayBox& a_src, const Box& a_valid, const Box& a_region)
+{
+    const IntVect lo = a_region.smallEnd();
+    const IntVect sz = a_region.size();
+    Box bx = a_valid;
+    bx.convert(a_region.type());
+    bx &= a_src.box();
+    for (BoxIterator bit(bx); bit.ok(); ++bit) {
+        const IntVect iv = bit() - lo;
+        size_t idx = iv[0] + sz[0] * (size_t)(iv[1] D_TERM(, , +sz[1] * (size_t)iv[2]));
+        a_dst[idx] = a_src(bit(), 0);
+    }
+}
+static std::vector<double>
+gather(const LDFAB& a_src, const Box& a_region)
+{
+    std::vector<double> v(a_region.numPts(), 0.0);
+    for (DataIterator dit = a_src.dataIterator(); dit.ok(); ++dit)
+        gatherFAB(v, a_src[dit], a_src.getBoxes()[dit], a_region);
+    return v;
+}
+
+struct OutFile {
+    FILE*         bin;
+    std::ofstream txt;
+    size_t        off = 0;
+    OutFile(const std::string& p) : bin(fopen((p + ".bin").c_str(), "wb")), txt(p + ".txt")
+    {
+        txt << std::setprecision(17) << std::scientific;
+    }
+    ~OutFile() { fclose(bin); }
+    void
+    put(const std::string& name, const std::vector<double>& v)
+    {
+        fwrite(v.data(), sizeof(double), v.size(), bin);
+        txt << "array " << name << " " << off << " " << v.size() << "\n";
+        off += v.size();
+    }
+    template <class T>
+    void
+    kv(const std::string& k, const T& v)
+    {
+        txt << k << " = " << v << "\n";
+    }
+};
+
+
+int
+main(int argc, char* argv[])
+{
+    if (argc < 2) {
+        fprintf(stderr, "usage: %s <deck> [key=value ...]\n", argv[0]);
+        return 2;
+    }
+    ParmParse ppRoot(argc - 2, argv + 2, NULL, argv[1]);
+
+    const ProblemContext* ctx = ProblemContext::getInstance();
+    ParmParse             drv("drv");
+
+    std::string mode = "solve", mapName = "cartesian", inFile, outPrefix = "ref_out";
+    drv.query("mode", mode);
+    drv.query("map", mapName);
+    drv.query("in", inFile);
+    drv.query("out", outPrefix);
+    int reps = 1, useMGSolver = 0, relaxIters = 1;
+    drv.query("reps", reps);
+    drv.query("useMGSolver", useMGSolver);
+    drv.query("relaxIters", relaxIters);
+
+    const ProblemDomain& domain = ctx->base.domain;
+    const Box            domBox = domain.domainBox();
+    const RealVect       L      = ctx->base.L;
+
+    // Geometry (exec/*/UserMain.cpp::oneTimeSetup).
+    GeoSourceInterface* geoPtr = nullptr;
+    if (mapName == "cartesian") {
+        geoPtr = new CartesianMap();
+    } else if (mapName == "stretched") {
+        Vector<Real> vampl(SpaceDim, 0.0);
+        drv.queryarr("ampl", vampl, 0, SpaceDim);
+        const RealVect dx   = L / RealVect(ctx->base.nx);
+        const RealVect xmin = RealVect(ctx->base.nxOffset) * dx;
+        const RealVect xmax = xmin + L;
+        geoPtr              = new StretchedMap(xmin, xmax, RealVect(vampl));
+    } else {
+        MayDay::Error("drv.map must be cartesian or stretched");
+    }
+
+    // Grids.
+    Vector<Box> boxes;
+    makeBaseGrids(boxes, domain, ctx->base.maxBaseGridSize, ctx->base.splitDirs, ctx->base.blockFactor);
+    DisjointBoxLayout grids;
+    grids.defineAndLoadBalance(boxes, nullptr, domain);
+
+    LevelGeometry levGeo(domain, L, nullptr, geoPtr);
+    levGeo.createMetricCache(grids);
+
+    // Operator + solver, as AMRNSLevel::validateOpsAndSolvers does.
+    std::shared_ptr<BCTools::BCFunction> bcPtr(new BCTools::HomogNeumBC);
+    std::shared_ptr<TapOp> opPtr(new TapOp(levGeo, DisjointBoxLayout(), DisjointBoxLayout(), 1, bcPtr, 0.0, 1.0, nullptr));
+
+    OutFile out(outPrefix);
+    out.kv("spacedim", SpaceDim);
+    out.kv("numBoxes", boxes.size());
+    {
+        LayoutIterator lit = grids.layoutIterator();
+        int            n   = 0;
+        for (lit.reset(); lit.ok(); ++lit, ++n) {
+            const Box& b = grids[lit];
+            out.txt << "box " << n;
+            for (int d = 0; d < SpaceDim; ++d) out.txt << " " << b.smallEnd(d);
+            for (int d = 0; d < SpaceDim; ++d) out.txt << " " << b.bigEnd(d);
+            out.txt << "\n";
+        }
+    }
+    out.kv("hasNullSpace", (int)opPtr->hasNullSpace());
+    out.kv("relaxMethod", ctx->proj.relaxMethod);
+
+    // Metric dump (lets the tests pin the host-side geometry of the product).
+    {
+        out.put("J", gather(opPtr->J(), domBox));
+        out.put("Dinv", gather(opPtr->Dinv(), domBox));
+        for (int d = 0; d < SpaceDim; ++d) {
+            const FArrayBox&    M = opPtr->M(d);
+            std::vector<double> v(M.box().numPts() * 2);
+            for (size_t i = 0; i < v.size(); ++i) v[i] = M.dataPtr(0)[i];
+            out.put(std::string("M") + char('0' + d), v);
+        }
+        for (int d = 0; d < SpaceDim; ++d) {
+            Box fcDom = surroundingNodes(domBox, d);
+            std::vector<double> v(fcDom.numPts(), 0.0);
+            for (DataIterator dit(grids); dit.ok(); ++dit)
+                gatherFAB(v, opPtr->getFCJgup()[dit][d], grids[dit], fcDom);
+            out.put(std::string("Jgup") + char('0' + d), v);
+        }
+    }
+
+    // Read input.
+    std::vector<double> in;
+    if (!inFile.empty()) {
+        FILE* f = fopen(inFile.c_str(), "rb");
+        if (!f) MayDay::Error("cannot open drv.in");
+        fseek(f, 0, SEEK_END);
+        const long nb = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        in.resize(nb / sizeof(double));
+        if (fread(in.data(), sizeof(double), in.size(), f) != in.size()) MayDay::Error("short read");
+        fclose(f);
+    }
+    const size_t N = domBox.numPts();
+
+    if (mode == "applyop") {
+        LDFAB phi(grids, 1, IntVect::Unit), lhs(grids, 1);
+        for (DataIterator dit(grids); dit.ok(); ++dit) phi[dit].setVal(0.0);
+        scatter(phi, in.data(), domBox);
+        opPtr->applyOp(lhs, phi, nullptr, 0.0, true, true);
+        out.put("lhs", gather(lhs, domBox));
+        g_norms.clear();
+        out.kv("norm2", opPtr->norm(lhs, 2));
+        out.kv("norm0", opPtr->norm(lhs, 0));
+        return 0;
+    }
+
+    if (mode == "relax") {
+        LDFAB phi(grids, 1, IntVect::Unit), rhs(grids, 1);
+        for (DataIterator dit(grids); dit.ok(); ++dit) phi[dit].setVal(0.0);
+        scatter(phi, in.data(), domBox);
+        scatter(rhs, in.data() + N, domBox);
+        opPtr->relax(phi, rhs, 0.0, relaxIters);
+        out.put("phi", gather(phi, domBox));
+        return 0;
+    }
+
+    // Solver.
+    Elliptic::LevelHybridSolver          hybrid;
+    Elliptic::MGSolver<LDFAB>            mg;
+    Elliptic::LevelHybridSolver::Options hopt = Elliptic::LevelHybridSolver::getDefaultOptions();
+    if (useMGSolver) {
+        Vector<IntVect> sched;
+        Vector<int>     vs;
+        if (drv.contains("refSchedule")) {
+            drv.queryarr("refSchedule", vs, 0, drv.countval("refSchedule"));
+            for (size_t i = 0; i + SpaceDim <= vs.size(); i += SpaceDim)
+                sched.push_back(IntVect(D_DECL(vs[i], vs[i + 1], vs[i + 2])));
+        }
+        mg.define(*opPtr, hopt.mgOptions, sched);
+        const auto& o = mg.getOptions();
+        out.kv("maxDepth", o.maxDepth);
+    } else {
+        hybrid.define(opPtr, hopt);
+        struct Peek : Elliptic::LevelHybridSolver { using Elliptic::LevelHybridSolver::computeSolveMode; };
+        std::shared_ptr<const Elliptic::MGOperator<LDFAB>> mgOpPtr = opPtr;
+        out.kv("solveMode", (int)Peek::computeSolveMode(mgOpPtr, hopt));  // 1 MG, 2 Leptic, 3 Leptic_MG
+        out.kv("maxDepth", hybrid.getOptions().mgOptions.maxDepth);
+    }
+
+    LDFAB rhs(grids, 1), phi(grids, 1, IntVect::Unit);
+    LevelData<FluxBox> vel, gradPhi;
+    double initDivNorm = 0.0;
+
+    if (mode == "project") {
+        vel.define(grids, 1);
+        gradPhi.define(grids, 1);
+        size_t off = 0;
+        for (int d = 0; d < SpaceDim; ++d) {
+            const Box fcDom = surroundingNodes(domBox, d);
+            for (DataIterator dit(grids); dit.ok(); ++dit)
+                scatterFAB(vel[dit][d], grids[dit], in.data() + off, fcDom);
+            off += fcDom.numPts();
+        }
+        opPtr->levelDivergence(rhs, vel);
+        initDivNorm = opPtr->PoissonOp::norm(rhs, ctx->proj.normType);
+        out.put("div", gather(rhs, domBox));
+        out.kv("initDivNorm", initDivNorm);
+    } else if (mode == "solve") {
+        scatter(rhs, in.data(), domBox);
+    } else {
+        MayDay::Error("unknown drv.mode");
+    }
+
+    Elliptic::SolverStatus status;
+    std::vector<double>    times;
+    std::vector<double>    firstNorms;
+    for (int rep = 0; rep < reps; ++rep) {
+        g_norms.clear();
+        g_relaxCalls = g_relaxIters = 0;
+        const auto t0 = std::chrono::high_resolution_clock::now();
+        if (useMGSolver) {
+            status = mg.solve(phi, nullptr, rhs, 0.0, true, true);
+        } else {
+            status = hybrid.solve(phi, nullptr, rhs, 0.0, true, true);
+        }
+        const auto t1 = std::chrono::high_resolution_clock::now();
+        times.push_back(std::chrono::duration<double>(t1 - t0).count());
+        if (rep == 0) firstNorms = g_norms;
+    }
+    out.put("phi", gather(phi, domBox));
+    out.put("norms", firstNorms);
+    out.put("solveTimes", times);
+    out.kv("status", status.getSolverStatus());
+    out.kv("initResNorm", status.getInitResNorm());
+    out.kv("finalResNorm", status.getFinalResNorm());
+    out.kv("relaxCallsDepth0", g_relaxCalls);
+    out.kv("relaxItersDepth0", g_relaxIters);
+
+    if (mode == "project") {
+        // AMRNSLevelProject.cpp:326-337, 352-357.
+        opPtr->levelGradient(gradPhi, phi, nullptr, 0.0, true, true);
+        for (DataIterator dit(grids); dit.ok(); ++dit)
+            for (int d = 0; d < SpaceDim; ++d) vel[dit][d].plus(gradPhi[dit][d], -1.0);
+        for (int d = 0; d < SpaceDim; ++d) {
+            const Box           fcDom = surroundingNodes(domBox, d);
+            std::vector<double> v(fcDom.numPts(), 0.0), g(fcDom.numPts(), 0.0);
+            for (DataIterator dit(grids); dit.ok(); ++dit) {
+                gatherFAB(v, vel[dit][d], grids[dit], fcDom);
+                gatherFAB(g, gradPhi[dit][d], grids[dit], fcDom);
+            }
+            out.put(std::string("vel") + char('0' + d), v);
+            out.put(std::string("grad") + char('0' + d), g);
+        }
+        opPtr->levelDivergence(rhs, vel);
+        out.kv("finalDivNorm", opPtr->PoissonOp::norm(rhs, ctx->proj.normType));
+        out.put("divAfter", gather(rhs, domBox));
+    }
+    return 0;
+}
