@@ -1,0 +1,189 @@
+/* somar_b200.h -- C ABI of the B200-native pressure projection for SOMAR.
+ *
+ * This is the drop-in boundary: plain C, POD arguments, opaque handles, int return codes
+ * (0 = ok; on failure sb_last_error() holds the message -- the C++ shim turns that into
+ * MayDay::Error, the reference's error convention, Grade1_Basics/Debug.H:258).
+ *
+ * Every entry point names the reference interface it stands in for (path:line relative to
+ * /root/reference/src).  T = LevelData<FArrayBox>.  Conventions taken over unchanged:
+ *   - fp64 everywhere, Fortran order (x fastest), cell indices are global ints and may be
+ *     negative (Grade0_Chombo/BoxTools/BaseFabImplem.H:237);
+ *   - the vertical is the last direction and is never split between boxes when
+ *     relaxMethod == VERTLINE (Grade3_Calculus/Elliptic/PoissonOp.cpp:550-575);
+ *   - 2-D problems (CH_SPACEDIM == 2 builds of the reference) are passed with dim = 2; their
+ *     directions (x, z) are stored in slots 0 and 2 of every int[3]/double[3] here, slot 1
+ *     must describe a single layer (lo = hi = 0);
+ *   - a "field" is one LevelData: all boxes of this rank, 1 component, 1 ghost layer.
+ */
+#ifndef SOMAR_B200_H
+#define SOMAR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sb_context sb_context;
+typedef struct sb_op      sb_op;     /* Elliptic::PoissonOp at one MG depth            */
+typedef struct sb_field   sb_field;  /* LevelData<FArrayBox> or one FluxBox direction  */
+typedef struct sb_solver  sb_solver; /* Elliptic::MGSolver<T> / LevelHybridSolver      */
+
+/* ProjectorParameters::RelaxMethod (Grade5_SOMAR/ProjectorParameters.H) */
+enum { SB_RELAX_NONE = 0, SB_RELAX_JACOBI = 2, SB_RELAX_JACOBIRB = 3, SB_RELAX_GS = 4, SB_RELAX_GSRB = 5, SB_RELAX_VERTLINE = 6 };
+/* Elliptic::SolverStatus (Grade3_Calculus/Elliptic/SolverStatus.H:46-51) */
+enum { SB_STATUS_UNDEFINED = -1, SB_STATUS_DIVERGED = 0, SB_STATUS_CONVERGED = 1, SB_STATUS_SINGULAR = 2, SB_STATUS_MAXITERS = 3, SB_STATUS_HANG = 4 };
+/* GeoSourceInterface implementations (Grade3_Calculus/maps) */
+enum { SB_MAP_CARTESIAN = 0, SB_MAP_STRETCHED = 1, SB_MAP_CALLBACK = 2 };
+/* field centering */
+enum { SB_CELL = -1, SB_FACE_X = 0, SB_FACE_Y = 1, SB_FACE_Z = 2 };
+/* LevelHybridSolver::SolveMode (LevelHybridSolver.H) */
+enum { SB_MODE_MG = 1, SB_MODE_LEPTIC = 2, SB_MODE_LEPTIC_MG = 3 };
+
+/* GeoSourceInterface::interp (GeoSourceInterface.H): x[n] = map_mu(xi[n]). */
+typedef void (*sb_map_fn)(double* x, const double* xi, int n, int mu, void* user);
+
+/* Everything PoissonOp's main constructor reads from LevelGeometry, the grids, the BC functor
+ * and ProblemContext (PoissonOp.cpp:33-128). */
+typedef struct sb_level_desc {
+    int    dim;              /* 2 or 3 (CH_SPACEDIM of the reference build)                        */
+    int    domain_lo[3];     /* ProblemDomain::domainBox()                                        */
+    int    domain_hi[3];
+    int    periodic[3];      /* ProblemDomain::isPeriodic(d)                                      */
+    double dXi[3];           /* LevelGeometry::getDXi()                                           */
+    int    num_boxes;        /* DisjointBoxLayout, all ranks, in layout order                     */
+    const int* box_lo;       /* [num_boxes][3]                                                    */
+    const int* box_hi;       /* [num_boxes][3]                                                    */
+    const int* box_rank;     /* [num_boxes] owner (DisjointBoxLayout::procID); NULL = all rank 0  */
+    int    map_kind;         /* SB_MAP_*                                                          */
+    double map_xmin[3];      /* StretchedMap(xmin, xmax, ampl) (maps/StretchedMap.cpp:9-38)       */
+    double map_xmax[3];
+    double map_ampl[3];
+    sb_map_fn map_fn;        /* SB_MAP_CALLBACK                                                   */
+    void*  map_user;
+    double bc_alpha[3][2];   /* Robin BC alpha*phi + beta*dphi/dn = 0 per (dir, side);            */
+    double bc_beta[3][2];    /* BCTools::HomogNeumBC is alpha = 0, beta = 1 (AMRNSLevelBC.cpp:48) */
+    double alpha;            /* operator J(alpha + beta*Lap); the projector uses 0, 1             */
+    double beta;
+    int    relax_method;     /* proj.relaxMethod, read by PoissonOp.cpp:54 and MGSolverI.H:154    */
+} sb_level_desc;
+
+/* BiCGStabSolver<T>::Options (LevelSolver.H) */
+typedef struct sb_bottom_options {
+    double absTol, relTol, small, hang, convergenceMetric;
+    int    maxIters, maxRestarts, normType, verbosity, numSmoothPrecond;
+} sb_bottom_options;
+
+/* MGSolver<T>::Options (MGSolver.H:57-92) */
+typedef struct sb_mg_options {
+    double absTol, relTol, convergenceMetric, hang;
+    int    numSmoothDown, numSmoothUp, numSmoothBottom, numSmoothPrecond;
+    int    prolongOrder, prolongOrderFMG, numSmoothUpFMG;
+    int    maxDepth, numCycles, maxIters, normType, verbosity;
+    sb_bottom_options bottom;
+} sb_mg_options;
+
+#define SB_MAX_HISTORY 64
+typedef struct sb_solver_status {
+    int    status;                        /* SB_STATUS_*                                        */
+    int    num_iters;                     /* outer MG iterations executed                       */
+    double init_res_norm;                 /* SolverStatus::getInitResNorm                       */
+    double final_res_norm;                /* SolverStatus::getFinalResNorm                      */
+    int    num_norms;                     /* entries of res_norms                               */
+    double res_norms[SB_MAX_HISTORY];     /* absResNorms of MGSolverI.H:281,360 in call order   */
+    int    solve_mode;                    /* SB_MODE_* (hybrid solver only)                     */
+    int    max_depth;                     /* MGSolver::Options::maxDepth after define           */
+    double device_ms;                     /* CUDA-event time of the solve on this rank          */
+} sb_solver_status;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+const char* sb_last_error(void);
+int sb_version(void);
+/* One context per process / GPU.  rank, nranks describe the horizontal decomposition. */
+int sb_context_create(sb_context** ctx, int device, int rank, int nranks);
+int sb_context_destroy(sb_context* ctx);
+int sb_context_sync(sb_context* ctx);
+/* Number of kernels this library launched on the context's stream since creation. */
+long long sb_context_launch_count(sb_context* ctx);
+/* NCCL communicator for halo exchange and scalar reductions (stands in for Chombo's MPI layer,
+ * BoxTools/BoxLayoutDataI.H:665-812, BaseTools/Comm.cpp:19,41).  id is ncclUniqueId (128 B). */
+int sb_comm_get_unique_id(void* id128);
+int sb_comm_init(sb_context* ctx, const void* id128);
+
+/* ---- PoissonOp --------------------------------------------------------------------------- */
+/* PoissonOp::PoissonOp(levGeo, fineGrids, crseGrids, 1, bcFunc, alpha, beta) PoissonOp.cpp:33.
+ * The metric (J, Jgup) is built the way LevelGeometry::createMetricCache does
+ * (LevelGeometry.cpp:238-277) from the map in desc, or can be overwritten with
+ * sb_op_set_metric before sb_op_finalize. */
+int sb_op_create(sb_context* ctx, const sb_level_desc* desc, sb_op** op);
+/* Raw LevelGeometry caches for one box: J over [lo,hi] (cell box), Jgup_d over the face box. */
+int sb_op_set_metric(sb_op* op, int centering, int box_id, const double* host, const int lo[3], const int hi[3]);
+/* PoissonOp::setAlphaAndBeta -> cacheMatrixElements + checkForNullSpace (PoissonOp.cpp:510-718). */
+int sb_op_finalize(sb_op* op);
+int sb_op_destroy(sb_op* op);
+int sb_op_has_null_space(sb_op* op, int* out);
+/* MGOperator::newMGOperator(refRatio) (PoissonOp.cpp:970-985, coarsening ctor :334-405). */
+int sb_op_new_mg_operator(sb_op* op, const int ref[3], sb_op** crse);
+int sb_op_get_info(sb_op* op, int domain_lo[3], int domain_hi[3], double dXi[3], int* num_local_boxes);
+/* Read back a cached coefficient over the domain box in global Fortran order (tests): which =
+ * 0 J, 1 Dinv, 2/3/4 M_d (length 2*N_d: lower diagonals then upper), 5/6/7 Jgup_d (face box). */
+int sb_op_get_coefficient(sb_op* op, int which, double* host, long long capacity);
+
+/* ---- fields ------------------------------------------------------------------------------ */
+int sb_field_create(sb_op* op, int centering, sb_field** f);
+int sb_field_destroy(sb_field* f);
+/* Copy host FAB data (box [lo,hi] in the field's centering, ghosts included, Fortran order)
+ * into / out of the device field; only the part inside this rank's valid+ghost region moves. */
+int sb_field_upload(sb_field* f, const double* host, const int lo[3], const int hi[3]);
+int sb_field_download(sb_field* f, double* host, const int lo[3], const int hi[3]);
+
+/* ---- LevelOperator / StateOps / MGOperator methods ------------------------------------------ */
+int sb_op_apply_bcs(sb_op* op, sb_field* phi, int homog);                         /* PoissonOp.cpp:726-763 */
+int sb_op_apply_op(sb_op* op, sb_field* lhs, sb_field* phi, int homog);           /* PoissonOp.H applyOp   */
+int sb_op_residual(sb_op* op, sb_field* res, sb_field* phi, sb_field* rhs, int homog); /* LevelOperator.H:104 */
+int sb_op_relax(sb_op* op, sb_field* cor, sb_field* res, int iters);              /* PoissonOp.cpp:917     */
+int sb_op_precond(sb_op* op, sb_field* phi, sb_field* rhs, int relax_iters);      /* PoissonOp.cpp:893     */
+int sb_op_remove_kernel(sb_op* op, sb_field* phi);                                /* PoissonOp.cpp:821     */
+int sb_op_norm(sb_op* op, sb_field* x, int p, double pow_scale, double* out);     /* LDFABOps.cpp:134      */
+int sb_op_dot(sb_op* op, sb_field* a, sb_field* b, double* out);                  /* LDFABOps.cpp:98       */
+int sb_op_incr(sb_op* op, sb_field* lhs, sb_field* x, double scale);              /* LDFABOps.cpp:170      */
+int sb_op_axby(sb_op* op, sb_field* lhs, sb_field* x, sb_field* y, double a, double b);
+int sb_op_scale(sb_op* op, sb_field* lhs, double scale);
+int sb_op_set_to_zero(sb_op* op, sb_field* lhs);
+int sb_op_assign_local(sb_op* op, sb_field* dst, sb_field* src);
+int sb_op_mg_restrict(sb_op* fine, sb_op* crse, sb_field* crse_res, sb_field* fine_res);          /* PoissonOp.cpp:993  */
+int sb_op_mg_prolong(sb_op* fine, sb_op* crse, sb_field* fine_phi, sb_field* crse_cor, int order); /* PoissonOp.cpp:1032 */
+/* PoissonOp::levelDivergence (PoissonOp.cpp:1568) and levelGradient (:1486).  vel/grad are the
+ * D directions of a LevelData<FluxBox>. */
+int sb_op_level_divergence(sb_op* op, sb_field* div, sb_field* const vel[3]);
+int sb_op_level_gradient(sb_op* op, sb_field* const grad[3], sb_field* phi, int homog);
+/* vel[d] -= scale * grad[d]  (AMRNSLevelProject.cpp:331-336 with scale 1; :155-160 with projDt). */
+int sb_op_flux_incr(sb_op* op, sb_field* const vel[3], sb_field* const grad[3], double scale);
+
+/* ---- solvers ----------------------------------------------------------------------------- */
+void sb_mg_default_options(sb_mg_options* opt);        /* ProjectorParameters.cpp:124-222 defaults */
+void sb_mg_quick_and_dirty_options(sb_mg_options* opt);/* MGSolverI.H:56-74                        */
+/* MGSolver<T>::define(topOp, opt, refSchedule) (MGSolverI.H:140-204).  schedule = num_sched
+ * ref ratios ending with (1,1,1), or NULL/0 to run the reference's coarsening strategy. */
+int sb_mgsolver_create(sb_op* top, const sb_mg_options* opt, const int* schedule, int num_sched, sb_solver** s);
+/* LevelHybridSolver::define (LevelHybridSolver.cpp:127-190): picks the solve mode by lepticity. */
+int sb_hybrid_solver_create(sb_op* top, const sb_mg_options* opt, sb_solver** s);
+int sb_solver_destroy(sb_solver* s);
+int sb_solver_get_schedule(sb_solver* s, int* schedule, int capacity, int* num_sched);
+int sb_solver_set_options(sb_solver* s, const sb_mg_options* opt);   /* modifyOptionsExceptMaxDepth */
+/* MGSolver<T>::solve / LevelHybridSolver::solve(phi, NULL, rhs, time, homog, setPhiToZero, metric). */
+int sb_solver_solve(sb_solver* s, sb_field* phi, sb_field* rhs, int homog, int set_phi_to_zero,
+                    double convergence_metric, sb_solver_status* status);
+/* One vCycle_residualEq(cor, res, depth 0) (MGSolverI.H:617) -- the unit of the headline metric. */
+int sb_solver_vcycle(sb_solver* s, sb_field* cor, sb_field* res);
+
+/* ---- the projection bracket, host buffers in and out --------------------------------------- */
+/* AMRNSLevel::projectCorrect, single level (AMRNSLevelProject.cpp:247-373): vel is the advecting
+ * (J-scaled) face velocity, D host arrays over the face-centred *domain* box in global Fortran
+ * order; p may be NULL.  On return vel is projected, phi (cell-centred domain box) holds the
+ * correction, p += phi/projDt.  Copies H2D/D2H are part of the call. */
+int sb_project_host(sb_solver* s, double* const vel[3], double* phi, double* p, double proj_dt,
+                    double* init_div_norm, double* final_div_norm, sb_solver_status* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

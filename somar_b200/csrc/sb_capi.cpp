@@ -1,0 +1,423 @@
+// sb_capi.cpp -- the extern "C" boundary declared in include/somar_b200.h.  No exception and no
+// C++ type crosses it; failures set the thread-local message read by sb_last_error().
+#include <cstring>
+
+#include "sb_comm.h"
+#include "sb_host.h"
+
+using namespace sb;
+
+static thread_local std::string g_err;
+
+#define SB_TRY try {
+#define SB_END                                            \
+    return 0;                                             \
+    }                                                     \
+    catch (const std::exception& e) { g_err = e.what(); return 1; } \
+    catch (...) { g_err = "unknown error"; return 1; }
+#define REQ(p) if (!(p)) SB_FAIL("null argument: " #p)
+
+extern "C" {
+
+const char* sb_last_error(void) { return g_err.c_str(); }
+int         sb_version(void) { return 100; }
+
+int sb_context_create(sb_context** ctx, int device, int rank, int nranks)
+{
+    SB_TRY REQ(ctx);
+    if (nranks < 1 || rank < 0 || rank >= nranks) SB_FAIL("bad rank / nranks");
+    *ctx = new sb_context(device, rank, nranks);
+    SB_END
+}
+int sb_context_destroy(sb_context* ctx) { SB_TRY delete ctx; SB_END }
+int sb_context_sync(sb_context* ctx) { SB_TRY REQ(ctx); ctx->c.sync(); SB_END }
+long long sb_context_launch_count(sb_context* ctx) { return ctx ? k::launch_count() - ctx->c.launches0 : -1; }
+int sb_comm_get_unique_id(void* id128) { SB_TRY REQ(id128); Comm::getUniqueId(id128); SB_END }
+int sb_comm_init(sb_context* ctx, const void* id128)
+{
+    SB_TRY REQ(ctx); REQ(id128);
+    if (ctx->c.comm) SB_FAIL("communicator already initialised");
+    ctx->c.comm = new Comm(&ctx->c, id128);
+    SB_END
+}
+
+// ---- PoissonOp ------------------------------------------------------------------------------
+int sb_op_create(sb_context* ctx, const sb_level_desc* desc, sb_op** op)
+{
+    SB_TRY REQ(ctx); REQ(desc); REQ(op);
+    *op = new sb_op{new Op(&ctx->c, *desc), true};
+    SB_END
+}
+int sb_op_destroy(sb_op* op)
+{
+    SB_TRY if (op) { if (op->owned) delete op->op; delete op; }
+    SB_END
+}
+
+static void copy3d(Op& o, int centering, double* dev, double* host, const int lo[3], const int hi[3], bool toDevice)
+{
+    // allowed region of the device array in global indices
+    int alo[3], ahi[3];
+    for (int d = 0; d < 3; ++d) {
+        alo[d] = o.tile.lo[d] - 1;
+        ahi[d] = o.tile.hi[d] + 1;
+        if (d == centering) alo[d] = o.tile.lo[d];  // faces: valid faces only in their own direction
+    }
+    int clo[3], chi[3];
+    for (int d = 0; d < 3; ++d) {
+        clo[d] = std::max(lo[d], alo[d]);
+        chi[d] = std::min(hi[d], ahi[d]);
+        if (chi[d] < clo[d]) return;
+    }
+    const size_t hnx = (size_t)(hi[0] - lo[0] + 1), hny = (size_t)(hi[1] - lo[1] + 1);
+    cudaMemcpy3DParms p;
+    std::memset(&p, 0, sizeof(p));
+    cudaPitchedPtr hp = make_cudaPitchedPtr(host, hnx * sizeof(double), hnx, hny);
+    cudaPitchedPtr dp = make_cudaPitchedPtr(dev, (size_t)o.lay.px * sizeof(double), (size_t)o.lay.px, (size_t)o.lay.py);
+    cudaPos hpos = make_cudaPos((size_t)(clo[0] - lo[0]) * sizeof(double), (size_t)(clo[1] - lo[1]), (size_t)(clo[2] - lo[2]));
+    cudaPos dpos = make_cudaPos((size_t)(OX + clo[0] - o.tile.lo[0]) * sizeof(double), (size_t)(1 + clo[1] - o.tile.lo[1]),
+                                (size_t)(1 + clo[2] - o.tile.lo[2]));
+    p.extent = make_cudaExtent((size_t)(chi[0] - clo[0] + 1) * sizeof(double), (size_t)(chi[1] - clo[1] + 1),
+                               (size_t)(chi[2] - clo[2] + 1));
+    if (toDevice) { p.srcPtr = hp; p.srcPos = hpos; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
+    else { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
+    SB_CUDA(cudaMemcpy3DAsync(&p, o.ctx->st));
+}
+
+int sb_op_set_metric(sb_op* op, int centering, int box_id, const double* host, const int lo[3], const int hi[3])
+{
+    SB_TRY REQ(op); REQ(host);
+    Op& o = *op->op;
+    if (box_id < 0 || box_id >= (int)o.boxes.size()) SB_FAIL("box_id out of range");
+    if (o.boxRank[box_id] != o.ctx->rank) return 0;
+    if (centering < -1 || centering > 2) SB_FAIL("bad centering");
+    // copy only the part over this box (cells) / its faces
+    const Box3& b = o.boxes[box_id];
+    int clo[3], chi[3];
+    for (int d = 0; d < 3; ++d) {
+        clo[d] = std::max(lo[d], b.lo[d]);
+        chi[d] = std::min(hi[d], b.hi[d] + (d == centering ? 1 : 0));
+    }
+    // stage through a contiguous sub-box copy: cudaMemcpy3D handles the strides
+    const size_t hnx = (size_t)(hi[0] - lo[0] + 1), hny = (size_t)(hi[1] - lo[1] + 1);
+    const double* sub = host + (clo[0] - lo[0]) + hnx * ((size_t)(clo[1] - lo[1]) + hny * (size_t)(clo[2] - lo[2]));
+    // describe the sub-box as its own host box with the parent's pitch: emulate by per-plane copies
+    double* dev = centering < 0 ? o.J : o.Jgup[centering];
+    for (int kk = clo[2]; kk <= chi[2]; ++kk) {
+        const double* hp = sub + hnx * hny * (size_t)(kk - clo[2]);
+        double*       dp = dev + o.lay.idx(clo[0] - o.tile.lo[0], clo[1] - o.tile.lo[1], kk - o.tile.lo[2]);
+        SB_CUDA(cudaMemcpy2DAsync(dp, (size_t)o.lay.px * sizeof(double), hp, hnx * sizeof(double),
+                                  (size_t)(chi[0] - clo[0] + 1) * sizeof(double), (size_t)(chi[1] - clo[1] + 1),
+                                  cudaMemcpyHostToDevice, o.ctx->st));
+    }
+    o.ctx->sync();
+    SB_END
+}
+int sb_op_finalize(sb_op* op) { SB_TRY REQ(op); op->op->finalize(); op->op->ctx->sync(); SB_END }
+int sb_op_has_null_space(sb_op* op, int* out) { SB_TRY REQ(op); REQ(out); *out = op->op->hasNullSpace; SB_END }
+int sb_op_new_mg_operator(sb_op* op, const int ref[3], sb_op** crse)
+{
+    SB_TRY REQ(op); REQ(crse);
+    if (!op->op->finalized) SB_FAIL("sb_op_finalize first");
+    if (ref[0] == 1 && ref[1] == 1 && ref[2] == 1) SB_FAIL("newMGOperator(Unit) clones are not needed: reuse the handle");
+    *crse = new sb_op{new Op(*op->op, ref), true};
+    SB_END
+}
+int sb_op_get_info(sb_op* op, int domain_lo[3], int domain_hi[3], double dXi[3], int* num_local_boxes)
+{
+    SB_TRY REQ(op);
+    for (int d = 0; d < 3; ++d) {
+        if (domain_lo) domain_lo[d] = op->op->domain.lo[d];
+        if (domain_hi) domain_hi[d] = op->op->domain.hi[d];
+        if (dXi) dXi[d] = op->op->dXi[d];
+    }
+    if (num_local_boxes) *num_local_boxes = op->op->nlocal();
+    SB_END
+}
+int sb_op_get_coefficient(sb_op* op, int which, double* host, long long capacity)
+{
+    SB_TRY REQ(op); REQ(host);
+    Op& o = *op->op;
+    if (which >= 2 && which <= 4) {
+        const auto& m = o.hM[which - 2];
+        if ((long long)m.size() > capacity) SB_FAIL("capacity too small");
+        std::memcpy(host, m.data(), m.size() * sizeof(double));
+        return 0;
+    }
+    int centering = -1;
+    double* dev = nullptr;
+    if (which == 0) dev = o.J;
+    else if (which == 1) dev = o.Dinv;
+    else if (which >= 5 && which <= 7) { centering = which - 5; dev = o.Jgup[centering]; }
+    else SB_FAIL("bad coefficient id");
+    int lo[3], hi[3];
+    long long n = 1;
+    for (int d = 0; d < 3; ++d) { lo[d] = o.domain.lo[d]; hi[d] = o.domain.hi[d] + (d == centering ? 1 : 0); n *= hi[d] - lo[d] + 1; }
+    if (n > capacity) SB_FAIL("capacity too small");
+    copy3d(o, centering, dev, host, lo, hi, false);
+    o.ctx->sync();
+    SB_END
+}
+
+// ---- fields ---------------------------------------------------------------------------------
+int sb_field_create(sb_op* op, int centering, sb_field** f)
+{
+    SB_TRY REQ(op); REQ(f);
+    if (centering < -1 || centering > 2) SB_FAIL("bad centering");
+    *f = new sb_field(op->op, centering);
+    SB_END
+}
+int sb_field_destroy(sb_field* f) { SB_TRY delete f; SB_END }
+int sb_field_upload(sb_field* f, const double* host, const int lo[3], const int hi[3])
+{
+    SB_TRY REQ(f); REQ(host);
+    copy3d(*f->f.op, f->f.centering, f->f.d, const_cast<double*>(host), lo, hi, true);
+    f->f.op->ctx->sync();
+    SB_END
+}
+int sb_field_download(sb_field* f, double* host, const int lo[3], const int hi[3])
+{
+    SB_TRY REQ(f); REQ(host);
+    copy3d(*f->f.op, f->f.centering, f->f.d, host, lo, hi, false);
+    f->f.op->ctx->sync();
+    SB_END
+}
+
+// ---- operator methods ------------------------------------------------------------------------
+#define OPF(o) (*(o)->op)
+#define D(fld_) ((fld_)->f.d)
+static void sameOp(sb_op* op, std::initializer_list<sb_field*> fs)
+{
+    if (!op) SB_FAIL("null op");
+    if (!op->op->finalized) SB_FAIL("sb_op_finalize has not been called");
+    for (sb_field* f : fs) {
+        if (!f) SB_FAIL("null field");
+        if (f->f.op != op->op) SB_FAIL("field belongs to another operator / MG depth");
+    }
+}
+int sb_op_apply_bcs(sb_op* op, sb_field* phi, int homog) { SB_TRY sameOp(op, {phi}); OPF(op).applyBCs(D(phi), homog); SB_END }
+int sb_op_apply_op(sb_op* op, sb_field* lhs, sb_field* phi, int homog)
+{
+    SB_TRY sameOp(op, {lhs, phi}); OPF(op).applyOp(D(lhs), D(phi), homog); SB_END
+}
+int sb_op_residual(sb_op* op, sb_field* res, sb_field* phi, sb_field* rhs, int homog)
+{
+    SB_TRY sameOp(op, {res, phi, rhs}); OPF(op).residual(D(res), D(phi), D(rhs), homog); SB_END
+}
+int sb_op_relax(sb_op* op, sb_field* cor, sb_field* res, int iters)
+{
+    SB_TRY sameOp(op, {cor, res}); OPF(op).relax(D(cor), D(res), iters);
+    if (OPF(op).relaxMethod == SB_RELAX_VERTLINE) OPF(op).checkPivot();
+    SB_END
+}
+int sb_op_precond(sb_op* op, sb_field* phi, sb_field* rhs, int it) { SB_TRY sameOp(op, {phi, rhs}); OPF(op).preCond(D(phi), D(rhs), it); SB_END }
+int sb_op_remove_kernel(sb_op* op, sb_field* phi) { SB_TRY sameOp(op, {phi}); OPF(op).removeKernel(D(phi)); SB_END }
+int sb_op_norm(sb_op* op, sb_field* x, int p, double pow_scale, double* out)
+{
+    SB_TRY sameOp(op, {x}); REQ(out); *out = OPF(op).norm(D(x), p, pow_scale); SB_END
+}
+int sb_op_dot(sb_op* op, sb_field* a, sb_field* b, double* out) { SB_TRY sameOp(op, {a, b}); REQ(out); *out = OPF(op).dotProduct(D(a), D(b)); SB_END }
+int sb_op_incr(sb_op* op, sb_field* lhs, sb_field* x, double s) { SB_TRY sameOp(op, {lhs, x}); OPF(op).incr(D(lhs), D(x), s); SB_END }
+int sb_op_axby(sb_op* op, sb_field* lhs, sb_field* x, sb_field* y, double a, double b)
+{
+    SB_TRY sameOp(op, {lhs, x, y}); OPF(op).axby(D(lhs), D(x), D(y), a, b); SB_END
+}
+int sb_op_scale(sb_op* op, sb_field* lhs, double s) { SB_TRY sameOp(op, {lhs}); OPF(op).scale(D(lhs), s); SB_END }
+int sb_op_set_to_zero(sb_op* op, sb_field* lhs) { SB_TRY sameOp(op, {lhs}); OPF(op).setToZero(D(lhs)); SB_END }
+int sb_op_assign_local(sb_op* op, sb_field* dst, sb_field* src) { SB_TRY sameOp(op, {dst, src}); OPF(op).assignLocal(D(dst), D(src)); SB_END }
+int sb_op_mg_restrict(sb_op* fine, sb_op* crse, sb_field* crse_res, sb_field* fine_res)
+{
+    SB_TRY sameOp(fine, {fine_res}); sameOp(crse, {crse_res});
+    OPF(fine).MGRestrict(OPF(crse), D(crse_res), D(fine_res));
+    SB_END
+}
+int sb_op_mg_prolong(sb_op* fine, sb_op* crse, sb_field* fine_phi, sb_field* crse_cor, int order)
+{
+    SB_TRY sameOp(fine, {fine_phi}); sameOp(crse, {crse_cor});
+    OPF(fine).MGProlong(OPF(crse), D(fine_phi), D(crse_cor), order);
+    SB_END
+}
+static void fluxPtrs(sb_op* op, sb_field* const f[3], double* out[3])
+{
+    for (int d = 0; d < 3; ++d) {
+        out[d] = nullptr;
+        if (op->op->dim == 2 && d == 1) { if (f[d]) out[d] = D(f[d]); continue; }
+        if (!f[d]) SB_FAIL("null flux component");
+        if (f[d]->f.op != op->op) SB_FAIL("field belongs to another operator");
+        if (f[d]->f.centering != d) SB_FAIL("flux component has the wrong centering");
+        out[d] = D(f[d]);
+    }
+}
+int sb_op_level_divergence(sb_op* op, sb_field* div, sb_field* const vel[3])
+{
+    SB_TRY sameOp(op, {div});
+    double* v[3]; fluxPtrs(op, vel, v);
+    OPF(op).levelDivergence(D(div), v);
+    SB_END
+}
+int sb_op_level_gradient(sb_op* op, sb_field* const grad[3], sb_field* phi, int homog)
+{
+    SB_TRY sameOp(op, {phi});
+    double* g[3]; fluxPtrs(op, grad, g);
+    OPF(op).levelGradient(g, D(phi), homog);
+    SB_END
+}
+int sb_op_flux_incr(sb_op* op, sb_field* const vel[3], sb_field* const grad[3], double scale)
+{
+    SB_TRY sameOp(op, {});
+    double *v[3], *g[3]; fluxPtrs(op, vel, v); fluxPtrs(op, grad, g);
+    for (int d = 0; d < 3; ++d) {
+        if (op->op->dim == 2 && d == 1) continue;
+        k::incr_valid(op->op->st(), op->op->lay, v[d], g[d], -scale, d);  // FArrayBox::plus(grad, -scale)
+    }
+    SB_END
+}
+
+// ---- solvers ---------------------------------------------------------------------------------
+int sb_mgsolver_create(sb_op* top, const sb_mg_options* opt, const int* schedule, int num_sched, sb_solver** s)
+{
+    SB_TRY sameOp(top, {}); REQ(opt); REQ(s);
+    std::vector<std::array<int, 3>> sched;
+    for (int i = 0; i < num_sched; ++i) sched.push_back({schedule[3 * i], schedule[3 * i + 1], schedule[3 * i + 2]});
+    std::unique_ptr<sb_solver> p(new sb_solver);
+    p->s.isHybrid = false;
+    p->s.op       = top->op;
+    p->s.opt      = *opt;
+    p->s.mode     = SB_MODE_MG;
+    p->s.mg.define(*top->op, *opt, sched, true);
+    top->op->ctx->sync();
+    *s = p.release();
+    SB_END
+}
+int sb_hybrid_solver_create(sb_op* top, const sb_mg_options* opt, sb_solver** s)
+{
+    SB_TRY sameOp(top, {}); REQ(opt); REQ(s);
+    std::unique_ptr<sb_solver> p(new sb_solver);
+    p->s.isHybrid = true;
+    p->s.define(*top->op, *opt);
+    top->op->ctx->sync();
+    *s = p.release();
+    SB_END
+}
+int sb_solver_destroy(sb_solver* s) { SB_TRY delete s; SB_END }
+int sb_solver_get_schedule(sb_solver* s, int* schedule, int capacity, int* num_sched)
+{
+    SB_TRY REQ(s); REQ(num_sched);
+    const auto& sc = s->s.mg.refSchedule;
+    *num_sched     = (int)sc.size();
+    if (schedule) {
+        if (capacity < (int)sc.size()) SB_FAIL("capacity too small");
+        for (size_t i = 0; i < sc.size(); ++i)
+            for (int d = 0; d < 3; ++d) schedule[3 * i + d] = sc[i][d];
+    }
+    SB_END
+}
+int sb_solver_set_options(sb_solver* s, const sb_mg_options* opt)
+{
+    SB_TRY REQ(s); REQ(opt);
+    s->s.mg.modifyOptionsExceptMaxDepth(*opt);
+    const int md = s->s.opt.maxDepth;
+    s->s.opt = *opt; s->s.opt.maxDepth = md;
+    SB_END
+}
+static void fillStatus(sb_solver* s, const SolverStatus& st, sb_solver_status* out, float ms)
+{
+    if (!out) return;
+    std::memset(out, 0, sizeof(*out));
+    out->status         = st.status;
+    out->num_iters      = s->s.mg.lastIters;
+    out->init_res_norm  = st.initResNorm;
+    out->final_res_norm = st.finalResNorm;
+    const auto& h       = s->s.mg.absResNorms;
+    out->num_norms      = (int)std::min<size_t>(h.size(), SB_MAX_HISTORY);
+    for (int i = 0; i < out->num_norms; ++i) out->res_norms[i] = h[i];
+    out->solve_mode = s->s.mode;
+    out->max_depth  = s->s.mg.opt.maxDepth;
+    out->device_ms  = ms;
+}
+int sb_solver_solve(sb_solver* s, sb_field* phi, sb_field* rhs, int homog, int set_phi_to_zero, double metric,
+                    sb_solver_status* status)
+{
+    SB_TRY REQ(s); REQ(phi); REQ(rhs);
+    Op& o = *s->s.op;
+    if (phi->f.op != &o || rhs->f.op != &o) SB_FAIL("fields do not live on the solver's top operator");
+    cudaEvent_t e0, e1;
+    SB_CUDA(cudaEventCreate(&e0)); SB_CUDA(cudaEventCreate(&e1));
+    SB_CUDA(cudaEventRecord(e0, o.st()));
+    SolverStatus st = s->s.solve(D(phi), D(rhs), homog, set_phi_to_zero, metric);
+    SB_CUDA(cudaEventRecord(e1, o.st()));
+    o.ctx->sync();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    fillStatus(s, st, status, ms);
+    SB_END
+}
+int sb_solver_vcycle(sb_solver* s, sb_field* cor, sb_field* res)
+{
+    SB_TRY REQ(s); REQ(cor); REQ(res);
+    Op& o = *s->s.op;
+    if (cor->f.op != &o || res->f.op != &o) SB_FAIL("fields do not live on the solver's top operator");
+    s->s.mg.vCycle_residualEq(D(cor), D(res), 0);
+    SB_END
+}
+
+// AMRNSLevel::projectCorrect, single level (Grade5_SOMAR/AMRNSLevelProject.cpp:247-373).
+int sb_project_host(sb_solver* s, double* const vel[3], double* phi, double* p, double proj_dt, double* init_div_norm,
+                    double* final_div_norm, sb_solver_status* status)
+{
+    SB_TRY REQ(s); REQ(vel);
+    Op& o = *s->s.op;
+    if (o.ctx->nranks != 1) SB_FAIL("sb_project_host takes whole-domain host arrays: single rank only (use the field API per rank)");
+    struct Tmp {
+        std::vector<double*> v;
+        ~Tmp() { for (double* q : v) cudaFree(q); }
+        double* get(Op& o) { v.push_back(o.alloc()); return v.back(); }
+    } tmp;
+    double *U[3] = {nullptr, nullptr, nullptr}, *G[3] = {nullptr, nullptr, nullptr};
+    int     lo[3], hi[3];
+    for (int d = 0; d < 3; ++d) {
+        if (o.dim == 2 && d == 1) continue;
+        REQ(vel[d]);
+        U[d] = tmp.get(o); G[d] = tmp.get(o);
+        for (int e = 0; e < 3; ++e) { lo[e] = o.domain.lo[e]; hi[e] = o.domain.hi[e] + (e == d ? 1 : 0); }
+        copy3d(o, d, U[d], vel[d], lo, hi, true);
+    }
+    double* div = tmp.get(o);
+    double* ph  = tmp.get(o);
+    cudaEvent_t e0, e1;
+    SB_CUDA(cudaEventCreate(&e0)); SB_CUDA(cudaEventCreate(&e1));
+    o.levelDivergence(div, U);                                   // :293
+    const double n0 = o.norm(div, s->s.opt.normType);            // :297
+    if (init_div_norm) *init_div_norm = n0;
+    SB_CUDA(cudaEventRecord(e0, o.st()));
+    SolverStatus st = s->s.solve(ph, div, true, true, -1.0);     // :316
+    SB_CUDA(cudaEventRecord(e1, o.st()));
+    o.levelGradient(G, ph, true);                                // :328
+    for (int d = 0; d < 3; ++d)
+        if (U[d]) k::incr_valid(o.st(), o.lay, U[d], G[d], -1.0, d);  // :331-336
+    if (final_div_norm) {                                        // :354-357
+        o.levelDivergence(div, U);
+        *final_div_norm = o.norm(div, s->s.opt.normType);
+    }
+    for (int d = 0; d < 3; ++d) {
+        if (!U[d]) continue;
+        for (int e = 0; e < 3; ++e) { lo[e] = o.domain.lo[e]; hi[e] = o.domain.hi[e] + (e == d ? 1 : 0); }
+        copy3d(o, d, U[d], vel[d], lo, hi, false);
+    }
+    for (int e = 0; e < 3; ++e) { lo[e] = o.domain.lo[e]; hi[e] = o.domain.hi[e]; }
+    if (phi) copy3d(o, -1, ph, phi, lo, hi, false);
+    o.ctx->sync();
+    if (p && phi) {                                              // :340-349  p += phi / projDt
+        const long long n = o.domain.numPts();
+        const double    s1 = 1.0 / proj_dt;
+        for (long long i = 0; i < n; ++i) p[i] = p[i] + s1 * phi[i];
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    fillStatus(s, st, status, ms);
+    SB_END
+}
+
+}  // extern "C"

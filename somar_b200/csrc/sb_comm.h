@@ -1,0 +1,21 @@
+// sb_comm.h -- NCCL plumbing for the horizontal box decomposition: face-ghost exchange between
+// neighbouring tiles and scalar all-reduces.  Stands in for Chombo's MPI layer
+// (BoxTools/BoxLayoutDataI.H:665-812 exchange, BaseTools/Comm.cpp:14-50 reduce).
+// NCCL is bound at run time with dlopen so the library has no link-time dependency on it.
+#pragma once
+#include "sb_host.h"
+
+namespace sb {
+
+struct Comm {
+    Context* ctx;
+    void*    comm = nullptr;   // ncclComm_t
+    double*  dscal = nullptr;  // device staging for scalar reductions
+    Comm(Context* ctx, const void* id128);
+    ~Comm();
+    static void getUniqueId(void* id128);
+    void allreduceHost(double* v, int n, bool isMax);
+    void exchangeFaces(Op& op, double* phi);
+};
+
+}  // namespace sb

@@ -1,0 +1,167 @@
+// sb_core.h -- internal types shared by the host driver (sb_op.cpp, sb_mg.cpp, sb_capi.cpp)
+// and the CUDA kernels (sb_kernels.cu).  Nothing here crosses the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/somar_b200.h"
+
+namespace sb {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+#define SB_FAIL(msg) throw ::sb::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg))
+#define SB_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) SB_FAIL(std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+struct Box3 {
+    int lo[3], hi[3];
+    int size(int d) const { return hi[d] - lo[d] + 1; }
+    long long numPts() const { return (long long)size(0) * size(1) * size(2); }
+    bool operator==(const Box3& o) const
+    {
+        for (int d = 0; d < 3; ++d)
+            if (lo[d] != o.lo[d] || hi[d] != o.hi[d]) return false;
+        return true;
+    }
+};
+
+// floor division (Chombo's coarsen for negative indices, BoxTools/IntVect.H coarsen)
+inline int fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+inline Box3 coarsen(const Box3& b, const int r[3])
+{
+    Box3 c;
+    for (int d = 0; d < 3; ++d) { c.lo[d] = fdiv(b.lo[d], r[d]); c.hi[d] = fdiv(b.hi[d], r[d]); }
+    return c;
+}
+inline Box3 refine(const Box3& b, const int r[3])
+{
+    Box3 c;
+    for (int d = 0; d < 3; ++d) { c.lo[d] = b.lo[d] * r[d]; c.hi[d] = (b.hi[d] + 1) * r[d] - 1; }
+    return c;
+}
+inline bool coarsenable(const Box3& b, const int r[3]) { return refine(coarsen(b, r), r) == b; }
+
+// Data layout of every field of one rank at one MG depth ("fused tile"): the union of the
+// rank's boxes is one rectangle [tile.lo, tile.hi]; a field is a pitched 3-D array with one
+// ghost layer in y and z, OX pad cells (>= 1 ghost) left of x and >= 1 right.  The same shape
+// serves cell- and face-centred data (a face array needs n+1 entries in its own direction).
+constexpr int OX = 4;  // first valid x sits on a 32-byte sector boundary
+struct Lay {
+    int nx, ny, nz;     // valid cells of the tile
+    int lo0, lo1, lo2;  // global index of the first valid cell
+    int px, py, pz;     // allocated extents
+    long long sy, sz;   // strides (elements)
+    long long n;        // total elements
+    __host__ __device__ long long idx(int i, int j, int k) const  // local indices, ghosts = -1 / n
+    {
+        return (long long)(OX + i) + sy * (long long)(1 + j) + sz * (long long)(1 + k);
+    }
+};
+inline Lay makeLay(const Box3& tile)
+{
+    Lay L;
+    L.nx = tile.size(0); L.ny = tile.size(1); L.nz = tile.size(2);
+    L.lo0 = tile.lo[0]; L.lo1 = tile.lo[1]; L.lo2 = tile.lo[2];
+    L.px = ((L.nx + 8 + 3) / 4) * 4;
+    L.py = L.ny + 2;
+    L.pz = L.nz + 2;
+    L.sy = L.px;
+    L.sz = (long long)L.px * L.py;
+    L.n  = L.sz * L.pz;
+    return L;
+}
+
+// What a side of the tile touches.
+enum SideKind { SIDE_PHYS = 0, SIDE_PERIODIC_SELF = 1, SIDE_NEIGHBOR = 2 };
+
+// Robin ghost fill constants of one side (BCToolsF.ChF:222-337): a = alpha/8 (2 cells) or
+// alpha/2 (1 cell), bb = beta/dx.
+struct SideBC {
+    int    kind;       // SideKind
+    int    twoCells;   // numValidCells >= 2 (BCTools.cpp:381)
+    double a, bb;      // as above
+    int    neighbor;   // rank (SIDE_NEIGHBOR)
+};
+
+// Per-depth coefficient pointers handed to kernels.
+struct Coef {
+    const double* J;
+    const double* Dinv;
+    const double* mxl; const double* mxr;  // [nx] lower / upper off-diagonals, tile-local index
+    const double* myl; const double* myr;  // [ny]
+    const double* mzl; const double* mzr;  // [nz]
+    const double* loBC; const double* hiBC;  // [py*px] slabs (index = OX+i + sy*(1+j))
+    double beta;
+};
+
+struct BoxList {  // boxes of this rank in tile-local coordinates, on the device
+    int  n;
+    int* lo;  // [n][3]
+    int* hi;  // [n][3]
+};
+
+// ---- kernel launchers (sb_kernels.cu).  All asynchronous on `st`. -------------------------
+namespace k {
+void fill(cudaStream_t st, double* a, long long n, double v);
+void copy_valid(cudaStream_t st, const Lay& L, double* dst, const double* src);
+void scale_valid(cudaStream_t st, const Lay& L, double* a, double s, int faceDir);
+void incr_valid(cudaStream_t st, const Lay& L, double* y, const double* x, double s, int faceDir);
+void axby_valid(cudaStream_t st, const Lay& L, double* z, const double* x, const double* y, double a, double b);
+void add_scalar_valid(cudaStream_t st, const Lay& L, double* a, const double* sumvol /* dev: sum, vol */);
+void mult_valid(cudaStream_t st, const Lay& L, double* dst, const double* src, const double* m);  // dst = src*m
+
+// ghost fill of the six tile sides (physical Robin BC or periodic self-copy)
+void fill_ghosts(cudaStream_t st, const Lay& L, double* phi, const SideBC bc[3][2], int dim);
+// faces, then edges (needed only by the quadratic prolongation's mixed differences)
+void fill_ghosts_with_edges(cudaStream_t st, const Lay& L, double* phi, const SideBC bc[3][2], int dim);
+long long launch_count();
+// pack / unpack of one side's face layer for neighbour exchange
+void pack_face(cudaStream_t st, const Lay& L, const double* phi, int dir, int side, double* buf);
+void unpack_face(cudaStream_t st, const Lay& L, double* phi, int dir, int side, const double* buf);
+
+void apply_op(cudaStream_t st, const Lay& L, const Coef& c, double* lhs, const double* phi);
+void residual(cudaStream_t st, const Lay& L, const Coef& c, double* res, const double* phi, const double* rhs);
+void gsrb_pass(cudaStream_t st, const Lay& L, const Coef& c, double* phi, const double* rhs, int pass);
+void jacobi(cudaStream_t st, const Lay& L, const Coef& c, double* phi, const double* res, int pass /* -1 all */);
+// one colour of vertical line relaxation; wd/wb are scratch of nz*ny*((nx+1)/2) doubles;
+// *pivotFlag is set to 1 if LAPACK dgtsv would have interchanged rows.
+void vertline_pass(cudaStream_t st, const Lay& L, const Coef& c, double* phi, const double* rhs, int pass,
+                   double* wd, double* wb, int* pivotFlag);
+
+void restrict_avg(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* crse, const double* fine);
+void prolong_const(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse);
+void prolong_linear(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse);
+void prolong_quad1(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse);
+void prolong_quad2(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse, int dim);
+void restrict_face(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], int dir, double* crse, const double* fine);
+
+void compute_dinv(cudaStream_t st, const Lay& L, const Coef& c, double alpha, double* Dinv, int dim);
+void compute_vert_bcs(cudaStream_t st, const Lay& L, const Coef& c, double sLo, double sHi, double* loBC, double* hiBC);
+// J / Jgup from per-box 1-D dx/dXi tables (cell tables c*, node tables f*), box in tile-local indices
+void fill_metric_box(cudaStream_t st, const Lay& L, const int blo[3], const int bhi[3], const double* cx, const double* cy,
+                     const double* cz, const double* fx, const double* fy, const double* fz, double* J, double* Jg0,
+                     double* Jg1, double* Jg2);
+
+void divergence(cudaStream_t st, const Lay& L, double* div, const double* u0, const double* u1, const double* u2,
+                double dxinv0, double dxinv1, double dxinv2, int dim);
+void gradient(cudaStream_t st, const Lay& L, double* g, const double* phi, const double* Jgup, int dir, double oneOnDx,
+              double beta, int scaleBeta);
+
+// Reductions.  op: 0 max|x|, 1 sum|x|, 2 sum x^2, 3 sum x*y, 4 sum (J*dv)*x and sum J*dv (2 outputs).
+// One result per box (or 2 for op 4) lands in out[] (device); partial is scratch.
+void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, const double* x, const double* y,
+                  double dv, double* partial, double* out);
+int  reduce_partial_len(int nboxes);
+}  // namespace k
+
+}  // namespace sb

@@ -1,0 +1,197 @@
+// sb_host.h -- host-side mirror of the reference's operator / solver classes for the
+// projection path.  Names follow the reference (PoissonOp, MGSolver, BiCGStabSolver,
+// LevelHybridSolver); each method cites the code it mirrors.
+#pragma once
+#include <array>
+#include <map>
+
+#include "sb_core.h"
+
+namespace sb {
+
+struct Comm;  // NCCL wrapper (sb_comm.cpp)
+
+struct Context {
+    int          device = 0, rank = 0, nranks = 1;
+    cudaStream_t st     = nullptr;
+    double*      hpin   = nullptr;  // pinned host scratch (scalars coming back from reductions)
+    size_t       hpinLen = 0;
+    void*        scratch = nullptr;  // device scratch shared by all depths (line-relax workspace)
+    size_t       scratchBytes = 0;
+    Comm*        comm = nullptr;
+    long long    launches0 = 0;
+
+    Context(int dev, int rank, int nranks);
+    ~Context();
+    void* getScratch(size_t bytes);
+    void  sync() { SB_CUDA(cudaStreamSynchronize(st)); }
+    // Comm::reduce (BaseTools/Comm.cpp:14-50)
+    void allreduceSum(double* v, int n);
+    void allreduceMax(double* v, int n);
+};
+
+struct MapSpec {
+    int       kind = SB_MAP_CARTESIAN;
+    double    xmin[3] = {0, 0, 0}, xmax[3] = {1, 1, 1}, ampl[3] = {0, 0, 0};
+    sb_map_fn fn = nullptr;
+    void*     user = nullptr;
+    // GeoSourceInterface::interp
+    void interp(std::vector<double>& x, const std::vector<double>& xi, int mu) const;
+    // GeoSourceInterface::fill_physCoor(Vector<Real>&, mu, dXi, box): n points starting at index
+    // lo, cell- (type 0) or node-centred (type 1), xi accumulated by repeated addition.
+    std::vector<double> physCoor(int mu, double dXi, int lo, int n, int nodeType) const;
+    // fill_dxdXi over n points starting at lo of the given centring (GeoSourceInterface.cpp:166-199).
+    std::vector<double> dxdXi(int mu, double dXi, int lo, int n, int nodeType, double scale = 1.0) const;
+};
+
+struct Op;
+
+struct Field {
+    Op*     op;
+    int     centering;  // SB_CELL or face dir
+    double* d = nullptr;
+    Field(Op* op, int centering);
+    ~Field();
+    Field(const Field&) = delete;
+};
+
+// Elliptic::PoissonOp at one MG depth (Grade3_Calculus/Elliptic/PoissonOp.{H,cpp}).
+struct Op {
+    Context* ctx;
+    int      dim;
+    Box3     domain;
+    int      periodic[3];
+    double   dXi[3];
+    double   alpha, beta;
+    int      relaxMethod;
+    MapSpec  map;
+    double   bcAlpha[3][2], bcBeta[3][2];
+    int      depth = 0;
+
+    std::vector<Box3> boxes;    // all ranks
+    std::vector<int>  boxRank;
+    std::vector<int>  local;    // indices into boxes owned by this rank
+    std::vector<Box3> tiles;    // tile of every rank
+    Box3              tile;
+    Lay               lay;
+    SideBC            side[3][2];
+    bool              hasNullSpace = false;
+    bool              finalized    = false;
+
+    // device data
+    double* J = nullptr;
+    double* Dinv = nullptr;
+    double* Jgup[3] = {nullptr, nullptr, nullptr};
+    double* mtab = nullptr;  // mxl, mxr, myl, myr, mzl, mzr back to back
+    double* loBC = nullptr;
+    double* hiBC = nullptr;
+    int*    boxLoHi = nullptr;  // [2][nlocal][3]
+    double* redPartial = nullptr;
+    double* redOut = nullptr;
+    int*    pivotFlag = nullptr;
+    std::vector<double> hM[3];  // host copies of the 1-D tables over the whole domain (2*N_d)
+    double* xbuf[3][2][2] = {};  // exchange buffers [dir][side][send/recv]
+
+    Op(Context* ctx, const sb_level_desc& d);
+    Op(const Op& fine, const int ref[3]);  // coarsening ctor, PoissonOp.cpp:334-405
+    ~Op();
+    Op& operator=(const Op&) = delete;
+
+    void    setupLayout();
+    void    fillMetricFromMap();          // LevelGeometry::createMetricCache, LevelGeometry.cpp:238-277
+    void    cacheMatrixElements();        // PoissonOp.cpp:510-665
+    bool    checkForNullSpace();          // PoissonOp.cpp:670-696
+    void    finalize();                   // setAlphaAndBeta, PoissonOp.cpp:707-718
+    Coef    coef() const;
+    BoxList boxlist() const;
+    int     nlocal() const { return (int)local.size(); }
+    cudaStream_t st() const { return ctx->st; }
+
+    // LevelOperator / MGOperator / StateOps surface
+    void   applyBCs(double* phi, bool homog);
+    void   applyBCsWithEdges(double* phi);
+    void   exchange(double* phi);
+    void   applyOp(double* lhs, double* phi, bool homog);
+    void   residual(double* res, double* phi, const double* rhs, bool homog);
+    void   relax(double* cor, const double* res, int iters);
+    void   preCond(double* phi, const double* rhs, int relaxIters);
+    void   removeKernel(double* phi);
+    double norm(const double* x, int p, double powScale = 1.0);
+    double dotProduct(const double* a, const double* b);
+    void   incr(double* lhs, const double* x, double scale) { k::incr_valid(st(), lay, lhs, x, scale, -1); }
+    void   axby(double* lhs, const double* x, const double* y, double a, double b) { k::axby_valid(st(), lay, lhs, x, y, a, b); }
+    void   scale(double* lhs, double s) { k::scale_valid(st(), lay, lhs, s, -1); }
+    void   setToZero(double* lhs) { k::fill(st(), lhs, lay.n, 0.0); }
+    void   assignLocal(double* dst, const double* src) { k::copy_valid(st(), lay, dst, src); }
+    void   MGRestrict(Op& crse, double* crseRes, const double* fineRes);
+    void   MGProlong(Op& crse, double* finePhi, double* crseCor, int order);
+    void   levelDivergence(double* div, double* const vel[3]);
+    void   levelGradient(double* const grad[3], double* phi, bool homog);
+    void   checkPivot();
+    double* alloc() const;
+};
+
+// SemicoarseningStrategy / HorizCoarseningStrategy (Elliptic/MGCoarseningStrategy.cpp)
+std::vector<std::array<int, 3>> createMGRefSchedule(const Op& top, int maxDepth, bool horizStrategy, bool doVertCoarsening);
+
+struct SolverStatus {
+    int    status = SB_STATUS_UNDEFINED;
+    double initResNorm = -1.0, finalResNorm = -1.0;
+    void clear() { status = SB_STATUS_UNDEFINED; initResNorm = finalResNorm = -1.0; }
+};
+
+// Elliptic::BiCGStabSolver<T> (Elliptic/LevelSolverI.H:252-536)
+struct BiCGStabSolver {
+    Op*               op = nullptr;
+    sb_bottom_options opt;
+    double *r = nullptr, *r_tilde = nullptr, *e = nullptr, *p = nullptr, *p_tilde = nullptr, *s_tilde = nullptr, *t = nullptr,
+           *v = nullptr;
+    int    lastIters = 0;
+    void   define(Op* op);
+    ~BiCGStabSolver();
+    SolverStatus solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double convergenceMetric = -1.0);
+};
+
+// Elliptic::MGSolver<T> (Elliptic/MGSolverI.H)
+struct MGSolver {
+    sb_mg_options                    opt;
+    std::vector<std::array<int, 3>>  refSchedule;
+    std::vector<Op*>                 ops;        // ops[0] is the caller's top op
+    std::vector<std::unique_ptr<Op>> owned;      // depths >= 1
+    std::vector<double*>             tmpRes, cor, res;  // per-depth workspace (cor/res of depth d >= 1 are crseCor/crseRes)
+    double *                         topRes = nullptr, *topCor = nullptr;
+    std::unique_ptr<BiCGStabSolver>  bottom;
+    SolverStatus                     status;
+    std::vector<double>              absResNorms;  // history of the last solve
+    int                              lastIters = 0;
+
+    void define(Op& top, const sb_mg_options& opt, std::vector<std::array<int, 3>> sched, bool useBottomSolver = true);
+    ~MGSolver();
+    SolverStatus solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double convergenceMetric = -1.0);
+    SolverStatus cycle(bool fmgMode, double* phi, const double* rhs, bool homog, bool setPhiToZero, double convergenceMetric);
+    void vCycle_residualEq(double* cor, const double* res, int depth);
+    void fmg_residualEq(double* cor, const double* res, int depth);
+    void modifyOptionsExceptMaxDepth(const sb_mg_options& o);
+};
+
+// Elliptic::LevelHybridSolver (Elliptic/LevelHybridSolver.cpp); only SolveMode::MG is built.
+struct HybridSolver {
+    Op*                 op = nullptr;
+    int                 mode = 0;
+    bool                isHybrid = false;  // false: plain MGSolver behind the same handle
+    MGSolver            mg;
+    double *            cor = nullptr, *res = nullptr;
+    std::vector<double> resNorms;
+    sb_mg_options       opt;
+    static int computeSolveMode(const Op& op);  // LevelHybridSolver.cpp:457-498
+    void define(Op& top, const sb_mg_options& o);
+    ~HybridSolver();
+    SolverStatus solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double convergenceMetric);
+};
+
+}  // namespace sb
+
+struct sb_context { sb::Context c; sb_context(int d, int r, int n) : c(d, r, n) {} };
+struct sb_op { sb::Op* op; bool owned; };
+struct sb_field { sb::Field f; sb_field(sb::Op* op, int c) : f(op, c) {} };
+struct sb_solver { sb::HybridSolver s; };

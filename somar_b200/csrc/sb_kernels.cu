@@ -1,0 +1,710 @@
+// sb_kernels.cu -- hand-written fp64 CUDA kernels (sm_100a) for SOMAR's pressure projection.
+//
+// Compiled with -fmad=false: every kernel evaluates its expression in the association order of
+// the reference's Chombo-Fortran leaf (cited per kernel, path:line relative to
+// /root/reference/src/Grade3_Calculus), so element-wise results agree with the CPU code to the
+// last bit and only reductions differ (summation order).
+//
+// Layout: see sb_core.h (Lay).  x is contiguous; threadIdx.x always runs along x.
+#include "sb_core.h"
+
+namespace sb {
+namespace k {
+
+static long long g_launches = 0;
+long long launch_count() { return g_launches; }
+#define LAUNCHED() (++g_launches)
+
+static inline dim3 grid3(int nx, int ny, int nz, dim3 b)
+{
+    return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y, (nz + b.z - 1) / b.z);
+}
+static const dim3 B3(64, 4, 1);
+
+// ------------------------------------------------------------------------------------------
+// BLAS-1 over valid cells (Elliptic/StateOps/LDFABOps.cpp:170-250, BoxTools/FArrayBox.cpp).
+// faceDir >= 0 extends the range by one in that direction (face-centred data).
+// ------------------------------------------------------------------------------------------
+__global__ void fill_k(double* a, long long n, double v)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long s = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += s) a[i] = v;
+}
+void fill(cudaStream_t st, double* a, long long n, double v)
+{
+    if (v == 0.0) {
+        cudaMemsetAsync(a, 0, n * sizeof(double), st);
+    } else {
+        fill_k<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 32), 256, 0, st>>>(a, n, v);
+    }
+    LAUNCHED();
+}
+
+template <class F>
+__global__ void valid_k(Lay L, int ex, int ey, int ez, F f)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.nx + ex || j >= L.ny + ey || k >= L.nz + ez) return;
+    f(L.idx(i, j, k), i, j, k);
+}
+template <class F>
+static void launch_valid(cudaStream_t st, const Lay& L, int faceDir, F f)
+{
+    const int ex = faceDir == 0, ey = faceDir == 1, ez = faceDir == 2;
+    valid_k<<<grid3(L.nx + ex, L.ny + ey, L.nz + ez, B3), B3, 0, st>>>(L, ex, ey, ez, f);
+    LAUNCHED();
+}
+
+void copy_valid(cudaStream_t st, const Lay& L, double* dst, const double* src)
+{
+    launch_valid(st, L, -1, [=] __device__(long long c, int, int, int) { dst[c] = src[c]; });
+}
+void scale_valid(cudaStream_t st, const Lay& L, double* a, double s, int faceDir)
+{
+    launch_valid(st, L, faceDir, [=] __device__(long long c, int, int, int) { a[c] = a[c] * s; });
+}
+// FArrayBox::plus(x, scale): this += scale * x
+void incr_valid(cudaStream_t st, const Lay& L, double* y, const double* x, double s, int faceDir)
+{
+    launch_valid(st, L, faceDir, [=] __device__(long long c, int, int, int) { y[c] = y[c] + s * x[c]; });
+}
+// Grade1_Basics/FABAlgebraF.ChF:145-165
+void axby_valid(cudaStream_t st, const Lay& L, double* z, const double* x, const double* y, double a, double b)
+{
+    launch_valid(st, L, -1, [=] __device__(long long c, int, int, int) { z[c] = a * x[c] + b * y[c]; });
+}
+// PoissonOp::removeKernel (Elliptic/PoissonOp.cpp:838-842): phi -= sum/vol
+void add_scalar_valid(cudaStream_t st, const Lay& L, double* a, const double* sumvol)
+{
+    launch_valid(st, L, -1, [=] __device__(long long c, int, int, int) {
+        const double avg = sumvol[0] / sumvol[1];
+        a[c]             = a[c] - avg;
+    });
+}
+void mult_valid(cudaStream_t st, const Lay& L, double* dst, const double* src, const double* m)
+{
+    launch_valid(st, L, -1, [=] __device__(long long c, int, int, int) { dst[c] = src[c] * m[c]; });
+}
+
+// ------------------------------------------------------------------------------------------
+// Ghost fill of one direction: physical Robin BC (BCToolsF.ChF:222-337, as driven by
+// BCTools.cpp:334-415) or periodic wrap inside the tile.  ext = 1 extends the tangential
+// range over the ghosts of the lower-numbered directions (used before the quadratic prolong,
+// where edge ghosts matter: PoissonOp.cpp:1115-1125).
+// ------------------------------------------------------------------------------------------
+__global__ void fill_ghosts_dir_k(Lay L, double* phi, int dir, SideBC lo, SideBC hi, int ext0, int ext1)
+{
+    // (a, b) run over the two tangential directions in ascending order.
+    int       na, nb;
+    long long sa, sb, sn;
+    int       nn;
+    if (dir == 0) { na = L.ny; nb = L.nz; sa = L.sy; sb = L.sz; sn = 1; nn = L.nx; }
+    else if (dir == 1) { na = L.nx; nb = L.nz; sa = 1; sb = L.sz; sn = L.sy; nn = L.ny; }
+    else { na = L.nx; nb = L.ny; sa = 1; sb = L.sy; sn = L.sz; nn = L.nz; }
+    const int a = blockIdx.x * blockDim.x + threadIdx.x - ext0;
+    const int b = blockIdx.y * blockDim.y + threadIdx.y - ext1;
+    if (a >= na + ext0 || b >= nb + ext1) return;
+    const long long base = L.idx(0, 0, 0) + sa * a + sb * b;  // cell 0 along dir
+    for (int side = 0; side < 2; ++side) {
+        const SideBC&   bc = side ? hi : lo;
+        const long long g  = side ? base + sn * nn : base - sn;             // ghost
+        const long long p0 = side ? base + sn * (nn - 1) : base;            // first interior
+        const long long p1 = side ? base + sn * (nn - 2) : base + sn;       // second interior
+        if (bc.kind == SIDE_PHYS) {
+            if (bc.twoCells) {
+                // BCToolsF.ChF:313-331 (homogeneous branch)
+                const double cg = 3.0 * bc.a + bc.bb;
+                const double c0 = 6.0 * bc.a - bc.bb;
+                const double c1 = -1.0 * bc.a;
+                phi[g]          = -(c0 * phi[p0] + c1 * phi[p1]) / cg;
+            } else {
+                // BCToolsF.ChF:255-270
+                const double cg = bc.a + bc.bb;
+                const double c0 = bc.a - bc.bb;
+                phi[g]          = -(c0 * phi[p0]) / cg;
+            }
+        } else if (bc.kind == SIDE_PERIODIC_SELF) {
+            phi[g] = side ? phi[base] : phi[base + sn * (nn - 1)];
+        }
+    }
+}
+void fill_ghosts_dir(cudaStream_t st, const Lay& L, double* phi, int dir, const SideBC& lo, const SideBC& hi, int ext0,
+                     int ext1)
+{
+    if (lo.kind == SIDE_NEIGHBOR && hi.kind == SIDE_NEIGHBOR) return;
+    int na, nb;
+    if (dir == 0) { na = L.ny; nb = L.nz; }
+    else if (dir == 1) { na = L.nx; nb = L.nz; }
+    else { na = L.nx; nb = L.ny; }
+    dim3 b(dir == 0 ? 8 : 64, dir == 0 ? 16 : 2, 1);
+    fill_ghosts_dir_k<<<grid3(na + 2 * ext0, nb + 2 * ext1, 1, b), b, 0, st>>>(L, phi, dir, lo, hi, ext0, ext1);
+    LAUNCHED();
+}
+void fill_ghosts(cudaStream_t st, const Lay& L, double* phi, const SideBC bc[3][2], int dim)
+{
+    for (int d = 0; d < 3; ++d) {
+        if (dim == 2 && d == 1) continue;
+        fill_ghosts_dir(st, L, phi, d, bc[d][0], bc[d][1], 0, 0);
+    }
+}
+
+// Edge ghosts where two physical sides meet: BCTools::extrapCorners order 2
+// (BCTools.cpp:66-150 -> BCToolsF.ChF:123-196), applied to the domain-corner box; everywhere
+// else the reference's CornerCopier leaves the neighbouring box's face ghost there, which in
+// the fused tile is what the direction-by-direction fill already produced.
+__global__ void extrap_edge_k(Lay L, double* phi, int adir, int aside, int bdir, int bside)
+{
+    const int cdir = 3 - adir - bdir;
+    const int nc   = cdir == 0 ? L.nx : (cdir == 1 ? L.ny : L.nz);
+    const int t    = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nc) return;
+    const long long sd[3] = {1, L.sy, L.sz};
+    const int       nd[3] = {L.nx, L.ny, L.nz};
+    int             ijk[3];
+    ijk[cdir] = t;
+    ijk[adir] = aside ? nd[adir] : -1;
+    ijk[bdir] = bside ? nd[bdir] : -1;
+    const long long e  = L.idx(ijk[0], ijk[1], ijk[2]);
+    const long long ai = aside ? -sd[adir] : sd[adir];  // step inward along adir
+    const long long bi = bside ? -sd[bdir] : sd[bdir];
+    const double aval  = 3.0 * phi[e + ai] - 3.0 * phi[e + 2 * ai] + phi[e + 3 * ai];
+    const double bval  = 3.0 * phi[e + bi] - 3.0 * phi[e + 2 * bi] + phi[e + 3 * bi];
+    phi[e]             = 0.5 * (aval + bval);
+}
+// Fill every ghost a 9-point-per-plane stencil can touch (faces + edges).
+void fill_ghosts_with_edges(cudaStream_t st, const Lay& L, double* phi, const SideBC bc[3][2], int dim)
+{
+    fill_ghosts_dir(st, L, phi, 0, bc[0][0], bc[0][1], 0, 0);
+    if (dim == 3) fill_ghosts_dir(st, L, phi, 1, bc[1][0], bc[1][1], 1, 0);
+    fill_ghosts_dir(st, L, phi, 2, bc[2][0], bc[2][1], 1, dim == 3 ? 1 : 0);
+    for (int a = 0; a < 3; ++a)
+        for (int b = a + 1; b < 3; ++b) {
+            if (dim == 2 && (a == 1 || b == 1)) continue;
+            for (int as = 0; as < 2; ++as)
+                for (int bs = 0; bs < 2; ++bs) {
+                    if (bc[a][as].kind != SIDE_PHYS || bc[b][bs].kind != SIDE_PHYS) continue;
+                    const int c  = 3 - a - b;
+                    const int nc = c == 0 ? L.nx : (c == 1 ? L.ny : L.nz);
+                    extrap_edge_k<<<(nc + 127) / 128, 128, 0, st>>>(L, phi, a, as, b, bs);
+                    LAUNCHED();
+                }
+        }
+}
+
+// Pack / unpack one face layer (valid cells adjacent to the side -> buffer; buffer -> ghosts).
+// Stands in for Copier motion items of LevelData::exchange (BoxTools/BoxLayoutDataI.H:665-812).
+__global__ void pack_face_k(Lay L, const double* phi, int dir, int layer, double* buf, int unpack, double* phiw)
+{
+    int na, nb;
+    long long sa, sb, sn;
+    if (dir == 0) { na = L.ny; nb = L.nz; sa = L.sy; sb = L.sz; sn = 1; }
+    else if (dir == 1) { na = L.nx; nb = L.nz; sa = 1; sb = L.sz; sn = L.sy; }
+    else { na = L.nx; nb = L.ny; sa = 1; sb = L.sy; sn = L.sz; }
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y * blockDim.y + threadIdx.y;
+    if (a >= na || b >= nb) return;
+    const long long c = L.idx(0, 0, 0) + sa * a + sb * b + sn * layer;
+    if (unpack) phiw[c] = buf[a + (long long)na * b];
+    else buf[a + (long long)na * b] = phi[c];
+}
+void pack_face(cudaStream_t st, const Lay& L, const double* phi, int dir, int side, double* buf)
+{
+    int na, nb, nn;
+    if (dir == 0) { na = L.ny; nb = L.nz; nn = L.nx; }
+    else if (dir == 1) { na = L.nx; nb = L.nz; nn = L.ny; }
+    else { na = L.nx; nb = L.ny; nn = L.nz; }
+    dim3 b(dir == 0 ? 8 : 64, dir == 0 ? 16 : 2, 1);
+    pack_face_k<<<grid3(na, nb, 1, b), b, 0, st>>>(L, phi, dir, side ? nn - 1 : 0, buf, 0, nullptr);
+    LAUNCHED();
+}
+void unpack_face(cudaStream_t st, const Lay& L, double* phi, int dir, int side, const double* buf)
+{
+    int na, nb, nn;
+    if (dir == 0) { na = L.ny; nb = L.nz; nn = L.nx; }
+    else if (dir == 1) { na = L.nx; nb = L.nz; nn = L.ny; }
+    else { na = L.nx; nb = L.ny; nn = L.nz; }
+    dim3 b(dir == 0 ? 8 : 64, dir == 0 ? 16 : 2, 1);
+    pack_face_k<<<grid3(na, nb, 1, b), b, 0, st>>>(L, nullptr, dir, side ? nn : -1, const_cast<double*>(buf), 1, phi);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// Operator: lhs = beta*J*Sum_d(M_dL phi_- + M_dR phi_+) + phi/Dinv
+// (Elliptic/PoissonOpF.ChF:151-199), and the residual rhs - lhs (LevelOperator.H:104-117:
+// applyOp, scale(-1), incr(rhs, 1) -- (-lhs) + rhs is bit-identical to rhs - lhs).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double stencil7(const Lay& L, const Coef& c, const double* __restrict__ phi, long long q, int i,
+                                           int j, int k)
+{
+    double s = c.mxl[i] * phi[q - 1] + c.mxr[i] * phi[q + 1] + c.myl[j] * phi[q - L.sy] + c.myr[j] * phi[q + L.sy];
+    s        = s + c.mzl[k] * phi[q - L.sz] + c.mzr[k] * phi[q + L.sz];
+    return s;
+}
+__global__ void apply_op_k(Lay L, Coef c, double* __restrict__ out, const double* __restrict__ phi,
+                           const double* __restrict__ rhs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.nx || j >= L.ny) return;
+    const long long q   = L.idx(i, j, k);
+    const double    lap = stencil7(L, c, phi, q, i, j, k);
+    const double    lhs = c.beta * c.J[q] * lap + phi[q] / c.Dinv[q];
+    out[q]              = rhs ? rhs[q] - lhs : lhs;
+}
+void apply_op(cudaStream_t st, const Lay& L, const Coef& c, double* lhs, const double* phi)
+{
+    apply_op_k<<<grid3(L.nx, L.ny, L.nz, B3), B3, 0, st>>>(L, c, lhs, phi, nullptr);
+    LAUNCHED();
+}
+void residual(cudaStream_t st, const Lay& L, const Coef& c, double* res, const double* phi, const double* rhs)
+{
+    apply_op_k<<<grid3(L.nx, L.ny, L.nz, B3), B3, 0, st>>>(L, c, res, phi, rhs);
+    LAUNCHED();
+}
+
+// Point red-black Gauss-Seidel, one colour: phi = (rhs - beta*J*S[phi]) * Dinv on cells with
+// (i+j+k+pass) even in global indices (PoissonOpF.ChF:420-474, DO_RBPASS :27-46).
+__global__ void gsrb_k(Lay L, Coef c, double* __restrict__ phi, const double* __restrict__ rhs, int pass)
+{
+    const int j  = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k  = blockIdx.z;
+    const int i0 = (L.lo0 + L.lo1 + j + L.lo2 + k + pass) & 1;
+    const int i  = i0 + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= L.nx || j >= L.ny) return;
+    const long long q = L.idx(i, j, k);
+    const double    s = stencil7(L, c, phi, q, i, j, k);
+    phi[q]            = (rhs[q] - c.beta * c.J[q] * s) * c.Dinv[q];
+}
+void gsrb_pass(cudaStream_t st, const Lay& L, const Coef& c, double* phi, const double* rhs, int pass)
+{
+    gsrb_k<<<grid3((L.nx + 1) / 2, L.ny, L.nz, B3), B3, 0, st>>>(L, c, phi, rhs, pass);
+    LAUNCHED();
+}
+
+// Jacobi / red-black Jacobi update phi += Dinv*res (PoissonOpF.ChF:264-310).
+__global__ void jacobi_k(Lay L, Coef c, double* __restrict__ phi, const double* __restrict__ res, int pass)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.nx || j >= L.ny) return;
+    if (pass >= 0 && ((L.lo0 + i + L.lo1 + j + L.lo2 + k + pass) & 1)) return;
+    const long long q = L.idx(i, j, k);
+    phi[q]            = phi[q] + c.Dinv[q] * res[q];
+}
+void jacobi(cudaStream_t st, const Lay& L, const Coef& c, double* phi, const double* res, int pass)
+{
+    jacobi_k<<<grid3(L.nx, L.ny, L.nz, B3), B3, 0, st>>>(L, c, phi, res, pass);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// Vertical line relaxation, one colour (PoissonOpF.ChF:851-1019 + LAPACK dgtsv, NRHS = 1).
+// One thread owns one column with (i+j+pass) even.  The elimination follows dgtsv's
+// no-interchange branch operation by operation; if dgtsv would have interchanged rows
+// (|d| < |dl|) the flag is raised so the host can fail loudly instead of drifting.
+// v1: modified diagonal d' and rhs b' are parked in compact scratch (wd, wb).
+// ------------------------------------------------------------------------------------------
+__global__ void vertline_k(Lay L, Coef c, double* __restrict__ phi, const double* __restrict__ rhs, int pass,
+                           double* __restrict__ wd, double* __restrict__ wb, int* pivotFlag)
+{
+    const int hx = (L.nx + 1) / 2;
+    const int ic = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j  = blockIdx.y * blockDim.y + threadIdx.y;
+    if (j >= L.ny) return;
+    const int i = ((L.lo0 + L.lo1 + j + pass) & 1) + 2 * ic;
+    if (i >= L.nx) return;
+    const int       N   = L.nz;
+    const double    mxl = c.mxl[i], mxr = c.mxr[i], myl = c.myl[j], myr = c.myr[j];
+    const long long q0  = L.idx(i, j, 0);
+    const long long s2  = L.idx(i, j, -1) - L.sz + L.sz;  // slab index (k = -1 plane offset removed below)
+    const long long slab = (long long)(OX + i) + L.sy * (long long)(1 + j);
+    (void)s2;
+    const long long ws = (long long)hx * L.ny;  // scratch plane stride
+    long long       w  = ic + (long long)hx * j;
+
+    // row k = 0
+    long long q    = q0;
+    double    Jb   = c.J[q] * c.beta;  // Jval * beta
+    double    lphi = mxl * phi[q - 1] + mxr * phi[q + 1] + myl * phi[q - L.sy] + myr * phi[q + L.sy];
+    double    b    = rhs[q] - Jb * lphi;
+    double    d    = 1.0 / c.Dinv[q] + c.loBC[slab];
+    if (N == 1) {
+        d = d + c.hiBC[slab];
+        if (d == 0.0) { atomicOr(pivotFlag, 2); return; }  // dgtsv INFO = N: reference leaves B unsolved
+        phi[q] = b / d;
+        return;
+    }
+    double du = c.beta * c.J[q] * c.mzr[0];
+    int    bad = 0;
+    for (int k = 0; k < N - 1; ++k) {
+        // next row's raw entries
+        const long long qn = q + L.sz;
+        const double    Jn = c.J[qn];
+        lphi               = mxl * phi[qn - 1] + mxr * phi[qn + 1] + myl * phi[qn - L.sy] + myr * phi[qn + L.sy];
+        double bn          = rhs[qn] - Jn * c.beta * lphi;
+        double dn          = 1.0 / c.Dinv[qn];
+        if (k + 1 == N - 1) dn = dn + c.hiBC[slab];
+        const double dl = c.beta * Jn * c.mzl[k + 1];
+        // dgtsv: if |d(i)| >= |dl(i)| ... fact = dl/d; d(i+1) -= fact*du(i); b(i+1) -= fact*b(i)
+        if (!(fabs(d) >= fabs(dl)) || d == 0.0) bad = 1;
+        const double fact = dl / d;
+        wd[w]             = d;
+        wb[w]             = b;
+        dn                = dn - fact * du;
+        bn                = bn - fact * b;
+        d                 = dn;
+        b                 = bn;
+        du                = c.beta * Jn * c.mzr[k + 1];
+        q                 = qn;
+        w += ws;
+    }
+    if (d == 0.0) bad = 1;
+    if (bad) atomicOr(pivotFlag, 1);
+    // back substitution: b(N) /= d(N); b(i) = (b(i) - du(i)*b(i+1)) / d(i)
+    double x = b / d;
+    phi[q]   = x;
+    for (int k = N - 2; k >= 0; --k) {
+        q -= L.sz;
+        w -= ws;
+        const double duk = c.beta * c.J[q] * c.mzr[k];
+        x                = (wb[w] - duk * x) / wd[w];
+        phi[q]           = x;
+    }
+}
+void vertline_pass(cudaStream_t st, const Lay& L, const Coef& c, double* phi, const double* rhs, int pass, double* wd,
+                   double* wb, int* pivotFlag)
+{
+    const int hx = (L.nx + 1) / 2;
+    dim3      b(hx >= 64 ? 64 : 32, hx >= 64 ? 2 : 4, 1);
+    vertline_k<<<grid3(hx, L.ny, 1, b), b, 0, st>>>(L, c, phi, rhs, pass, wd, wb, pivotFlag);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// Restriction: block average, sum in Fortran loop order (CFInterpF.ChF:1085-1120).
+// ------------------------------------------------------------------------------------------
+__global__ void restrict_k(Lay Lf, Lay Lc, int r0, int r1, int r2, double* __restrict__ crse, const double* __restrict__ fine)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= Lc.nx || j >= Lc.ny) return;
+    const double refScale = 1.0 / (double)(r0 * r1 * r2);
+    double       s        = 0.0;
+    for (int c = 0; c < r2; ++c)
+        for (int b = 0; b < r1; ++b)
+            for (int a = 0; a < r0; ++a) s = s + fine[Lf.idx(i * r0 + a, j * r1 + b, k * r2 + c)];
+    crse[Lc.idx(i, j, k)] = s * refScale;
+}
+void restrict_avg(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* crse, const double* fine)
+{
+    restrict_k<<<grid3(Lc.nx, Lc.ny, Lc.nz, B3), B3, 0, st>>>(Lf, Lc, ref[0], ref[1], ref[2], crse, fine);
+    LAUNCHED();
+}
+// Face-centred average (CFInterpF.ChF:1221-1258): Jgup coarsening at MG setup.
+__global__ void restrict_face_k(Lay Lf, Lay Lc, int r0, int r1, int r2, int dir, double* __restrict__ crse,
+                                const double* __restrict__ fine)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= Lc.nx + (dir == 0) || j >= Lc.ny + (dir == 1) || k >= Lc.nz + (dir == 2)) return;
+    const int    rd       = dir == 0 ? r0 : (dir == 1 ? r1 : r2);
+    const double refScale = (double)rd / (double)(r0 * r1 * r2);
+    const int    n0 = dir == 0 ? 1 : r0, n1 = dir == 1 ? 1 : r1, n2 = dir == 2 ? 1 : r2;
+    double       s = 0.0;
+    for (int c = 0; c < n2; ++c)
+        for (int b = 0; b < n1; ++b)
+            for (int a = 0; a < n0; ++a) s = s + fine[Lf.idx(i * r0 + a, j * r1 + b, k * r2 + c)];
+    crse[Lc.idx(i, j, k)] = refScale * s;
+}
+void restrict_face(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], int dir, double* crse, const double* fine)
+{
+    restrict_face_k<<<grid3(Lc.nx + 1, Lc.ny + 1, Lc.nz + 1, B3), B3, 0, st>>>(Lf, Lc, ref[0], ref[1], ref[2], dir, crse, fine);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// Prolongation fine += I(crse) (PoissonOpF.ChF:1031-1320).  One thread per fine cell.
+// order 0: constant; order 1 adds the slope terms in the same kernel (the running sum is
+// evaluated in the reference's order: ((fine + crse) + dxf0*m0) + dxf1*m1) + dxf2*m2).
+// ------------------------------------------------------------------------------------------
+__global__ void prolong_k(Lay Lf, Lay Lc, int r0, int r1, int r2, double* __restrict__ fine, const double* __restrict__ crse,
+                          int order)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= Lf.nx || j >= Lf.ny) return;
+    const int       ic = i / r0, jc = j / r1, kc = k / r2;
+    const long long qc = Lc.idx(ic, jc, kc);
+    const long long qf = Lf.idx(i, j, k);
+    double          f  = fine[qf];
+    if (order == 0 || order == 1) f = f + crse[qc];
+    if (order == 1) {
+        const long long s0 = r0 == 1 ? 0 : 1, s1 = r1 == 1 ? 0 : Lc.sy, s2 = r2 == 1 ? 0 : Lc.sz;
+        const double    sc0 = r0 == 1 ? 0.0 : 1.0 / r0, sc1 = r1 == 1 ? 0.0 : 1.0 / r1, sc2 = r2 == 1 ? 0.0 : 1.0 / r2;
+        const double    m0 = 0.5 * (crse[qc + s0] - crse[qc - s0]);
+        const double    m1 = 0.5 * (crse[qc + s1] - crse[qc - s1]);
+        const double    m2 = 0.5 * (crse[qc + s2] - crse[qc - s2]);
+        const double    dxf0 = -0.5 + (((i - ic * r0) + 0.5) * sc0);
+        const double    dxf1 = -0.5 + (((j - jc * r1) + 0.5) * sc1);
+        const double    dxf2 = -0.5 + (((k - kc * r2) + 0.5) * sc2);
+        f                    = f + dxf0 * m0 + dxf1 * m1 + dxf2 * m2;
+    }
+    if (order == 2) {  // QuadUpgrade1 :1203-1245
+        const double mid  = -2.0 * crse[qc];
+        const double mm0  = 0.25 * (crse[qc + 1] + mid + crse[qc - 1]);
+        const double mm1  = 0.25 * (crse[qc + Lc.sy] + mid + crse[qc - Lc.sy]);
+        const double mm2  = 0.25 * (crse[qc + Lc.sz] + mid + crse[qc - Lc.sz]);
+        const double dxf0 = -0.5 + (((i - ic * r0) + 0.5) / r0);
+        const double dxf1 = -0.5 + (((j - jc * r1) + 0.5) / r1);
+        const double dxf2 = -0.5 + (((k - kc * r2) + 0.5) / r2);
+        f                 = f + dxf0 * dxf0 * mm0 + dxf1 * dxf1 * mm1 + dxf2 * dxf2 * mm2;
+    }
+    fine[qf] = f;
+}
+// QuadUpgrade2 :1249-1322 (mixed second differences; note the reference's own sign pattern for
+// the x-y pair, and that the 2-D build uses that same pattern for its only pair).
+__global__ void prolong_quad2_k(Lay Lf, Lay Lc, int r0, int r1, int r2, double* __restrict__ fine,
+                                const double* __restrict__ crse, int dim)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= Lf.nx || j >= Lf.ny) return;
+    const int       ic = i / r0, jc = j / r1, kc = k / r2;
+    const long long qc = Lc.idx(ic, jc, kc);
+    const long long qf = Lf.idx(i, j, k);
+    const long long sy = Lc.sy, sz = Lc.sz;
+    const double    dxf0 = -0.5 + (((i - ic * r0) + 0.5) / r0);
+    const double    dxf1 = -0.5 + (((j - jc * r1) + 0.5) / r1);
+    const double    dxf2 = -0.5 + (((k - kc * r2) + 0.5) / r2);
+    if (dim == 2) {
+        // CH_SPACEDIM == 2 branch: directions (x, z) here.
+        const double mm0 = 0.25 * (crse[qc + 1 + sz] + crse[qc + 1 - sz] - crse[qc - 1 + sz] - crse[qc - 1 - sz]);
+        fine[qf]         = fine[qf] + dxf0 * dxf2 * mm0;
+    } else {
+        const double mm0 = 0.25 * (crse[qc + sy + sz] - crse[qc + sy - sz] - crse[qc - sy + sz] + crse[qc - sy - sz]);
+        const double mm1 = 0.25 * (crse[qc + 1 + sz] - crse[qc + 1 - sz] - crse[qc - 1 + sz] + crse[qc - 1 - sz]);
+        const double mm2 = 0.25 * (crse[qc + 1 + sy] + crse[qc + 1 - sy] - crse[qc - 1 + sy] - crse[qc - 1 - sy]);
+        fine[qf]         = fine[qf] + dxf1 * dxf2 * mm0 + dxf2 * dxf0 * mm1 + dxf0 * dxf1 * mm2;
+    }
+}
+void prolong_const(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse)
+{
+    prolong_k<<<grid3(Lf.nx, Lf.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[0], ref[1], ref[2], fine, crse, 0);
+    LAUNCHED();
+}
+void prolong_linear(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse)
+{
+    prolong_k<<<grid3(Lf.nx, Lf.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[0], ref[1], ref[2], fine, crse, 1);
+    LAUNCHED();
+}
+void prolong_quad1(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse)
+{
+    prolong_k<<<grid3(Lf.nx, Lf.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[0], ref[1], ref[2], fine, crse, 2);
+    LAUNCHED();
+}
+void prolong_quad2(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse, int dim)
+{
+    prolong_quad2_k<<<grid3(Lf.nx, Lf.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[0], ref[1], ref[2], fine, crse, dim);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// Setup: Dinv = 1/(J*(alpha - beta*(MxL+MxR+yzDiags))) (PoissonOpF.ChF:106-144) and the
+// Robin terms folded into the tridiagonal end rows (PoissonOpF.ChF:635-694).
+// ------------------------------------------------------------------------------------------
+__global__ void dinv_k(Lay L, Coef c, double alpha, double* __restrict__ Dinv, int dim)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.nx || j >= L.ny) return;
+    double yz;
+    if (dim == 3) yz = c.myl[j] + c.myr[j] + c.mzl[k] + c.mzr[k];
+    else yz = c.mzl[k] + c.mzr[k];  // 2-D build: "My" is the vertical
+    const long long q = L.idx(i, j, k);
+    Dinv[q]           = 1.0 / (c.J[q] * (alpha - c.beta * (c.mxl[i] + c.mxr[i] + yz)));
+}
+void compute_dinv(cudaStream_t st, const Lay& L, const Coef& c, double alpha, double* Dinv, int dim)
+{
+    dinv_k<<<grid3(L.nx, L.ny, L.nz, B3), B3, 0, st>>>(L, c, alpha, Dinv, dim);
+    LAUNCHED();
+}
+__global__ void vert_bcs_k(Lay L, Coef c, double sLo, double sHi, double* __restrict__ loBC, double* __restrict__ hiBC)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= L.nx || j >= L.ny) return;
+    const long long slab = (long long)(OX + i) + L.sy * (long long)(1 + j);
+    loBC[slab]           = -c.beta * c.J[L.idx(i, j, 0)] * c.mzl[0] * sLo;
+    hiBC[slab]           = -c.beta * c.J[L.idx(i, j, L.nz - 1)] * c.mzr[L.nz - 1] * sHi;
+}
+void compute_vert_bcs(cudaStream_t st, const Lay& L, const Coef& c, double sLo, double sHi, double* loBC, double* hiBC)
+{
+    vert_bcs_k<<<grid3(L.nx, L.ny, 1, B3), B3, 0, st>>>(L, c, sLo, sHi, loBC, hiBC);
+    LAUNCHED();
+}
+
+// J = ((1*dxdXi_x)*dxdXi_y)*dxdXi_z and Jgup_d likewise with a divide for d
+// (GeoSourceInterface.cpp:206-222, 326-350), from the per-box 1-D tables that
+// LevelGeometry::createMetricCache's per-box fills amount to.  Tables are indexed from the
+// box's small end (cell tables n entries, node tables n+1).
+__global__ void metric_k(Lay L, int b0, int b1, int b2, int n0, int n1, int n2, const double* cx, const double* cy,
+                         const double* cz, const double* fx, const double* fy, const double* fz, double* J, double* Jg0,
+                         double* Jg1, double* Jg2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i > n0 || j > n1 || k > n2) return;
+    const long long q  = L.idx(b0 + i, b1 + j, b2 + k);
+    const bool      ci = i < n0, cj = j < n1, ck = k < n2;
+    if (ci && cj && ck) J[q] = 1.0 * cx[i] * cy[j] * cz[k];
+    if (cj && ck) Jg0[q] = 1.0 / fx[i] * cy[j] * cz[k];
+    if (ci && ck) Jg1[q] = 1.0 * cx[i] / fy[j] * cz[k];
+    if (ci && cj) Jg2[q] = 1.0 * cx[i] * cy[j] / fz[k];
+}
+void fill_metric_box(cudaStream_t st, const Lay& L, const int blo[3], const int bhi[3], const double* cx, const double* cy,
+                     const double* cz, const double* fx, const double* fy, const double* fz, double* J, double* Jg0,
+                     double* Jg1, double* Jg2)
+{
+    const int n0 = bhi[0] - blo[0] + 1, n1 = bhi[1] - blo[1] + 1, n2 = bhi[2] - blo[2] + 1;
+    metric_k<<<grid3(n0 + 1, n1 + 1, n2 + 1, B3), B3, 0, st>>>(L, blo[0], blo[1], blo[2], n0, n1, n2, cx, cy, cz, fx, fy, fz, J,
+                                                                Jg0, Jg1, Jg2);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// Divergence of the advecting velocity (FiniteDiffF.ChF:42-115) and the face gradient
+// Jg^{dd} * (phi(i) - phi(i-e_d)) / dXi_d (FiniteDiffF.ChF:123-147 + FArrayBox::mult,
+// PoissonOp.cpp:1508-1534; the optional *beta of :1537-1541).
+// ------------------------------------------------------------------------------------------
+__global__ void div_k(Lay L, double* __restrict__ div, const double* __restrict__ u0, const double* __restrict__ u1,
+                      const double* __restrict__ u2, double dxinv0, double dxinv1, double dxinv2, int dim)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.nx || j >= L.ny) return;
+    const long long q = L.idx(i, j, k);
+    if (dim == 3)
+        div[q] = (u0[q + 1] - u0[q]) * dxinv0 + (u1[q + L.sy] - u1[q]) * dxinv1 + (u2[q + L.sz] - u2[q]) * dxinv2;
+    else
+        div[q] = (u0[q + 1] - u0[q]) * dxinv0 + (u2[q + L.sz] - u2[q]) * dxinv2;
+}
+void divergence(cudaStream_t st, const Lay& L, double* div, const double* u0, const double* u1, const double* u2,
+                double dxinv0, double dxinv1, double dxinv2, int dim)
+{
+    div_k<<<grid3(L.nx, L.ny, L.nz, B3), B3, 0, st>>>(L, div, u0, u1, u2, dxinv0, dxinv1, dxinv2, dim);
+    LAUNCHED();
+}
+__global__ void grad_k(Lay L, double* __restrict__ g, const double* __restrict__ phi, const double* __restrict__ Jgup, int dir,
+                       double oneOnDx, double beta, int scaleBeta)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= L.nx + (dir == 0) || j >= L.ny + (dir == 1) || k >= L.nz + (dir == 2)) return;
+    const long long q = L.idx(i, j, k);
+    const long long s = dir == 0 ? 1 : (dir == 1 ? L.sy : L.sz);
+    double          v = (phi[q] - phi[q - s]) * oneOnDx;
+    v                 = v * Jgup[q];
+    if (scaleBeta) v = v * beta;
+    g[q] = v;
+}
+void gradient(cudaStream_t st, const Lay& L, double* g, const double* phi, const double* Jgup, int dir, double oneOnDx,
+              double beta, int scaleBeta)
+{
+    grad_k<<<grid3(L.nx + 1, L.ny + 1, L.nz + 1, B3), B3, 0, st>>>(L, g, phi, Jgup, dir, oneOnDx, beta, scaleBeta);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
+// Reductions per reference box (LDFABOps.cpp:98-164 sums box by box; the 2-norm is
+// sqrt(Sum_box (Sum x^2)/numPts_box), FArrayBox.cpp:138-141).  Two deterministic stages:
+// RCH chunks per box, then one block per box adds the chunk partials in a fixed order.
+// ------------------------------------------------------------------------------------------
+constexpr int RCH = 64;
+__device__ __forceinline__ double block_reduce(double v, int op, double* sm)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_down_sync(0xffffffffu, v, o);
+        v              = op == 0 ? fmax(v, w) : v + w;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        v = lane < (blockDim.x >> 5) ? sm[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+            const double w = __shfl_down_sync(0xffffffffu, v, o);
+            v              = op == 0 ? fmax(v, w) : v + w;
+        }
+    }
+    __syncthreads();
+    return v;  // valid in thread 0
+}
+__global__ void reduce1_k(Lay L, BoxList bl, int op, const double* __restrict__ x, const double* __restrict__ y, double dv,
+                          double* __restrict__ partial)
+{
+    __shared__ double sm[32];
+    const int bx = blockIdx.y, ch = blockIdx.x;
+    const int lo0 = bl.lo[3 * bx], lo1 = bl.lo[3 * bx + 1], lo2 = bl.lo[3 * bx + 2];
+    const int n0 = bl.hi[3 * bx] - lo0 + 1, n1 = bl.hi[3 * bx + 1] - lo1 + 1, n2 = bl.hi[3 * bx + 2] - lo2 + 1;
+    const long long rows = (long long)n1 * n2;
+    double          a = 0.0, b = 0.0;
+    for (long long r = ch; r < rows; r += RCH) {
+        const int       j = lo1 + (int)(r % n1), k = lo2 + (int)(r / n1);
+        const long long q = L.idx(lo0, j, k);
+        for (int i = threadIdx.x; i < n0; i += blockDim.x) {
+            const double v = x[q + i];
+            if (op == 0) a = fmax(a, fabs(v));
+            else if (op == 1) a = a + fabs(v);
+            else if (op == 2) a = a + v * v;
+            else if (op == 3) a = a + v * y[q + i];
+            else { const double s = y[q + i] * dv; a = a + s * v; b = b + s; }  // IntegralF.ChF:37-58
+        }
+    }
+    a = block_reduce(a, op, sm);
+    if (op == 4) b = block_reduce(b, 1, sm);
+    if (threadIdx.x == 0) {
+        partial[2 * ((long long)bx * RCH + ch)]     = a;
+        partial[2 * ((long long)bx * RCH + ch) + 1] = b;
+    }
+}
+__global__ void reduce2_k(int op, const double* __restrict__ partial, double* __restrict__ out)
+{
+    __shared__ double sm[32];
+    const int bx = blockIdx.x;
+    double    a = 0.0, b = 0.0;
+    if (threadIdx.x < RCH) {
+        a = partial[2 * ((long long)bx * RCH + threadIdx.x)];
+        b = partial[2 * ((long long)bx * RCH + threadIdx.x) + 1];
+    }
+    a = block_reduce(a, op, sm);
+    if (op == 4) b = block_reduce(b, 1, sm);
+    if (threadIdx.x == 0) {
+        if (op == 4) { out[2 * bx] = a; out[2 * bx + 1] = b; }
+        else out[bx] = a;
+    }
+}
+int  reduce_partial_len(int nboxes) { return 2 * RCH * nboxes; }
+void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, const double* x, const double* y, double dv,
+                  double* partial, double* out)
+{
+    reduce1_k<<<dim3(RCH, boxes.n), 256, 0, st>>>(L, boxes, op, x, y, dv, partial);
+    LAUNCHED();
+    reduce2_k<<<boxes.n, 64, 0, st>>>(op, partial, out);
+    LAUNCHED();
+}
+
+}  // namespace k
+}  // namespace sb

@@ -1,0 +1,437 @@
+// sb_mg.cpp -- the solver control flow of the projection, mirrored from the reference so that
+// iteration counts and convergence decisions are identical: MGSolver<T> (Elliptic/MGSolverI.H),
+// BiCGStabSolver<T> (Elliptic/LevelSolverI.H:252-536), the coarsening strategies
+// (Elliptic/MGCoarseningStrategy.cpp) and LevelHybridSolver (Elliptic/LevelHybridSolver.cpp).
+// Fields live on the device; only scalars (norms, dot products) come back to the host, exactly
+// where the reference performs an MPI_Allreduce.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "sb_host.h"
+
+namespace sb {
+
+// ---------------------------------------------------------------------------------------------
+// Coarsening strategies.
+namespace {
+using IV = std::array<int, 3>;
+
+bool coarsenableAll(const std::vector<Box3>& boxes, const IV& r)
+{
+    for (const Box3& b : boxes)
+        if (!coarsenable(b, r.data())) return false;
+    return true;
+}
+// SemicoarseningStrategy::measureAnisotropy (MGCoarseningStrategy.H:103-107)
+double isoSemi(const double dx[3], int dim)
+{
+    if (dim == 2) { const double m = std::min(dx[0], dx[2]); return (dx[0] / m) * (dx[2] / m); }
+    const double m = std::min(std::min(dx[0], dx[1]), dx[2]);
+    return (dx[0] / m) * (dx[1] / m) * (dx[2] / m);
+}
+// HorizCoarseningStrategy::measureAnisotropy (MGCoarseningStrategy.H:153-156)
+double isoHoriz(const double dx[3], int dim)
+{
+    if (dim == 2) { const double m = std::min(dx[0], dx[0]); return dx[0] / m; }
+    const double m = std::min(dx[0], dx[1]);
+    return (dx[0] / m) * (dx[1] / m);
+}
+// computeNextRefRatio (MGCoarseningStrategy.cpp:138-175, 281-310)
+IV nextRef(const double dx[3], const std::vector<Box3>& grids, const std::vector<IV>& refList, bool horiz, int dim)
+{
+    const double isoLimiter = 0.75;
+    auto         iso        = [&](const double* d) { return horiz ? isoHoriz(d, dim) : isoSemi(d, dim); };
+    size_t       isoIdx     = std::numeric_limits<size_t>::max();
+    double       isoVal     = iso(dx);
+    const double lastIsoVal = isoVal;
+    for (size_t cur = 0; cur < refList.size(); ++cur) {
+        const IV&    r        = refList[cur];
+        const double cdx[3]   = {dx[0] * r[0], dx[1] * r[1], dx[2] * r[2]};
+        const double curIso   = iso(cdx);
+        if (!coarsenableAll(grids, r)) continue;
+        if (curIso < isoLimiter * lastIsoVal && isoIdx < refList.size()) continue;
+        if (curIso <= isoVal) { isoIdx = cur; isoVal = curIso; }
+    }
+    if (isoIdx < refList.size()) return refList[isoIdx];
+    return IV{1, 1, 1};
+}
+}  // namespace
+
+std::vector<IV> createMGRefSchedule(const Op& top, int maxDepth, bool horizStrategy, bool doVertCoarsening)
+{
+    const int       dim = top.dim;
+    std::vector<IV> refList;
+    if (!horizStrategy) {
+        if (dim == 2) refList = {{2, 1, 1}, {1, 1, 2}, {2, 1, 2}};
+        else refList = {{2, 1, 1}, {1, 2, 1}, {1, 1, 2}, {1, 2, 2}, {2, 1, 2}, {2, 2, 1}, {2, 2, 2}};
+    } else {
+        if (dim == 2) refList = {{2, 1, 1}};
+        else refList = {{2, 1, 1}, {1, 2, 1}, {2, 2, 1}};
+    }
+    // curDx = L / N with L = N * dXi (MGSolverI.H:148-151, MGCoarseningStrategy.cpp:68)
+    double curDx[3];
+    for (int d = 0; d < 3; ++d) {
+        const double N = (double)top.domain.size(d);
+        curDx[d]       = (N * top.dXi[d]) / N;
+    }
+    std::vector<Box3> cur = top.boxes;  // minBoxSize = 1: coarsening by it is a no-op
+    std::vector<IV>   sched;
+    while (true) {
+        if (maxDepth >= 0 && sched.size() == (size_t)maxDepth) break;
+        IV r = nextRef(curDx, cur, refList, horizStrategy, dim);
+        if (r == IV{1, 1, 1}) break;
+        if (horizStrategy && doVertCoarsening && coarsenableAll(cur, IV{1, 1, 2})) r[2] = 2;
+        for (Box3& b : cur) b = coarsen(b, r.data());
+        for (int d = 0; d < 3; ++d) curDx[d] *= (double)r[d];
+        sched.push_back(r);
+    }
+    sched.push_back(IV{1, 1, 1});
+    return sched;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Options.
+}  // namespace sb
+
+extern "C" void sb_mg_default_options(sb_mg_options* o)
+{
+    // Grade5_SOMAR/ProjectorParameters.cpp:124-222 defaults, as MGSolverI.H:22-50 copies them.
+    o->absTol = 1.0e-12; o->relTol = 1.0e-6; o->convergenceMetric = -1.0; o->hang = 1.0e-7;
+    o->numSmoothDown = 16; o->numSmoothUp = 16; o->numSmoothBottom = 2; o->numSmoothPrecond = 2;
+    o->prolongOrder = 1; o->prolongOrderFMG = 3; o->numSmoothUpFMG = 2;
+    o->maxDepth = -1; o->numCycles = -1; o->maxIters = 10; o->normType = 2; o->verbosity = 0;
+    o->bottom.absTol = 1.0e-6; o->bottom.relTol = 1.0e-4; o->bottom.small = 1.0e-30; o->bottom.hang = 1.0e-7;
+    o->bottom.convergenceMetric = -1.0;
+    o->bottom.maxIters = 80; o->bottom.maxRestarts = 5; o->bottom.normType = 2; o->bottom.verbosity = 0;
+    o->bottom.numSmoothPrecond = 2;
+}
+extern "C" void sb_mg_quick_and_dirty_options(sb_mg_options* o)
+{
+    // MGSolverI.H:56-74
+    sb_mg_default_options(o);
+    o->absTol = 1.0e-300; o->relTol = 1.0e-300; o->numCycles = -1; o->maxIters = 1; o->verbosity = 0;
+    o->bottom.absTol = 1.0e-300; o->bottom.relTol = 1.0e-300; o->bottom.verbosity = 0;
+}
+
+namespace sb {
+
+// ---------------------------------------------------------------------------------------------
+// BiCGStab bottom solver (LevelSolverI.H:252-536).
+void BiCGStabSolver::define(Op* o)
+{
+    op = o;
+    r = op->alloc(); r_tilde = op->alloc(); e = op->alloc(); p = op->alloc();
+    p_tilde = op->alloc(); s_tilde = op->alloc(); t = op->alloc(); v = op->alloc();
+}
+BiCGStabSolver::~BiCGStabSolver()
+{
+    for (double* q : {r, r_tilde, e, p, p_tilde, s_tilde, t, v})
+        if (q) cudaFree(q);
+}
+SolverStatus BiCGStabSolver::solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double a_convergenceMetric)
+{
+    SolverStatus st;
+    st.status = SB_STATUS_UNDEFINED;
+    Op& o     = *op;
+    if (setPhiToZero) o.setToZero(phi);
+    int recount = 0;
+    o.residual(r, phi, rhs, homog);
+    o.assignLocal(r_tilde, r);
+    o.setToZero(e);
+    o.setToZero(p_tilde);
+    o.setToZero(s_tilde);
+    int    i      = 0;
+    double rho[4] = {0, 0, 0, 0};
+    double norm[2];
+    norm[0]              = o.norm(r, opt.normType);
+    double initial_norm  = norm[0];
+    double initial_rnorm = norm[0];
+    norm[1]              = norm[0];
+    st.initResNorm       = initial_norm;
+    double alpha[2] = {0, 0}, beta[2] = {0, 0}, omega[2] = {0, 0};
+    bool   init     = true;
+    int    restarts = 0;
+    if (opt.convergenceMetric > 0.0) initial_norm = opt.convergenceMetric;
+    if (a_convergenceMetric > 0.0) initial_norm = a_convergenceMetric;
+    const double smallReal = 1.0e4 * std::numeric_limits<double>::epsilon();
+
+    while ((i < opt.maxIters && norm[0] > opt.absTol * norm[1]) && (norm[1] > 0)) {
+        i++;
+        norm[1] = norm[0]; alpha[1] = alpha[0]; beta[1] = beta[0]; omega[1] = omega[0];
+        rho[3] = rho[2]; rho[2] = rho[1];
+        rho[1] = o.dotProduct(r_tilde, r);
+        if (std::abs(rho[1]) < smallReal) {  // RealCmp::isZero
+            o.incr(phi, e, 1.0);
+            st.finalResNorm = initial_norm;
+            st.status       = SB_STATUS_SINGULAR;
+            lastIters       = i;
+            return st;
+        }
+        if (init) {
+            o.assignLocal(p, r);
+            init = false;
+        } else {
+            beta[1] = (rho[1] / rho[2]) * (alpha[1] / omega[1]);
+            o.scale(p, beta[1]);
+            o.incr(p, v, -beta[1] * omega[1]);
+            o.incr(p, r, 1.0);
+        }
+        o.preCond(p_tilde, p, opt.numSmoothPrecond);
+        o.applyOp(v, p_tilde, true);
+        const double m = o.dotProduct(r_tilde, v);
+        alpha[0]       = rho[1] / m;
+        if (std::abs(m) > opt.small * std::abs(rho[1])) {
+            o.incr(r, v, -alpha[0]);
+            norm[0] = o.norm(r, opt.normType);
+            o.incr(e, p_tilde, alpha[0]);
+        } else {
+            o.setToZero(r);
+            norm[0] = 0.0;
+        }
+        if (norm[0] > opt.absTol * initial_norm && norm[0] > opt.relTol * initial_rnorm) {
+            o.preCond(s_tilde, r, opt.numSmoothPrecond);
+            o.applyOp(t, s_tilde, true);
+            omega[0] = o.dotProduct(t, r) / o.dotProduct(t, t);
+            o.incr(e, s_tilde, omega[0]);
+            o.incr(r, t, -omega[0]);
+            norm[0] = o.norm(r, opt.normType);
+        }
+        if (norm[0] <= opt.absTol * initial_norm || norm[0] <= opt.relTol * initial_rnorm) {
+            st.finalResNorm = norm[0];
+            st.status       = SB_STATUS_CONVERGED;
+            break;
+        }
+        if (omega[0] == 0.0 || norm[0] > (1.0 - opt.hang) * norm[1]) {
+            if (recount == 0) {
+                recount = 1;
+            } else {
+                recount = 0;
+                o.incr(phi, e, 1.0);
+                if (restarts == opt.maxRestarts) {
+                    st.finalResNorm = norm[0];
+                    st.status       = SB_STATUS_MAXITERS;
+                    lastIters       = i;
+                    return st;
+                }
+                o.residual(r, phi, rhs, homog);
+                norm[0] = o.norm(r, opt.normType);
+                rho[1] = 0.0; rho[2] = 0.0; rho[3] = 0.0;
+                alpha[0] = 0; beta[0] = 0; omega[0] = 0;
+                o.assignLocal(r_tilde, r);
+                o.setToZero(e);
+                restarts++;
+                init = true;
+            }
+        }
+    }
+    o.incr(phi, e, 1.0);
+    st.finalResNorm = norm[0];
+    lastIters       = i;
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MGSolver<T>::define (MGSolverI.H:140-204)
+void MGSolver::define(Op& top, const sb_mg_options& a_opt, std::vector<IV> sched, bool useBottomSolver)
+{
+    opt = a_opt;
+    if (sched.empty()) {
+        if (top.relaxMethod == SB_RELAX_VERTLINE) refSchedule = createMGRefSchedule(top, opt.maxDepth, true, true);
+        else refSchedule = createMGRefSchedule(top, opt.maxDepth, false, false);
+    } else {
+        refSchedule = sched;
+    }
+    if (refSchedule.empty() || refSchedule.back() != IV{1, 1, 1}) SB_FAIL("the MG ref schedule must end with (1,1,1)");
+    opt.maxDepth = (int)refSchedule.size() - 1;
+    ops.assign(opt.maxDepth + 1, nullptr);
+    ops[0] = &top;
+    for (int d = 1; d <= opt.maxDepth; ++d) {
+        owned.emplace_back(new Op(*ops[d - 1], refSchedule[d - 1].data()));
+        ops[d] = owned.back().get();
+    }
+    tmpRes.assign(opt.maxDepth + 1, nullptr);
+    cor.assign(opt.maxDepth + 1, nullptr);
+    res.assign(opt.maxDepth + 1, nullptr);
+    for (int d = 0; d <= opt.maxDepth; ++d) {
+        tmpRes[d] = ops[d]->alloc();
+        if (d > 0) { cor[d] = ops[d]->alloc(); res[d] = ops[d]->alloc(); }
+    }
+    topRes = top.alloc();
+    topCor = top.alloc();
+    if (useBottomSolver) {
+        bottom.reset(new BiCGStabSolver);
+        bottom->define(ops[opt.maxDepth]);
+        bottom->opt = opt.bottom;
+    }
+    status.clear();
+}
+MGSolver::~MGSolver()
+{
+    for (auto* q : tmpRes) if (q) cudaFree(q);
+    for (auto* q : cor) if (q) cudaFree(q);
+    for (auto* q : res) if (q) cudaFree(q);
+    if (topRes) cudaFree(topRes);
+    if (topCor) cudaFree(topCor);
+}
+void MGSolver::modifyOptionsExceptMaxDepth(const sb_mg_options& o)
+{
+    const int old = opt.maxDepth;
+    opt           = o;
+    opt.maxDepth  = old;
+    if (bottom) bottom->opt = o.bottom;
+}
+
+SolverStatus MGSolver::solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double metric)
+{
+    // MGSolverI.H:232-262
+    return cycle(opt.numCycles < 0, phi, rhs, homog, setPhiToZero, metric);
+}
+
+// MGSolver<T>::vCycle (MGSolverI.H:265-430) and ::fmg (:434-612); the two outer loops differ only
+// in the call that produces the correction.
+SolverStatus MGSolver::cycle(bool fmgMode, double* phi, const double* rhs, bool homog, bool setPhiToZero, double a_metric)
+{
+    status.clear();
+    absResNorms.clear();
+    std::vector<double> relResNorms;
+    Op&     op  = *ops[0];
+    double* r   = topRes;
+    double* c   = topCor;
+    if (setPhiToZero) op.setToZero(phi);
+    if (a_metric > 0.0) { absResNorms.push_back(a_metric); relResNorms.push_back(1.0); }
+    else if (opt.convergenceMetric > 0.0) { absResNorms.push_back(opt.convergenceMetric); relResNorms.push_back(1.0); }
+
+    op.residual(r, phi, rhs, homog);
+    absResNorms.push_back(op.norm(r, opt.normType));
+    status.initResNorm = absResNorms[0];
+    relResNorms.push_back(absResNorms.back() / absResNorms[0]);
+    lastIters = 0;
+    if (relResNorms.back() < opt.relTol) {
+        status.finalResNorm = absResNorms.back();
+        status.status       = SB_STATUS_CONVERGED;
+        return status;
+    }
+    int iter;
+    for (iter = 1; iter <= opt.maxIters; ++iter) {
+        if (fmgMode) {
+            fmg_residualEq(c, r, 0);  // allFMG = true (MGSolverI.H:444, 517)
+        } else {
+            op.preCond(c, r, 0);
+            vCycle_residualEq(c, r, 0);
+        }
+        op.incr(phi, c, 1.0);
+        op.residual(r, phi, rhs, homog);
+        absResNorms.push_back(op.norm(r, opt.normType));
+        relResNorms.push_back(absResNorms.back() / absResNorms[0]);
+        lastIters = iter;
+        if (absResNorms.back() < opt.absTol) { status.status = SB_STATUS_CONVERGED; break; }
+        if (relResNorms.back() < opt.relTol) { status.status = SB_STATUS_CONVERGED; break; }
+        if (relResNorms[iter] > relResNorms[iter - 1]) {
+            op.incr(phi, c, -1.0);
+            absResNorms.pop_back();
+            relResNorms.pop_back();
+            --iter;
+            lastIters     = iter;
+            status.status = SB_STATUS_DIVERGED;
+            break;
+        }
+        if (relResNorms[iter] > (1.0 - opt.hang) * relResNorms[iter - 1]) { status.status = SB_STATUS_HANG; break; }
+    }
+    status.finalResNorm = absResNorms.back();
+    if (op.relaxMethod == SB_RELAX_VERTLINE)
+        for (Op* o : ops) o->checkPivot();
+    return status;
+}
+
+// MGSolver<T>::vCycle_residualEq (MGSolverI.H:617-754)
+void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth)
+{
+    Op& op = *ops[depth];
+    if (depth == opt.maxDepth) {
+        op.relax(a_cor, a_res, opt.numSmoothBottom);
+        if (bottom) bottom->solve(a_cor, a_res, true, false);
+        return;
+    }
+    Op&     crseOp  = *ops[depth + 1];
+    double* crseCor = cor[depth + 1];
+    double* crseRes = res[depth + 1];
+    double* tmp     = tmpRes[depth];
+    op.relax(a_cor, a_res, opt.numSmoothDown);
+    op.residual(tmp, a_cor, a_res, true);
+    op.MGRestrict(crseOp, crseRes, tmp);
+    crseOp.preCond(crseCor, crseRes, 0);
+    const int numCycles = std::abs(opt.numCycles);
+    for (int i = 0; i < numCycles; ++i) vCycle_residualEq(crseCor, crseRes, depth + 1);
+    op.MGProlong(crseOp, a_cor, crseCor, opt.prolongOrder);
+    op.relax(a_cor, a_res, opt.numSmoothUp);
+}
+
+// MGSolver<T>::fmg_residualEq (MGSolverI.H:758-820)
+void MGSolver::fmg_residualEq(double* a_cor, const double* a_res, int depth)
+{
+    Op& op = *ops[depth];
+    op.setToZero(a_cor);
+    if (depth < opt.maxDepth) {
+        Op&     crseOp  = *ops[depth + 1];
+        double* crseCor = cor[depth + 1];
+        double* crseRes = res[depth + 1];
+        op.MGRestrict(crseOp, crseRes, a_res);
+        fmg_residualEq(crseCor, crseRes, depth + 1);
+        op.MGProlong(crseOp, a_cor, crseCor, opt.prolongOrderFMG);
+        op.relax(a_cor, a_res, opt.numSmoothUpFMG);
+    }
+    const int numCycles = std::abs(opt.numCycles);
+    for (int i = 0; i < numCycles; ++i) vCycle_residualEq(a_cor, a_res, depth);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LevelHybridSolver (LevelHybridSolver.cpp).
+int HybridSolver::computeSolveMode(const Op& op)
+{
+    // :457-498: lepticity = min(dXi_x, dXi_y) / L_z
+    const double Lz   = (double)op.domain.size(2) * op.dXi[2];
+    const double dh   = op.dim == 2 ? std::min(op.dXi[0], op.dXi[0]) : std::min(op.dXi[0], op.dXi[1]);
+    const double lept = dh / Lz;
+    if (lept > 1.0) return SB_MODE_LEPTIC;
+    if (lept > 0.2) return SB_MODE_LEPTIC_MG;
+    return SB_MODE_MG;
+}
+void HybridSolver::define(Op& top, const sb_mg_options& o)
+{
+    op   = &top;
+    opt  = o;
+    mode = computeSolveMode(top);
+    if (isHybrid && mode != SB_MODE_MG)
+        SB_FAIL("LevelHybridSolver would pick the leptic solver for this grid (lepticity > 0.2); only SolveMode::MG is "
+                "implemented on the B200 path");
+    mg.define(top, o, {}, true);
+    opt.maxDepth = mg.opt.maxDepth;
+    cor = top.alloc();
+    res = top.alloc();
+}
+HybridSolver::~HybridSolver()
+{
+    if (cor) cudaFree(cor);
+    if (res) cudaFree(res);
+}
+SolverStatus HybridSolver::solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double metric)
+{
+    if (!isHybrid) return mg.solve(phi, rhs, homog, setPhiToZero, metric);
+    // LevelHybridSolver::solve (:266-292) + solveResidualEq, SolveMode::MG branch (:296-452)
+    Op& o = *op;
+    if (setPhiToZero) o.setToZero(phi);
+    o.residual(res, phi, rhs, homog);
+    o.setToZero(cor);
+    resNorms.clear();
+    resNorms.push_back(o.norm(res, opt.normType));
+    if (metric > 0.0) resNorms[0] = metric;
+    SolverStatus st = mg.solve(cor, res, true, false, -1.0);
+    resNorms.push_back(st.finalResNorm);
+    st.initResNorm  = resNorms[0];
+    st.finalResNorm = resNorms.back();
+    o.incr(phi, cor, 1.0);
+    return st;
+}
+
+}  // namespace sb

@@ -1,0 +1,621 @@
+// sb_op.cpp -- host driver of one MG depth: the B200 counterpart of Elliptic::PoissonOp
+// (reference Grade3_Calculus/Elliptic/PoissonOp.cpp).  All field arithmetic is in
+// sb_kernels.cu; this file holds geometry/setup logic and the call order of the reference.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "sb_comm.h"
+#include "sb_host.h"
+
+namespace sb {
+
+// ---------------------------------------------------------------------------------------------
+Context::Context(int dev, int rank_, int nranks_) : device(dev), rank(rank_), nranks(nranks_)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        SB_FAIL("no CUDA device visible: somar_b200 has no CPU fallback");
+    SB_CUDA(cudaSetDevice(dev));
+    SB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    hpinLen = 1 << 16;
+    SB_CUDA(cudaMallocHost((void**)&hpin, hpinLen * sizeof(double)));
+    launches0 = k::launch_count();
+}
+Context::~Context()
+{
+    delete comm;
+    if (scratch) cudaFree(scratch);
+    if (hpin) cudaFreeHost(hpin);
+    if (st) cudaStreamDestroy(st);
+}
+void* Context::getScratch(size_t bytes)
+{
+    if (bytes > scratchBytes) {
+        sync();
+        if (scratch) SB_CUDA(cudaFree(scratch));
+        SB_CUDA(cudaMalloc(&scratch, bytes));
+        scratchBytes = bytes;
+    }
+    return scratch;
+}
+void Context::allreduceSum(double* v, int n)
+{
+    if (nranks > 1) { if (!comm) SB_FAIL("nranks > 1 but sb_comm_init was not called"); comm->allreduceHost(v, n, false); }
+}
+void Context::allreduceMax(double* v, int n)
+{
+    if (nranks > 1) { if (!comm) SB_FAIL("nranks > 1 but sb_comm_init was not called"); comm->allreduceHost(v, n, true); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Geometry source.
+static const double kPi = 3.14159265358979323846264338327950288e0;  // Grade1_Basics/SOMAR_Constants.H:55
+
+void MapSpec::interp(std::vector<double>& x, const std::vector<double>& xi, int mu) const
+{
+    x.resize(xi.size());
+    if (kind == SB_MAP_CARTESIAN) {
+        x = xi;
+    } else if (kind == SB_MAP_STRETCHED) {
+        // maps/StretchedMap.cpp:9-38
+        const double A = ampl[mu], kk = 2.0 * kPi / (xmax[mu] - xmin[mu]), x0 = xmin[mu];
+        for (size_t n = 0; n < xi.size(); ++n) x[n] = xi[n] + A * std::sin(kk * (xi[n] - x0));
+    } else {
+        if (!fn) SB_FAIL("SB_MAP_CALLBACK without map_fn");
+        fn(x.data(), xi.data(), (int)xi.size(), mu, user);
+    }
+}
+std::vector<double> MapSpec::physCoor(int mu, double dXi_, int lo, int n, int nodeType) const
+{
+    std::vector<double> x(n);
+    if (kind == SB_MAP_CARTESIAN) {
+        // maps/CartesianMapF.ChF:31-80: x = dXi*(i + offset)
+        const double offset = (1.0 - nodeType) * 0.5;
+        for (int m = 0; m < n; ++m) x[m] = dXi_ * ((double)(lo + m) + offset);
+        return x;
+    }
+    // GeoSourceInterface.cpp:41-73
+    std::vector<double> vxi(n);
+    double              xi = lo * dXi_;
+    if (nodeType == 0) xi += 0.5 * dXi_;
+    for (int m = 0; m < n; ++m) { vxi[m] = xi; xi += dXi_; }
+    interp(x, vxi, mu);
+    return x;
+}
+std::vector<double> MapSpec::dxdXi(int mu, double dXi_, int lo, int n, int nodeType, double scale) const
+{
+    std::vector<double> d(n);
+    if (kind == SB_MAP_CARTESIAN) {  // maps/CartesianMap.cpp:117-130: setVal(scale)
+        std::fill(d.begin(), d.end(), scale);
+        return d;
+    }
+    const double scaledDXi = dXi_ / scale;
+    const double oneOnDx   = 1.0 / scaledDXi;
+    if (nodeType == 0) {
+        // cell-centred dest: nodes lo..lo+n, FINITEDIFF_PARTIALD_NC2CC
+        std::vector<double> x = physCoor(mu, dXi_, lo, n + 1, 1);
+        for (int m = 0; m < n; ++m) d[m] = (x[m + 1] - x[m]) * oneOnDx;
+    } else {
+        // node-centred dest: cells lo-1..lo+n-1, FINITEDIFF_PARTIALD_CC2NC
+        std::vector<double> x = physCoor(mu, dXi_, lo - 1, n + 1, 0);
+        for (int m = 0; m < n; ++m) d[m] = (x[m + 1] - x[m]) * oneOnDx;
+    }
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+Field::Field(Op* op_, int c) : op(op_), centering(c) { d = op->alloc(); }
+Field::~Field() { if (d) cudaFree(d); }
+
+double* Op::alloc() const
+{
+    double* p = nullptr;
+    SB_CUDA(cudaMalloc((void**)&p, lay.n * sizeof(double)));
+    SB_CUDA(cudaMemsetAsync(p, 0, lay.n * sizeof(double), ctx->st));
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+Op::Op(Context* c, const sb_level_desc& d) : ctx(c)
+{
+    dim = d.dim;
+    if (dim != 2 && dim != 3) SB_FAIL("dim must be 2 or 3");
+    for (int i = 0; i < 3; ++i) {
+        domain.lo[i] = d.domain_lo[i]; domain.hi[i] = d.domain_hi[i];
+        periodic[i] = d.periodic[i]; dXi[i] = d.dXi[i];
+        for (int s = 0; s < 2; ++s) { bcAlpha[i][s] = d.bc_alpha[i][s]; bcBeta[i][s] = d.bc_beta[i][s]; }
+        map.xmin[i] = d.map_xmin[i]; map.xmax[i] = d.map_xmax[i]; map.ampl[i] = d.map_ampl[i];
+    }
+    if (dim == 2 && domain.size(1) != 1) SB_FAIL("dim == 2 requires a single layer in slot 1");
+    map.kind = d.map_kind; map.fn = d.map_fn; map.user = d.map_user;
+    alpha = d.alpha; beta = d.beta; relaxMethod = d.relax_method;
+    if (d.num_boxes <= 0) SB_FAIL("empty box list");
+    boxes.resize(d.num_boxes); boxRank.resize(d.num_boxes);
+    for (int b = 0; b < d.num_boxes; ++b) {
+        for (int i = 0; i < 3; ++i) { boxes[b].lo[i] = d.box_lo[3 * b + i]; boxes[b].hi[i] = d.box_hi[3 * b + i]; }
+        boxRank[b] = d.box_rank ? d.box_rank[b] : 0;
+        if (boxRank[b] < 0 || boxRank[b] >= ctx->nranks) SB_FAIL("box_rank out of range");
+    }
+    setupLayout();
+    J = alloc();
+    for (int i = 0; i < 3; ++i) Jgup[i] = alloc();
+    fillMetricFromMap();
+}
+
+void Op::setupLayout()
+{
+    const int nr = ctx->nranks;
+    tiles.assign(nr, Box3{{0, 0, 0}, {-1, -1, -1}});
+    std::vector<long long> pts(nr, 0);
+    std::vector<int>       cnt(nr, 0);
+    local.clear();
+    for (size_t b = 0; b < boxes.size(); ++b) {
+        const int r = boxRank[b];
+        Box3&     t = tiles[r];
+        if (cnt[r]++ == 0) t = boxes[b];
+        else
+            for (int i = 0; i < 3; ++i) { t.lo[i] = std::min(t.lo[i], boxes[b].lo[i]); t.hi[i] = std::max(t.hi[i], boxes[b].hi[i]); }
+        pts[r] += boxes[b].numPts();
+        if (r == ctx->rank) local.push_back((int)b);
+    }
+    long long total = 0;
+    for (int r = 0; r < nr; ++r) {
+        if (cnt[r] == 0) SB_FAIL("rank " + std::to_string(r) + " owns no box");
+        if (pts[r] != tiles[r].numPts()) SB_FAIL("the boxes of one rank must tile a rectangle (horizontal box decomposition)");
+        total += pts[r];
+    }
+    if (total != domain.numPts()) SB_FAIL("boxes do not cover the domain (single-level operator)");
+    tile = tiles[ctx->rank];
+    lay  = makeLay(tile);
+
+    // What does each side of the tile touch?
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s) {
+            SideBC& sd = side[d][s];
+            sd = SideBC{SIDE_PHYS, 1, 0.0, 0.0, -1};
+            const bool atDom = s ? tile.hi[d] == domain.hi[d] : tile.lo[d] == domain.lo[d];
+            if (atDom && !periodic[d]) continue;
+            if (atDom && periodic[d] && tile.lo[d] == domain.lo[d] && tile.hi[d] == domain.hi[d]) { sd.kind = SIDE_PERIODIC_SELF; continue; }
+            // neighbour tile: same extents in the other directions, adjacent (or wrapped) in d
+            int want = s ? tile.hi[d] + 1 : tile.lo[d] - 1;
+            if (atDom) want = s ? domain.lo[d] : domain.hi[d];
+            int found = -1;
+            for (int r = 0; r < nr && found < 0; ++r) {
+                if (r == ctx->rank) continue;
+                const Box3& t = tiles[r];
+                bool ok = s ? t.lo[d] == want : t.hi[d] == want;
+                for (int o = 0; o < 3 && ok; ++o)
+                    if (o != d && (t.lo[o] != tile.lo[o] || t.hi[o] != tile.hi[o])) ok = false;
+                if (ok) found = r;
+            }
+            if (found < 0) SB_FAIL("rank tiles do not form a process grid (no neighbour across a tile side)");
+            sd.kind = SIDE_NEIGHBOR; sd.neighbor = found;
+        }
+
+    // device-side box list (tile-local indices) and reduction buffers
+    const int nl = nlocal();
+    std::vector<int> lh(6 * nl);
+    for (int b = 0; b < nl; ++b)
+        for (int i = 0; i < 3; ++i) {
+            lh[3 * b + i]          = boxes[local[b]].lo[i] - tile.lo[i];
+            lh[3 * nl + 3 * b + i] = boxes[local[b]].hi[i] - tile.lo[i];
+        }
+    SB_CUDA(cudaMalloc((void**)&boxLoHi, lh.size() * sizeof(int)));
+    SB_CUDA(cudaMemcpy(boxLoHi, lh.data(), lh.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMalloc((void**)&redPartial, k::reduce_partial_len(nl) * sizeof(double)));
+    SB_CUDA(cudaMalloc((void**)&redOut, 2 * nl * sizeof(double)));
+    SB_CUDA(cudaMalloc((void**)&pivotFlag, sizeof(int)));
+    SB_CUDA(cudaMemset(pivotFlag, 0, sizeof(int)));
+    if ((size_t)2 * nl + 16 > ctx->hpinLen) SB_FAIL("too many boxes per rank for the pinned scalar buffer");
+    SB_CUDA(cudaMalloc((void**)&mtab, 2 * (size_t)(lay.nx + lay.ny + lay.nz) * sizeof(double)));
+    SB_CUDA(cudaMalloc((void**)&loBC, (size_t)lay.sz * sizeof(double)));
+    SB_CUDA(cudaMalloc((void**)&hiBC, (size_t)lay.sz * sizeof(double)));
+    SB_CUDA(cudaMemset(loBC, 0, (size_t)lay.sz * sizeof(double)));
+    SB_CUDA(cudaMemset(hiBC, 0, (size_t)lay.sz * sizeof(double)));
+    // exchange buffers
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s)
+            if (side[d][s].kind == SIDE_NEIGHBOR) {
+                const size_t n = (size_t)(d == 0 ? lay.ny : lay.nx) * (d == 2 ? lay.ny : lay.nz);
+                for (int w = 0; w < 2; ++w) SB_CUDA(cudaMalloc((void**)&xbuf[d][s][w], n * sizeof(double)));
+            }
+}
+
+Op::~Op()
+{
+    cudaFree(J); cudaFree(Dinv);
+    for (int i = 0; i < 3; ++i) cudaFree(Jgup[i]);
+    cudaFree(mtab); cudaFree(loBC); cudaFree(hiBC); cudaFree(boxLoHi); cudaFree(redPartial); cudaFree(redOut); cudaFree(pivotFlag);
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s)
+            for (int w = 0; w < 2; ++w) cudaFree(xbuf[d][s][w]);
+}
+
+Coef Op::coef() const
+{
+    Coef c;
+    c.J = J; c.Dinv = Dinv;
+    c.mxl = mtab; c.mxr = mtab + lay.nx;
+    c.myl = mtab + 2 * lay.nx; c.myr = c.myl + lay.ny;
+    c.mzl = mtab + 2 * (lay.nx + lay.ny); c.mzr = c.mzl + lay.nz;
+    c.loBC = loBC; c.hiBC = hiBC; c.beta = beta;
+    return c;
+}
+BoxList Op::boxlist() const { return BoxList{nlocal(), boxLoHi, boxLoHi + 3 * nlocal()}; }
+
+// LevelGeometry::createMetricCache (LevelGeometry.cpp:238-277): per box, FABs grown by 4 ghosts,
+// each filled by GeoSourceInterface::fill_J / fill_Jgup, i.e. from 1-D dx/dXi tables whose xi is
+// accumulated from the grown box's small end.
+void Op::fillMetricFromMap()
+{
+    const int G = 4;
+    for (int lb = 0; lb < nlocal(); ++lb) {
+        const Box3& b = boxes[local[lb]];
+        std::vector<double> tab;
+        size_t off[6];
+        for (int mu = 0; mu < 3; ++mu) {
+            const int n = b.size(mu);
+            std::vector<double> c, f;
+            if (dim == 2 && mu == 1) { c.assign(n, 1.0); f.assign(n + 1, 1.0); }
+            else {
+                std::vector<double> cg = map.dxdXi(mu, dXi[mu], b.lo[mu] - G, n + 2 * G, 0);
+                std::vector<double> fg = map.dxdXi(mu, dXi[mu], b.lo[mu] - G, n + 2 * G + 1, 1);
+                c.assign(cg.begin() + G, cg.begin() + G + n);
+                f.assign(fg.begin() + G, fg.begin() + G + n + 1);
+            }
+            off[mu] = tab.size(); tab.insert(tab.end(), c.begin(), c.end());
+            off[3 + mu] = tab.size(); tab.insert(tab.end(), f.begin(), f.end());
+        }
+        double* dt = (double*)ctx->getScratch(tab.size() * sizeof(double));
+        SB_CUDA(cudaMemcpyAsync(dt, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+        int blo[3], bhi[3];
+        for (int i = 0; i < 3; ++i) { blo[i] = b.lo[i] - tile.lo[i]; bhi[i] = b.hi[i] - tile.lo[i]; }
+        k::fill_metric_box(st(), lay, blo, bhi, dt + off[0], dt + off[1], dt + off[2], dt + off[3], dt + off[4], dt + off[5], J,
+                           Jgup[0], Jgup[1], Jgup[2]);
+        ctx->sync();
+    }
+}
+
+// Coarsened operator (PoissonOp.cpp:334-405): grids, J (and Jgup) block-averaged from the finer
+// depth, matrix elements recomputed from the map at the coarse dXi.
+Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
+{
+    dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth + 1;
+    std::memcpy(periodic, f.periodic, sizeof(periodic));
+    std::memcpy(bcAlpha, f.bcAlpha, sizeof(bcAlpha));
+    std::memcpy(bcBeta, f.bcBeta, sizeof(bcBeta));
+    for (int d = 0; d < 3; ++d) dXi[d] = f.dXi[d] * (double)ref[d];
+    domain  = coarsen(f.domain, ref);
+    boxRank = f.boxRank;
+    boxes.resize(f.boxes.size());
+    for (size_t b = 0; b < boxes.size(); ++b) {
+        if (!coarsenable(f.boxes[b], ref)) SB_FAIL("Grids cannot be coarsened by the requested ref ratio");
+        boxes[b] = coarsen(f.boxes[b], ref);
+    }
+    setupLayout();
+    J = alloc();
+    k::restrict_avg(st(), f.lay, lay, ref, J, f.J);
+    for (int d = 0; d < 3; ++d) {
+        Jgup[d] = alloc();
+        if (dim == 2 && d == 1) continue;
+        k::restrict_face(st(), f.lay, lay, ref, d, Jgup[d], f.Jgup[d]);
+    }
+    hasNullSpace = f.hasNullSpace;
+    cacheMatrixElements();
+    finalized = true;
+}
+
+// PoissonOp::cacheMatrixElements (PoissonOp.cpp:510-665).
+void Op::cacheMatrixElements()
+{
+    std::vector<double> h(2 * (size_t)(lay.nx + lay.ny + lay.nz), 0.0);
+    size_t              off = 0;
+    for (int d = 0; d < 3; ++d) {
+        const int N = domain.size(d);
+        hM[d].assign(2 * (size_t)N, 0.0);
+        if (!(dim == 2 && d == 1)) {
+            // fill_dXidx = 1 / fill_dxdXi (GeoSourceInterface.cpp:228-243) over the flattened domain box
+            std::vector<double> fc = map.dxdXi(d, dXi[d], domain.lo[d], N + 1, 1);
+            std::vector<double> cc = map.dxdXi(d, dXi[d], domain.lo[d], N, 0);
+            for (auto& v : fc) v = 1.0 / v;
+            for (auto& v : cc) v = 1.0 / v;
+            // PoissonOpF.ChF:78-100
+            const double dxScale = 1.0 / (dXi[d] * dXi[d]);
+            for (int i = 0; i < N; ++i) {
+                const double c = dxScale * cc[i];
+                hM[d][i]       = c * fc[i];
+                hM[d][N + i]   = c * fc[i + 1];
+            }
+        }
+        const int n = d == 0 ? lay.nx : (d == 1 ? lay.ny : lay.nz);
+        const int o = tile.lo[d] - domain.lo[d];
+        for (int i = 0; i < n; ++i) { h[off + i] = hM[d][o + i]; h[off + n + i] = hM[d][N + o + i]; }
+        off += 2 * (size_t)n;
+    }
+    ctx->sync();
+    SB_CUDA(cudaMemcpy(mtab, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+
+    if (!Dinv) Dinv = alloc();
+    k::compute_dinv(st(), lay, coef(), alpha, Dinv, dim);
+
+    // Physical-boundary ghost-fill constants (BCTools.cpp:466-508: dx = dx/dXi * dXi at the
+    // boundary face; BCToolsF.ChF:222-337).
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s) {
+            SideBC& sd = side[d][s];
+            if (sd.kind != SIDE_PHYS || (dim == 2 && d == 1)) continue;
+            const int face = s ? domain.hi[d] + 1 : domain.lo[d];
+            const double dx = map.dxdXi(d, dXi[d], face, 1, 1, dXi[d])[0];
+            int minSize = std::numeric_limits<int>::max();
+            for (int lb : local) {
+                const Box3& b = boxes[lb];
+                if ((s ? b.hi[d] == domain.hi[d] : b.lo[d] == domain.lo[d])) minSize = std::min(minSize, b.size(d));
+            }
+            sd.twoCells = minSize >= 2;
+            sd.a  = sd.twoCells ? bcAlpha[d][s] / 8.0 : bcAlpha[d][s] / 2.0;
+            sd.bb = bcBeta[d][s] / dx;
+        }
+
+    if (relaxMethod == SB_RELAX_VERTLINE) {
+        if (tile.lo[2] != domain.lo[2] || tile.hi[2] != domain.hi[2])
+            SB_FAIL("Grids are not suitable for vertical line relaxation. Try setting base.splitDirs = 1 1 0 in 3D or 1 0 in 2D.");
+        for (const Box3& b : boxes)
+            if (b.lo[2] != domain.lo[2] || b.hi[2] != domain.hi[2])
+                SB_FAIL("Grids are not suitable for vertical line relaxation. Try setting base.splitDirs = 1 1 0 in 3D or 1 0 in 2D.");
+        // PoissonOpF.ChF:676-688
+        const double dz  = dXi[2];
+        const double sLo = (bcAlpha[2][0] - 2.0 * bcBeta[2][0] / dz) / (bcAlpha[2][0] + 2.0 * bcBeta[2][0] / dz);
+        const double sHi = (bcAlpha[2][1] - 2.0 * bcBeta[2][1] / dz) / (bcAlpha[2][1] + 2.0 * bcBeta[2][1] / dz);
+        if (periodic[2]) SB_FAIL("vertical line relaxation with a periodic vertical is not supported by the reference either");
+        k::compute_vert_bcs(st(), lay, coef(), sLo, sHi, loBC, hiBC);
+    }
+}
+
+// PoissonOp::checkForNullSpace (PoissonOp.cpp:670-696): L[1] == 0 to smallReal?
+bool Op::checkForNullSpace()
+{
+    double* ones = alloc();
+    double* L1   = alloc();
+    k::fill(st(), ones, lay.n, 1.0);
+    applyOp(L1, ones, true);
+    const double smallReal = 1.0e4 * std::numeric_limits<double>::epsilon();  // SOMAR_Constants.H:63
+    const double mx        = norm(L1, 0);
+    ctx->sync();
+    cudaFree(ones); cudaFree(L1);
+    return !(mx > smallReal);
+}
+
+void Op::finalize()
+{
+    cacheMatrixElements();
+    const double smallReal = 1.0e4 * std::numeric_limits<double>::epsilon();
+    // RealCmp::neq(alpha, 0) (SOMAR_Constants.H:94-105)
+    const bool alphaIsZero = std::abs(alpha - 0.0) <= smallReal * std::max(std::abs(alpha), 0.0);
+    hasNullSpace = alphaIsZero ? checkForNullSpace() : false;
+    finalized    = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LevelData::exchange(m_exCopier): faces only (Copier::trimEdges, PoissonOp.cpp:122-123);
+// periodic images are part of the copier.
+void Op::exchange(double* phi)
+{
+    SideBC only[3][2];
+    bool   any = false;
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s) {
+            only[d][s] = side[d][s];
+            if (only[d][s].kind == SIDE_PHYS) only[d][s].kind = -1;
+            if (only[d][s].kind == SIDE_PERIODIC_SELF) any = true;
+        }
+    if (any) k::fill_ghosts(st(), lay, phi, only, dim);
+    if (ctx->nranks > 1) ctx->comm->exchangeFaces(*this, phi);
+}
+
+// PoissonOp::applyBCs (PoissonOp.H:139-163, PoissonOp.cpp:726-763): exchange, (no CFI on a
+// single level), physical BCs.
+void Op::applyBCs(double* phi, bool homog)
+{
+    if (!homog) SB_FAIL("inhomogeneous BCs are not part of the projection path (HomogNeumBC)");
+    k::fill_ghosts(st(), lay, phi, side, dim);
+    if (ctx->nranks > 1) ctx->comm->exchangeFaces(*this, phi);
+}
+void Op::applyBCsWithEdges(double* phi)
+{
+    if (ctx->nranks > 1) SB_FAIL("quadratic prolongation across ranks is not implemented yet");
+    k::fill_ghosts_with_edges(st(), lay, phi, side, dim);
+}
+
+void Op::applyOp(double* lhs, double* phi, bool homog)
+{
+    applyBCs(phi, homog);
+    k::apply_op(st(), lay, coef(), lhs, phi);
+}
+void Op::residual(double* res, double* phi, const double* rhs, bool homog)
+{
+    applyBCs(phi, homog);
+    k::residual(st(), lay, coef(), res, phi, rhs);
+}
+
+void Op::checkPivot()
+{
+    int flag = 0;
+    SB_CUDA(cudaMemcpyAsync(&flag, pivotFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    ctx->sync();
+    if (flag) {
+        SB_CUDA(cudaMemset(pivotFlag, 0, sizeof(int)));
+        SB_FAIL("vertical line relaxation met a column where LAPACK dgtsv pivots or is singular (flag " + std::to_string(flag) +
+                "); the B200 path does not reproduce that branch");
+    }
+}
+
+// PoissonOp::relax (PoissonOp.cpp:917-955) and the relaxers behind it.
+void Op::relax(double* cor, const double* res, int iters)
+{
+    switch (relaxMethod) {
+        case SB_RELAX_NONE: break;
+        case SB_RELAX_GSRB:  // PoissonOp.cpp:1833-1870
+            for (int it = 0; it < iters; ++it) {
+                applyBCs(cor, true);
+                k::gsrb_pass(st(), lay, coef(), cor, res, 0);
+                exchange(cor);
+                k::gsrb_pass(st(), lay, coef(), cor, res, 1);
+            }
+            break;
+        case SB_RELAX_VERTLINE: {  // PoissonOp.cpp:1927-2010
+            if (iters == 0) return;
+            const size_t n  = (size_t)((lay.nx + 1) / 2) * lay.ny * lay.nz;
+            double*      wd = (double*)ctx->getScratch(2 * n * sizeof(double));
+            double*      wb = wd + n;
+            for (int it = 0; it < iters; ++it)
+                for (int pass = 0; pass < 2; ++pass) {
+                    if (pass == 0) applyBCs(cor, true);
+                    else exchange(cor);
+                    k::vertline_pass(st(), lay, coef(), cor, res, pass, wd, wb, pivotFlag);
+                }
+            break;
+        }
+        case SB_RELAX_JACOBI: {  // PoissonOp.cpp:1709-1735
+            double* r = (double*)ctx->getScratch(lay.n * sizeof(double));
+            for (int it = 0; it < iters; ++it) {
+                residual(r, cor, res, true);
+                k::jacobi(st(), lay, coef(), cor, r, -1);
+            }
+            break;
+        }
+        case SB_RELAX_JACOBIRB: {  // PoissonOp.cpp:1741-1775
+            double* r = (double*)ctx->getScratch(lay.n * sizeof(double));
+            for (int it = 0; it < iters; ++it)
+                for (int pass = 0; pass < 2; ++pass) {
+                    residual(r, cor, res, true);
+                    k::jacobi(st(), lay, coef(), cor, r, pass);
+                }
+            break;
+        }
+        default: SB_FAIL("relaxation method " + std::to_string(relaxMethod) + " is not available on the B200 path (sequential GS cannot be parallelised bit-faithfully)");
+    }
+}
+
+// PoissonOp::preCond (PoissonOp.cpp:893-911)
+void Op::preCond(double* phi, const double* rhs, int relaxIters)
+{
+    k::mult_valid(st(), lay, phi, rhs, Dinv);
+    relax(phi, rhs, relaxIters);
+}
+
+// PoissonOp::removeKernel (PoissonOp.cpp:821-846) -> Integral::sum (Integral.cpp:249-267)
+void Op::removeKernel(double* phi)
+{
+    if (!hasNullSpace) return;
+    const double dv = dXi[0] * dXi[1] * dXi[2];
+    k::reduce_boxes(st(), lay, boxlist(), 4, phi, J, dim == 2 ? dXi[0] * dXi[2] : dv, redPartial, redOut);
+    const int nl = nlocal();
+    if (ctx->nranks == 1 && nl == 1) {
+        k::add_scalar_valid(st(), lay, phi, redOut);
+        return;
+    }
+    SB_CUDA(cudaMemcpyAsync(ctx->hpin, redOut, 2 * nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    ctx->sync();
+    double sv[2] = {0.0, 0.0};
+    for (int b = 0; b < nl; ++b) { sv[0] += ctx->hpin[2 * b]; sv[1] += ctx->hpin[2 * b + 1]; }
+    ctx->allreduceSum(sv, 2);
+    ctx->hpin[0] = sv[0]; ctx->hpin[1] = sv[1];
+    SB_CUDA(cudaMemcpyAsync(redOut, ctx->hpin, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    k::add_scalar_valid(st(), lay, phi, redOut);
+    ctx->sync();  // hpin is reused by the next reduction
+}
+
+// StateOps::norm (LDFABOps.cpp:134-164) with FArrayBox::norm (FArrayBox.cpp:56-150)
+double Op::norm(const double* x, int p, double powScale)
+{
+    if (p < 0 || p > 2) SB_FAIL("norm type must be 0, 1 or 2");
+    const int nl = nlocal();
+    k::reduce_boxes(st(), lay, boxlist(), p, x, nullptr, 0.0, redPartial, redOut);
+    SB_CUDA(cudaMemcpyAsync(ctx->hpin, redOut, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    ctx->sync();
+    double ret = 0.0;
+    for (int b = 0; b < nl; ++b) {
+        const double numPts = (double)boxes[local[b]].numPts();
+        double       boxVal;
+        if (p == 0) boxVal = ctx->hpin[b];
+        else if (p == 1) boxVal = ctx->hpin[b] / numPts;
+        else boxVal = std::sqrt(ctx->hpin[b] / numPts);
+        if (p == 0) ret = std::max(ret, boxVal);
+        else ret += std::pow(boxVal, p);
+    }
+    if (p == 0) { ctx->allreduceMax(&ret, 1); }
+    else {
+        ctx->allreduceSum(&ret, 1);
+        ret = std::pow(ret * powScale, 1.0 / (double)p);
+    }
+    return ret;
+}
+
+// StateOps::dotProduct (LDFABOps.cpp:98-121)
+double Op::dotProduct(const double* a, const double* b)
+{
+    const int nl = nlocal();
+    k::reduce_boxes(st(), lay, boxlist(), 3, a, b, 0.0, redPartial, redOut);
+    SB_CUDA(cudaMemcpyAsync(ctx->hpin, redOut, nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    ctx->sync();
+    double val = 0.0;
+    for (int i = 0; i < nl; ++i) val += ctx->hpin[i];
+    ctx->allreduceSum(&val, 1);
+    return val;
+}
+
+// PoissonOp::MGRestrict (PoissonOp.cpp:993-1018)
+void Op::MGRestrict(Op& crse, double* crseRes, const double* fineRes)
+{
+    int ref[3];
+    for (int d = 0; d < 3; ++d) ref[d] = domain.size(d) / crse.domain.size(d);
+    k::restrict_avg(st(), lay, crse.lay, ref, crseRes, fineRes);
+}
+
+// PoissonOp::MGProlong (PoissonOp.cpp:1032-1152)
+void Op::MGProlong(Op& crse, double* finePhi, double* crseCor, int order)
+{
+    int ref[3];
+    for (int d = 0; d < 3; ++d) ref[d] = domain.size(d) / crse.domain.size(d);
+    if (order >= 1) {
+        crse.applyBCs(crseCor, true);
+        k::prolong_linear(st(), lay, crse.lay, ref, finePhi, crseCor);  // constant + slopes
+    } else {
+        k::prolong_const(st(), lay, crse.lay, ref, finePhi, crseCor);
+    }
+    if (order >= 2) {
+        bool noRoom = false;  // "Is there room for the stencil?" :1095-1104
+        for (const Box3& b : crse.boxes)
+            for (int d = 0; d < 3; ++d)
+                if (!(dim == 2 && d == 1) && b.size(d) < 4) noRoom = true;
+        if (!noRoom) {
+            k::prolong_quad1(st(), lay, crse.lay, ref, finePhi, crseCor);
+            crse.applyBCsWithEdges(crseCor);
+            k::prolong_quad2(st(), lay, crse.lay, ref, finePhi, crseCor, dim);
+        }
+    }
+    removeKernel(finePhi);
+}
+
+// PoissonOp::levelDivergence (PoissonOp.cpp:1568-1610)
+void Op::levelDivergence(double* div, double* const vel[3])
+{
+    const double m[3] = {1.0 / dXi[0], 1.0 / dXi[1], 1.0 / dXi[2]};  // mult/dXi with mult = 1
+    k::divergence(st(), lay, div, vel[0], vel[1], vel[2], m[0], m[1], m[2], dim);
+}
+
+// PoissonOp::levelGradient (PoissonOp.cpp:1486-1545)
+void Op::levelGradient(double* const grad[3], double* phi, bool homog)
+{
+    applyBCs(phi, homog);
+    const double smallReal = 1.0e4 * std::numeric_limits<double>::epsilon();
+    const bool   scaleBeta = !(std::abs(beta - 1.0) <= smallReal * std::max(std::abs(beta), 1.0));
+    for (int d = 0; d < 3; ++d) {
+        if (dim == 2 && d == 1) continue;
+        k::gradient(st(), lay, grad[d], phi, Jgup[d], d, 1.0 / dXi[d], beta, scaleBeta);
+    }
+}
+
+}  // namespace sb
