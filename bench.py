@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- pressure-solve throughput of the B200 path: DOF/s per V-cycle on the synthetic
+stratified 3-D Poisson problem S5 (1024 x 1024 x 256, fp64, 64 boxes of 128 x 128 x 256,
+vertical-line relaxation), BASELINE.json's headline metric and configuration.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched with torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one outer-iteration body of MGSolver::vCycle (reference MGSolverI.H:342-347):
+preCond(cor, res) then vCycle_residualEq(cor, res, depth 0) with the reference's default
+smoothing (16 down + 16 up line relaxations per depth, 2 at the bottom, BiCGStab bottom solve).
+`value` times K steps with the residual resident in HBM; `e2e` is the same step called with host
+buffers (pinned): residual H2D, V-cycle, correction D2H.  The fields (2.2 GB each) are far larger
+than the 126 MB L2, so no explicit flush is needed between steps.
+
+The reference arm times the reference's own CPU code (oracle/_ref: SOMAR's unmodified C++ solver
+stack) on one S5 box (128 x 128 x 256, same dXi) per host core, all cores at once -- the
+reference parallelises by MPI rank over boxes and there is no MPI here, so independent copies
+stand in for ranks (an upper bound: no halo exchange is paid).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX = (1024, 1024, 256)
+LDOM = (16.0, 16.0, 1.0)
+BOX = (128, 128, 0)
+BLOCK_FACTOR = 16
+METRIC = "pressure-solve DOF/s per V-cycle"
+UNIT = "DOF/s"
+# algorithmic bytes per cell of one full line-relaxation iteration (both colours): SURVEY.md 8(d)
+RELAX_BYTES_PER_CELL_ITER = 40.0
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                t = [x.strip() for x in line.split(",")]
+                if len(t) < 9:
+                    continue
+                try:
+                    sm.append(float(t[1]))
+                    mx.append(float(t[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def synthetic_residual(lo, hi, dXi, seed):
+    """RHS-B of SURVEY.md 8(d) on one tile: divergence of a sheared, noisy, stratified face velocity
+    (u = tanh shear + noise, v = noise, w = noise under a Gaussian pycnocline envelope; no flow
+    through the domain walls).  Cartesian map: the advecting velocity equals the Cartesian one."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    n = [int(h - l + 1) for l, h in zip(lo, hi)]
+    z_c = (np.arange(lo[2], hi[2] + 1) + 0.5) * dXi[2]
+    z_f = np.arange(lo[2], hi[2] + 2) * dXi[2]
+    res = np.zeros(n, order="F")
+    # d/dx of u
+    u = 0.05 * (2.0 * rng.random((n[0] + 1, n[1], n[2]), dtype=np.float64) - 1.0)
+    u += np.tanh((z_c + 0.2) / 0.1)[None, None, :]
+    if lo[0] == 0:
+        u[0] = 0.0
+    if hi[0] == NX[0] - 1:
+        u[-1] = 0.0
+    res += (u[1:] - u[:-1]) * (1.0 / dXi[0])
+    del u
+    v = 0.05 * (2.0 * rng.random((n[0], n[1] + 1, n[2]), dtype=np.float64) - 1.0)
+    if lo[1] == 0:
+        v[:, 0] = 0.0
+    if hi[1] == NX[1] - 1:
+        v[:, -1] = 0.0
+    res += (v[:, 1:] - v[:, :-1]) * (1.0 / dXi[1])
+    del v
+    w = 0.05 * (2.0 * rng.random((n[0], n[1], n[2] + 1), dtype=np.float64) - 1.0)
+    w *= np.exp(-((z_f + 0.2) / 0.1) ** 2)[None, None, :]
+    w[:, :, 0] = 0.0
+    w[:, :, -1] = 0.0
+    res += (w[:, :, 1:] - w[:, :, :-1]) * (1.0 / dXi[2])
+    return res
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    import somar_b200 as sb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N > 1 with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = sb.Context(local, rank, world)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(sb.Context.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.init_comm(bytes(idt.cpu().numpy().tobytes()))
+
+    nx = np.array(NX)
+    dXi = np.array(LDOM) / nx
+    lo = np.array([0, 0, -NX[2]])
+    hi = lo + nx - 1
+    blo, bhi = sb.make_base_grids(lo, hi, BOX, (1, 1, 0), BLOCK_FACTOR)
+    ranks = sb.assign_boxes_to_ranks(blo, bhi, world)
+    op = sb.PoissonOp(ctx, lo, hi, dXi, blo, bhi, box_rank=ranks, relax_method=sb.RELAX_VERTLINE)
+    opt = sb.default_options()  # reference defaults: 16/16/2 smooths, FMG outer loop, BiCGStab bottom
+    solver = sb.MGSolver(op, opt)
+    sched = solver.schedule
+
+    mine = ranks == rank
+    tlo, thi = blo[mine].min(axis=0), bhi[mine].max(axis=0)
+    ncell_tile = int(np.prod(thi - tlo + 1))
+    ncell = int(np.prod(nx))
+    res_h = torch.empty(ncell_tile, dtype=torch.float64, pin_memory=True)
+    cor_h = torch.empty(ncell_tile, dtype=torch.float64, pin_memory=True)
+    res_np = res_h.numpy().reshape(tuple(int(v) for v in thi - tlo + 1), order="F")
+    res_np[...] = synthetic_residual(tlo, thi, dXi, 20250829 + rank)
+
+    res, cor = op.field(), op.field()
+    res.upload_ptr(res_h.data_ptr(), tlo, thi)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def step():
+        op.preCond(cor, res, 0)
+        solver.vcycle(cor, res)
+
+    def step_e2e():
+        res.upload_ptr(res_h.data_ptr(), tlo, thi)
+        op.preCond(cor, res, 0)
+        solver.vcycle(cor, res)
+        cor.download_ptr(cor_h.data_ptr(), tlo, thi)
+
+    def timed(fn, steps):
+        barrier()
+        l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        for _ in range(steps):
+            fn()
+        ms = ctx.timer_stop()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        launches = ctx.launch_count() - l0
+        if dist is not None:
+            t = torch.tensor([ms, wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1])
+        return ms, wall, launches
+
+    if args.profile_mode:
+        step()
+        ms, wall_ms, launches = timed(step, args.steps)
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "ms_per_step_under_profiler": ms / args.steps, "gpu_launches": launches}))
+        return
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, wall_ms, launches = timed(step, args.steps)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # per-kernel accounting of the dominant kernel (line relaxation, depth 0) over one more step
+    ctx.profile(True)
+    step()
+    ctx.profile(False)
+    k_ms, k_n = ctx.profile_get("vertline@0")
+    r_ms, r_n = ctx.profile_get("residual@0")
+    tot_line = sum(ctx.profile_get(f"vertline@{d}")[0] for d in range(len(sched)))
+
+    # end to end with host buffers
+    step_e2e()
+    e_ms, e_wall, _ = timed(step_e2e, max(1, min(args.steps, 3)))
+    e_steps = max(1, min(args.steps, 3))
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        ms_per_step = ms / args.steps
+        value = ncell / (ms_per_step * 1e-3)
+        cells_per_launch = ncell_tile  # one colour pass sweeps the whole tile (half the columns are solved)
+        launch_ms = k_ms / max(k_n, 1)
+        achieved = (RELAX_BYTES_PER_CELL_ITER / 2.0) * cells_per_launch / (launch_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "S5 synthetic stratified 3D Poisson 1024x1024x256 fp64, 64 boxes 128x128x256, "
+                                   "VERTLINE relaxation, one preCond + vCycle_residualEq(depth 0) per step, reference default "
+                                   "smoothing 16+16 (2 bottom) + BiCGStab bottom",
+                       "mg_schedule": [list(r) for r in sched], "decomposition": f"{world} horizontal tile(s)",
+                       "l2": "fields (2.2 GB each) exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": ncell / (e_wall / e_steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * ncell_tile * world,
+                    "d2h_bytes_per_step": 8 * ncell_tile * world, "ms_per_step": e_wall / e_steps,
+                    "what": "residual from pinned host -> device, preCond + V-cycle, correction -> pinned host"},
+            "gpu_launches": launches,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "roofline": {"bound": "hbm", "kernel": "vertline_k (one colour pass of vertical line relaxation, depth 0)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "launch_ms": launch_ms, "launches_timed": k_n,
+                         "algorithmic_bytes_per_launch": (RELAX_BYTES_PER_CELL_ITER / 2.0) * cells_per_launch,
+                         "share_of_step": tot_line / (ms_per_step if ms_per_step > 0 else 1.0),
+                         "residual_launch_ms": r_ms / max(r_n, 1)},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(cores=None, reps=1)
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ref_binary():
+    return os.path.join(ROOT, "oracle", "_ref", "d3", "somar_ref")
+
+
+def _run_ref_copies(cores, reps, td):
+    """`cores` concurrent copies of the reference's V-cycle on one S5 box; returns per-copy time lists."""
+    import numpy as np
+    n = (BOX[0], BOX[1], NX[2])
+    L = (LDOM[0] * n[0] / NX[0], LDOM[1] * n[1] / NX[1], LDOM[2])
+    procs = []
+    for c in range(cores):
+        out = os.path.join(td, f"c{c}")
+        cmd = [ref_binary(), os.path.join(ROOT, "oracle", "decks", "base3d.inputs"),
+               f"base.nx={n[0]} {n[1]} {n[2]}", f"base.L={L[0]} {L[1]} {L[2]}", f"base.nxOffset=0 0 {-n[2]}",
+               f"base.maxBaseGridSize={BOX[0]} {BOX[1]} 0", f"base.blockFactor={BLOCK_FACTOR}", "proj.relaxMethod=6",
+               "drv.mode=vcycle", "drv.useMGSolver=1", f"drv.reps={reps}", f"drv.out={out}"]
+        procs.append((out, subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)))
+    times = []
+    for out, p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("oracle/_ref/d3/somar_ref failed")
+        data = np.fromfile(out + ".bin")
+        for line in open(out + ".txt"):
+            t = line.split()
+            if t[:2] == ["array", "vcycleTimes"]:
+                times.append(data[int(t[2]):int(t[2]) + int(t[3])])
+    return n, np.array(times)
+
+
+def cpu_baseline(cores=None, reps=1):
+    if not os.path.exists(ref_binary()):
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/d3/somar_ref not built"}
+    cores = cores or min(os.cpu_count() or 1, 32)
+    with tempfile.TemporaryDirectory() as td:
+        n, t = _run_ref_copies(cores, reps, td)
+    ncell = n[0] * n[1] * n[2]
+    per_copy = t.mean(axis=1)  # seconds per V-cycle of each copy
+    value = float(sum(ncell / s for s in per_copy))
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{cores} concurrent copies (1 per core, no MPI available) of the reference's vCycle_residualEq on one S5 box "
+                      f"{n[0]}x{n[1]}x{n[2]} (same dXi, same 16+16 smoothing), {reps} V-cycle(s) each; "
+                      f"{float(per_copy.mean()):.2f} s per V-cycle per core"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not os.path.exists(ref_binary()):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/d3/somar_ref not built (needs /root/reference at build time)"}))
+        return
+    cores = min(os.cpu_count() or 1, 32)
+    warm, steps = max(args.warmup, 0), max(args.steps, 1)
+    # bounded: each step is one V-cycle on one box per core (~10 s); cap the total
+    warm, steps = min(warm, 1), min(steps, 3)
+    t0 = time.perf_counter()
+    with tempfile.TemporaryDirectory() as td:
+        n, t = _run_ref_copies(cores, warm + steps, td)
+    ncell = n[0] * n[1] * n[2]
+    t = t[:, warm:]
+    per_copy = t.mean(axis=1)
+    value = float(sum(ncell / s for s in per_copy))
+    sample = (f"{cores} concurrent copies (1 per core; the reference is MPI-only and there is no MPI here) of the reference's "
+              f"preCond + vCycle_residualEq on one S5 box {n[0]}x{n[1]}x{n[2]} (same dXi and smoothing); {steps} timed V-cycles each")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": float(per_copy.mean() * 1e3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "S5 synthetic stratified 3D Poisson, per-box sample (see cpu_baseline.sample), VERTLINE, "
+                               "reference default smoothing 16+16 (2 bottom) + BiCGStab bottom"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="for runs under ncu: one warm-up step, K timed steps, no e2e / cpu legs (numbers printed are not bench values)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,12 @@ int sb_context_destroy(sb_context* ctx);
 int sb_context_sync(sb_context* ctx);
 /* Number of kernels this library launched on the context's stream since creation. */
 long long sb_context_launch_count(sb_context* ctx);
+/* CUDA-event stopwatch on the context's stream (what bench.py times with), and optional
+ * per-kernel accounting: keys are "<kernel>@<depth>" with kernel in {vertline, gsrb, residual}. */
+int sb_context_timer_start(sb_context* ctx);
+int sb_context_timer_stop(sb_context* ctx, double* ms);
+int sb_context_profile(sb_context* ctx, int enable);
+int sb_context_profile_get(sb_context* ctx, const char* key, double* total_ms, long long* count);
 /* NCCL communicator for halo exchange and scalar reductions (stands in for Chombo's MPI layer,
  * BoxTools/BoxLayoutDataI.H:665-812, BaseTools/Comm.cpp:19,41).  id is ncclUniqueId (128 B). */
 int sb_comm_get_unique_id(void* id128);

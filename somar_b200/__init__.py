@@ -78,7 +78,8 @@ def process_grid(nranks, nbx, nby):
         py = nranks // px
         if nbx % px or nby % py:
             continue
-        score = abs(np.log((nbx / px) / max(nby / py, 1e-9)))
+        # as square as possible; ties go to splitting y (x rows stay long and contiguous)
+        score = abs(np.log((nbx / px) / max(nby / py, 1e-9))) + (1e-6 if px > py else 0.0)
         if best is None or score < best[0]:
             best = (score, px, py)
     if best is None:
@@ -133,6 +134,22 @@ class Context:
     def sync(self):
         capi.check(self.lib.sb_context_sync(self.h))
 
+    def timer_start(self):
+        capi.check(self.lib.sb_context_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        capi.check(self.lib.sb_context_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile(self, enable=True):
+        capi.check(self.lib.sb_context_profile(self.h, int(enable)))
+
+    def profile_get(self, key):
+        ms, n = C.c_double(), C.c_longlong()
+        capi.check(self.lib.sb_context_profile_get(self.h, key.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def launch_count(self):
         return int(self.lib.sb_context_launch_count(self.h))
 
@@ -157,6 +174,17 @@ class Field:
         if self.centering >= 0:
             hi[self.centering] += 1
         return lo, hi
+
+    def upload_ptr(self, ptr, lo=None, hi=None):
+        """Upload from a raw host pointer (e.g. a pinned torch tensor) laid out as the box [lo, hi]."""
+        if lo is None:
+            lo, hi = self.box()
+        capi.check(self.lib.sb_field_upload(self.h, C.cast(ptr, capi.DP), _i3(lo), _i3(hi)))
+
+    def download_ptr(self, ptr, lo=None, hi=None):
+        if lo is None:
+            lo, hi = self.box()
+        capi.check(self.lib.sb_field_download(self.h, C.cast(ptr, capi.DP), _i3(lo), _i3(hi)))
 
     def upload(self, arr, lo=None, hi=None):
         if lo is None:

@@ -94,6 +94,10 @@ PROTOTYPES = {
     "sb_context_destroy": (C.c_int, [P]),
     "sb_context_sync": (C.c_int, [P]),
     "sb_context_launch_count": (C.c_longlong, [P]),
+    "sb_context_timer_start": (C.c_int, [P]),
+    "sb_context_timer_stop": (C.c_int, [P, DP]),
+    "sb_context_profile": (C.c_int, [P, C.c_int]),
+    "sb_context_profile_get": (C.c_int, [P, C.c_char_p, DP, C.POINTER(C.c_longlong)]),
     "sb_comm_get_unique_id": (C.c_int, [C.c_void_p]),
     "sb_comm_init": (C.c_int, [P, C.c_void_p]),
     "sb_op_create": (C.c_int, [P, C.POINTER(LevelDesc), PP]),

@@ -41,6 +41,44 @@ int sb_comm_init(sb_context* ctx, const void* id128)
     SB_END
 }
 
+int sb_context_timer_start(sb_context* ctx)
+{
+    SB_TRY REQ(ctx);
+    Context& c = ctx->c;
+    if (!c.tm0) { SB_CUDA(cudaEventCreate(&c.tm0)); SB_CUDA(cudaEventCreate(&c.tm1)); }
+    SB_CUDA(cudaEventRecord(c.tm0, c.st));
+    SB_END
+}
+int sb_context_timer_stop(sb_context* ctx, double* ms)
+{
+    SB_TRY REQ(ctx); REQ(ms);
+    Context& c = ctx->c;
+    if (!c.tm0) SB_FAIL("timer not started");
+    SB_CUDA(cudaEventRecord(c.tm1, c.st));
+    SB_CUDA(cudaEventSynchronize(c.tm1));
+    float f = 0;
+    SB_CUDA(cudaEventElapsedTime(&f, c.tm0, c.tm1));
+    *ms = f;
+    SB_END
+}
+int sb_context_profile(sb_context* ctx, int enable)
+{
+    SB_TRY REQ(ctx);
+    ctx->c.profResolve();
+    if (enable) ctx->c.prof.clear();
+    ctx->c.profiling = enable != 0;
+    SB_END
+}
+int sb_context_profile_get(sb_context* ctx, const char* key, double* total_ms, long long* count)
+{
+    SB_TRY REQ(ctx); REQ(key); REQ(total_ms); REQ(count);
+    ctx->c.profResolve();
+    auto it = ctx->c.prof.find(key);
+    *total_ms = it == ctx->c.prof.end() ? 0.0 : it->second.ms;
+    *count    = it == ctx->c.prof.end() ? 0 : it->second.count;
+    SB_END
+}
+
 // ---- PoissonOp ------------------------------------------------------------------------------
 int sb_op_create(sb_context* ctx, const sb_level_desc* desc, sb_op** op)
 {

@@ -20,6 +20,14 @@ struct Context {
     size_t       scratchBytes = 0;
     Comm*        comm = nullptr;
     long long    launches0 = 0;
+    // optional per-kernel timing (CUDA events on `st` around selected launches)
+    bool         profiling = false;
+    struct ProfRec { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; double ms = 0; long long count = 0; };
+    std::map<std::string, ProfRec> prof;
+    cudaEvent_t  tm0 = nullptr, tm1 = nullptr;  // sb_context_timer_start/stop
+    void profBegin(const char* key, int depth, cudaEvent_t* e0);
+    void profEnd(const char* key, int depth, cudaEvent_t e0);
+    void profResolve();
 
     Context(int dev, int rank, int nranks);
     ~Context();

@@ -30,6 +30,36 @@ Context::~Context()
     if (hpin) cudaFreeHost(hpin);
     if (st) cudaStreamDestroy(st);
 }
+void Context::profBegin(const char*, int, cudaEvent_t* e0)
+{
+    *e0 = nullptr;
+    if (!profiling) return;
+    SB_CUDA(cudaEventCreate(e0));
+    SB_CUDA(cudaEventRecord(*e0, st));
+}
+void Context::profEnd(const char* key, int depth, cudaEvent_t e0)
+{
+    if (!profiling || !e0) return;
+    cudaEvent_t e1;
+    SB_CUDA(cudaEventCreate(&e1));
+    SB_CUDA(cudaEventRecord(e1, st));
+    prof[std::string(key) + "@" + std::to_string(depth)].ev.emplace_back(e0, e1);
+}
+void Context::profResolve()
+{
+    sync();
+    for (auto& kv : prof) {
+        for (auto& pr : kv.second.ev) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, pr.first, pr.second);
+            kv.second.ms += ms;
+            kv.second.count += 1;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        kv.second.ev.clear();
+    }
+}
 void* Context::getScratch(size_t bytes)
 {
     if (bytes > scratchBytes) {
@@ -436,7 +466,10 @@ void Op::applyOp(double* lhs, double* phi, bool homog)
 void Op::residual(double* res, double* phi, const double* rhs, bool homog)
 {
     applyBCs(phi, homog);
+    cudaEvent_t e0;
+    ctx->profBegin("residual", depth, &e0);
     k::residual(st(), lay, coef(), res, phi, rhs);
+    ctx->profEnd("residual", depth, e0);
 }
 
 void Op::checkPivot()
@@ -458,10 +491,15 @@ void Op::relax(double* cor, const double* res, int iters)
         case SB_RELAX_NONE: break;
         case SB_RELAX_GSRB:  // PoissonOp.cpp:1833-1870
             for (int it = 0; it < iters; ++it) {
+                cudaEvent_t e0;
                 applyBCs(cor, true);
+                ctx->profBegin("gsrb", depth, &e0);
                 k::gsrb_pass(st(), lay, coef(), cor, res, 0);
+                ctx->profEnd("gsrb", depth, e0);
                 exchange(cor);
+                ctx->profBegin("gsrb", depth, &e0);
                 k::gsrb_pass(st(), lay, coef(), cor, res, 1);
+                ctx->profEnd("gsrb", depth, e0);
             }
             break;
         case SB_RELAX_VERTLINE: {  // PoissonOp.cpp:1927-2010
@@ -473,7 +511,10 @@ void Op::relax(double* cor, const double* res, int iters)
                 for (int pass = 0; pass < 2; ++pass) {
                     if (pass == 0) applyBCs(cor, true);
                     else exchange(cor);
+                    cudaEvent_t e0;
+                    ctx->profBegin("vertline", depth, &e0);
                     k::vertline_pass(st(), lay, coef(), cor, res, pass, wd, wb, pivotFlag);
+                    ctx->profEnd("vertline", depth, e0);
                 }
             break;
         }

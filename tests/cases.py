@@ -71,6 +71,6 @@ def rand_velocity(c, seed):
 
 
 def rel_err(a, b):
-    a, b = np.asarray(a).ravel(), np.asarray(b).ravel()
+    a, b = np.asarray(a).ravel(order="F"), np.asarray(b).ravel(order="F")
     den = np.max(np.abs(b))
     return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
