@@ -138,6 +138,11 @@ void jacobi(cudaStream_t st, const Lay& L, const Coef& c, double* phi, const dou
 void vertline_pass(cudaStream_t st, const Lay& L, const Coef& c, double* phi, const double* rhs, int pass,
                    double* wd, double* wb, int* pivotFlag);
 
+// shared-matrix fast path (see sb_kernels.cu); tab = [4][nz]
+size_t vertline_smem_bytes(int nz);
+void vertline_smem_pass(cudaStream_t st, const Lay& L, const Coef& c, const double* tab, double* phi, const double* rhs, int pass);
+void j_deviation(cudaStream_t st, const Lay& L, const double* J, const double* jcol, double* out);
+
 void restrict_avg(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* crse, const double* fine);
 void prolong_const(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse);
 void prolong_linear(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse);

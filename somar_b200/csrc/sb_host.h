@@ -97,6 +97,8 @@ struct Op {
     double* redPartial = nullptr;
     double* redOut = nullptr;
     int*    pivotFlag = nullptr;
+    double* lineTab = nullptr;   // [4][nz] tables of the shared-matrix line relaxation (s, f, g, MzR)
+    bool    lineFast = false;
     std::vector<double> hM[3];  // host copies of the 1-D tables over the whole domain (2*N_d)
     double* xbuf[3][2][2] = {};  // exchange buffers [dir][side][send/recv]
 
@@ -108,6 +110,7 @@ struct Op {
     void    setupLayout();
     void    fillMetricFromMap();          // LevelGeometry::createMetricCache, LevelGeometry.cpp:238-277
     void    cacheMatrixElements();        // PoissonOp.cpp:510-665
+    void    buildLineTables(double sLo, double sHi);
     bool    checkForNullSpace();          // PoissonOp.cpp:670-696
     void    finalize();                   // setAlphaAndBeta, PoissonOp.cpp:707-718
     Coef    coef() const;

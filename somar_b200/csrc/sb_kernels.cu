@@ -386,6 +386,177 @@ void vertline_pass(cudaStream_t st, const Lay& L, const Coef& c, double* phi, co
 }
 
 // ------------------------------------------------------------------------------------------
+// Vertical line relaxation, fast path for columns that all share one tridiagonal matrix.
+//
+// Dividing row k of the reference's column system (PoissonOpF.ChF:905-955) by beta*J_k gives
+//   MzL_k x_{k-1} + (alpha/beta - h - MzL_k - MzR_k + bc_k) x_k + MzR_k x_{k+1}
+//        = rhs_k / (beta J_k) - (MxL phi_W + MxR phi_E + MyL phi_S + MyR phi_N),
+// with h = MxL+MxR+MyL+MyR of the column.  When the horizontal metric is uniform (h and
+// J/Jz(k) do not depend on i, j -- every Cartesian-horizontal grid, stretched or not in z) the
+// matrix is the same for every column and its Thomas factorisation is a 1-D table built once
+// per MG depth on the host (tab: s = 1/(beta J_k), f_k = MzL_{k+1}/d'_k, g_k = 1/d'_k, MzR_k).
+// A CTA owns 32 columns of one colour in one grid row: all warps build the right-hand sides
+// into shared memory (x-contiguous loads, every load independent), one warp runs the two
+// Thomas sweeps out of shared memory, so no intermediate ever goes to HBM and J/Dinv are not
+// read at all.  Same mathematics as dgtsv's no-pivot branch; rounding differs at 1e-16.
+// ------------------------------------------------------------------------------------------
+template <int NW, int U, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) vertline_smem_k(Lay L, Coef c, const double* __restrict__ tab,
+                                                          double* __restrict__ phi, const double* __restrict__ rhs, int pass, int dbg)
+{
+    extern __shared__ double sm[];  // [N][32] right-hand sides, then tables -f, g, -(MzR g) (3*N)
+    const int     N    = L.nz;
+    double* const sf   = sm + (size_t)N * 32;
+    double* const sg   = sf + N;
+    double* const sc   = sg + N;
+    const int     lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int     j    = blockIdx.y;
+    const int     i    = ((L.lo0 + L.lo1 + j + pass) & 1) + 2 * (blockIdx.x * 32 + lane);
+    const bool    act  = i < L.nx;
+    const int     ii   = act ? i : 0;
+    const double  mxl = c.mxl[ii], mxr = c.mxr[ii], myl = c.myl[j], myr = c.myr[j];
+    const double* ts  = tab;
+    for (int k = threadIdx.x; k < N; k += NW * 32) {
+        sf[k] = tab[N + k];
+        sg[k] = tab[2 * N + k];
+        sc[k] = tab[3 * N + k];
+    }
+    const long long sz = L.sz, sy = L.sy;
+    const double*   pq = phi + L.idx(ii, j, 0);
+    const double*   rq = rhs + L.idx(ii, j, 0);
+
+    // Phase 1: right-hand sides b_k = rhs_k s_k - (MxL phi_W + MxR phi_E + MyL phi_S + MyR phi_N).
+    // Each warp takes U consecutive levels per trip; the 5*U loads of trip t+1 are issued before
+    // trip t is consumed (register double buffer), so loads are in flight all the time.
+    double a0[U][5], a1[U][5];
+    auto   issue = [&](double(&a)[U][5], int k0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int       k = min(k0 + u, N - 1);
+            const long long o = (long long)k * sz;
+            if (dbg != 2) { a[u][0] = pq[o - 1]; a[u][1] = pq[o + 1]; a[u][2] = pq[o - sy]; a[u][3] = pq[o + sy]; a[u][4] = rq[o]; }
+            else { a[u][0] = a[u][1] = a[u][2] = a[u][3] = a[u][4] = (double)k; }
+        }
+    };
+    auto consume = [&](double(&a)[U][5], int k0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u;
+            if (k < N) {
+                const double lphi = mxl * a[u][0] + mxr * a[u][1] + myl * a[u][2] + myr * a[u][3];
+                sm[k * 32 + lane] = act ? a[u][4] * ts[k] - lphi : 0.0;
+            }
+        }
+    };
+    {
+        int k0 = w * U;
+        if (k0 < N) issue(a0, k0);
+        while (k0 < N) {
+            const int k1 = k0 + NW * U;
+            if (k1 < N) issue(a1, k1);
+            consume(a0, k0);
+            k0 = k1;
+            if (k0 >= N) break;
+            const int k2 = k0 + NW * U;
+            if (k2 < N) issue(a0, k2);
+            consume(a1, k0);
+            k0 = k2;
+        }
+    }
+    __syncthreads();
+    if (w != 0 || dbg == 1) return;
+
+    // Phase 2 (one warp, one column per lane): y_k = b_k - f_{k-1} y_{k-1}, z_k = y_k g_k parked
+    // in place; then x_{N-1} = z_{N-1}, x_k = z_k - (MzR_k g_k) x_{k+1}.  Batches of T levels:
+    // all shared-memory operands of a batch are in registers before its FMA chain starts.
+    constexpr int T = 8;
+    double*       col = sm + lane;
+    double        y   = col[0];
+    col[0]            = y * sg[0];
+    int k = 1;
+    for (; k + T <= N; k += T) {
+        double bb[T], ff[T], gg[T], zz[T];
+#pragma unroll
+        for (int u = 0; u < T; ++u) { bb[u] = col[(k + u) * 32]; ff[u] = sf[k + u - 1]; gg[u] = sg[k + u]; }
+#pragma unroll
+        for (int u = 0; u < T; ++u) { y = fma(ff[u], y, bb[u]); zz[u] = y * gg[u]; }
+#pragma unroll
+        for (int u = 0; u < T; ++u) col[(k + u) * 32] = zz[u];
+    }
+    for (; k < N; ++k) {
+        y           = fma(sf[k - 1], y, col[k * 32]);
+        col[k * 32] = y * sg[k];
+    }
+    __syncwarp();
+    double  x = col[(N - 1) * 32];
+    double* p = phi + L.idx(ii, j, N - 1);
+    if (act) *p = x;
+    k = N - 2;
+    for (; k - (T - 1) >= 0; k -= T) {
+        double zb[T], cg[T], xx[T];
+#pragma unroll
+        for (int u = 0; u < T; ++u) { zb[u] = col[(k - u) * 32]; cg[u] = sc[k - u]; }
+#pragma unroll
+        for (int u = 0; u < T; ++u) { x = fma(cg[u], x, zb[u]); xx[u] = x; }
+        if (act) {
+#pragma unroll
+            for (int u = 0; u < T; ++u) p[-(long long)(u + 1) * sz] = xx[u];
+        }
+        p -= (long long)T * sz;
+    }
+    for (; k >= 0; --k) {
+        x = fma(sc[k], x, col[k * 32]);
+        p -= sz;
+        if (act) *p = x;
+    }
+}
+
+size_t vertline_smem_bytes(int nz) { return ((size_t)nz * 32 + 3 * (size_t)nz) * sizeof(double); }
+void vertline_smem_pass(cudaStream_t st, const Lay& L, const Coef& c, const double* tab, double* phi, const double* rhs,
+                        int pass)
+{
+    static int dbg = -1; if (dbg < 0) { const char* e = getenv("SB_LINE_DEBUG"); dbg = e ? atoi(e) : 0; }
+    const int    hx = (L.nx + 1) / 2;
+    const size_t sh = vertline_smem_bytes(L.nz);
+    static int   variant = -1;
+    if (variant < 0) {
+        const char* e = getenv("SB_LINE_VARIANT");  // development knob: 0 = <8,4,2>, 1 = <4,8,2>, 2 = <8,2,3>
+        variant       = e ? atoi(e) : 0;
+    }
+#define SB_LAUNCH_VL(NW, U, MB)                                                                                         \
+    {                                                                                                                   \
+        static size_t configured = 0;                                                                                   \
+        if (sh > configured) {                                                                                          \
+            cudaFuncSetAttribute(vertline_smem_k<NW, U, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);     \
+            configured = sh;                                                                                            \
+        }                                                                                                               \
+        vertline_smem_k<NW, U, MB><<<dim3((hx + 31) / 32, L.ny), NW * 32, sh, st>>>(L, c, tab, phi, rhs, pass, dbg);        \
+    }
+    if (variant == 1) SB_LAUNCH_VL(4, 8, 2)
+    else if (variant == 2) SB_LAUNCH_VL(8, 2, 3)
+    else SB_LAUNCH_VL(8, 4, 2)
+#undef SB_LAUNCH_VL
+    LAUNCHED();
+}
+// max over the tile of |J(i,j,k) - Jcol[k]| / |Jcol[k]| (is the metric a function of z only?)
+__global__ void jdev_k(Lay L, const double* __restrict__ J, const double* __restrict__ jcol, double* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    double    v = 0.0;
+    if (i < L.nx && j < L.ny) v = fabs(J[L.idx(i, j, k)] - jcol[k]) / fabs(jcol[k]);
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax((unsigned long long*)out, (unsigned long long)__double_as_longlong(v));
+}
+void j_deviation(cudaStream_t st, const Lay& L, const double* J, const double* jcol, double* out)
+{
+    cudaMemsetAsync(out, 0, sizeof(double), st);
+    jdev_k<<<grid3(L.nx, L.ny, L.nz, B3), B3, 0, st>>>(L, J, jcol, out);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
 // Restriction: block average, sum in Fortran loop order (CFInterpF.ChF:1085-1120).
 // ------------------------------------------------------------------------------------------
 __global__ void restrict_k(Lay Lf, Lay Lc, int r0, int r1, int r2, double* __restrict__ crse, const double* __restrict__ fine)

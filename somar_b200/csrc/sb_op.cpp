@@ -257,6 +257,7 @@ Op::~Op()
 {
     cudaFree(J); cudaFree(Dinv);
     for (int i = 0; i < 3; ++i) cudaFree(Jgup[i]);
+    cudaFree(lineTab);
     cudaFree(mtab); cudaFree(loBC); cudaFree(hiBC); cudaFree(boxLoHi); cudaFree(redPartial); cudaFree(redOut); cudaFree(pivotFlag);
     for (int d = 0; d < 3; ++d)
         for (int s = 0; s < 2; ++s)
@@ -400,7 +401,79 @@ void Op::cacheMatrixElements()
         const double sHi = (bcAlpha[2][1] - 2.0 * bcBeta[2][1] / dz) / (bcAlpha[2][1] + 2.0 * bcBeta[2][1] / dz);
         if (periodic[2]) SB_FAIL("vertical line relaxation with a periodic vertical is not supported by the reference either");
         k::compute_vert_bcs(st(), lay, coef(), sLo, sHi, loBC, hiBC);
+        buildLineTables(sLo, sHi);
     }
+}
+
+// Fast path of the line relaxation (vertline_smem_k): usable when every column of this depth has
+// the same tridiagonal matrix after dividing each row by beta*J, i.e. when the horizontal metric
+// is uniform.  Decided from the data, not from the map kind: the 1-D off-diagonal tables must be
+// constant in x and y and J must be a function of z only (to 1e-13).  Builds the Thomas
+// factorisation of that matrix once (the dgtsv no-interchange recurrence, PoissonOpF.ChF:905-1002).
+void Op::buildLineTables(double sLo, double sHi)
+{
+    lineFast = false;
+    const char* force = getenv("SB_LINE_KERNEL");  // "general" disables the fast path (tests)
+    if (force && std::string(force) == "general") return;
+    const int N = lay.nz;
+    if (k::vertline_smem_bytes(N) > 200 * 1024 || beta == 0.0) return;
+    // h = MxL+MxR+MyL+MyR constant over the whole domain?
+    double hmin = 1e300, hmax = -1e300;
+    for (int d = 0; d < 2; ++d) {
+        if (dim == 2 && d == 1) continue;
+        const int Nd = domain.size(d);
+        double lo = 1e300, hi = -1e300;
+        for (int i = 0; i < Nd; ++i) {
+            const double v = hM[d][i] + hM[d][Nd + i];
+            lo = std::min(lo, v); hi = std::max(hi, v);
+        }
+        if (hi - lo > 1e-13 * std::abs(hi)) return;
+        (void)hmin; (void)hmax;
+    }
+    double h = hM[0][0] + hM[0][domain.size(0)];
+    if (dim == 3) h += hM[1][0] + hM[1][domain.size(1)];
+    // J(i,j,k) == J(0,0,k)?
+    std::vector<double> jcol(N);
+    ctx->sync();
+    SB_CUDA(cudaMemcpy2D(jcol.data(), sizeof(double), J + lay.idx(0, 0, 0), (size_t)lay.sz * sizeof(double), sizeof(double), N,
+                         cudaMemcpyDeviceToHost));
+    if (!lineTab) SB_CUDA(cudaMalloc((void**)&lineTab, 4 * (size_t)N * sizeof(double)));
+    SB_CUDA(cudaMemcpy(lineTab, jcol.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+    k::j_deviation(st(), lay, J, lineTab, redOut);
+    double dev = 0.0;
+    SB_CUDA(cudaMemcpyAsync(&dev, redOut, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    ctx->sync();
+    ctx->allreduceMax(&dev, 1);
+    if (!(dev <= 1e-13)) return;
+    if (ctx->nranks > 1) {  // every rank must use the same column of J: take rank 0's via max (values agree to 1e-13)
+        ctx->allreduceMax(jcol.data(), std::min(N, 64));
+        if (N > 64) for (int o = 64; o < N; o += 64) ctx->allreduceMax(jcol.data() + o, std::min(64, N - o));
+    }
+    const int           Nz = domain.size(2);
+    const double*       mzl = hM[2].data();
+    const double*       mzr = hM[2].data() + Nz;
+    std::vector<double> t(4 * (size_t)N);
+    double              dprev = 0.0;
+    for (int k = 0; k < N; ++k) {
+        double diag = alpha / beta - h - mzl[k] - mzr[k];
+        if (k == 0) diag += -mzl[0] * sLo;
+        if (k == N - 1) diag += -mzr[N - 1] * sHi;
+        double d = diag;
+        if (k > 0) {
+            if (!(std::abs(dprev) >= std::abs(mzl[k])) || dprev == 0.0) return;  // dgtsv would interchange rows
+            const double f = mzl[k] / dprev;
+            t[N + (k - 1)] = -f;
+            d              = diag - f * mzr[k - 1];
+        }
+        if (d == 0.0) return;
+        t[k]         = 1.0 / (beta * jcol[k]);
+        t[2 * N + k] = 1.0 / d;
+        t[3 * N + k] = -(mzr[k] * (1.0 / d));
+        dprev        = d;
+    }
+    t[N + (N - 1)] = 0.0;
+    SB_CUDA(cudaMemcpy(lineTab, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    lineFast = true;
 }
 
 // PoissonOp::checkForNullSpace (PoissonOp.cpp:670-696): L[1] == 0 to smallReal?
@@ -505,15 +578,16 @@ void Op::relax(double* cor, const double* res, int iters)
         case SB_RELAX_VERTLINE: {  // PoissonOp.cpp:1927-2010
             if (iters == 0) return;
             const size_t n  = (size_t)((lay.nx + 1) / 2) * lay.ny * lay.nz;
-            double*      wd = (double*)ctx->getScratch(2 * n * sizeof(double));
-            double*      wb = wd + n;
+            double*      wd = lineFast ? nullptr : (double*)ctx->getScratch(2 * n * sizeof(double));
+            double*      wb = wd + (lineFast ? 0 : n);
             for (int it = 0; it < iters; ++it)
                 for (int pass = 0; pass < 2; ++pass) {
                     if (pass == 0) applyBCs(cor, true);
                     else exchange(cor);
                     cudaEvent_t e0;
                     ctx->profBegin("vertline", depth, &e0);
-                    k::vertline_pass(st(), lay, coef(), cor, res, pass, wd, wb, pivotFlag);
+                    if (lineFast) k::vertline_smem_pass(st(), lay, coef(), lineTab, cor, res, pass);
+                    else k::vertline_pass(st(), lay, coef(), cor, res, pass, wd, wb, pivotFlag);
                     ctx->profEnd("vertline", depth, e0);
                 }
             break;
