@@ -114,6 +114,16 @@ int sb_context_profile_get(sb_context* ctx, const char* key, double* total_ms, l
 int sb_comm_get_unique_id(void* id128);
 int sb_comm_init(sb_context* ctx, const void* id128);
 
+/* ---- host-only planning (no CUDA device needed) ---------------------------------------------- */
+/* The rectangle of boxes a rank owns and what each of its sides touches: side index 2*dir+side,
+ * kind 0 physical boundary, 1 periodic wrap onto itself, 2 neighbour rank (Copier::exchangeDefine,
+ * BoxTools/Copier.cpp:784, at tile granularity). */
+int sb_plan_tile(const sb_level_desc* desc, int rank, int nranks, int tile_lo[3], int tile_hi[3], int side_kind[6],
+                 int side_neighbor[6], int* num_local_boxes);
+/* The MG refinement schedule MGSolver::define would create (MGCoarseningStrategy.cpp:62-310):
+ * HorizCoarseningStrategy(doVertCoarsening) when relax_method is VERTLINE, else Semicoarsening. */
+int sb_plan_schedule(const sb_level_desc* desc, int max_depth, int* schedule, int capacity, int* num_sched);
+
 /* ---- PoissonOp --------------------------------------------------------------------------- */
 /* PoissonOp::PoissonOp(levGeo, fineGrids, crseGrids, 1, bcFunc, alpha, beta) PoissonOp.cpp:33.
  * The metric (J, Jgup) is built the way LevelGeometry::createMetricCache does

@@ -98,6 +98,42 @@ def assign_boxes_to_ranks(box_lo, box_hi, nranks):
     return (ix + px * iy).astype(np.int32)
 
 
+def _level_desc(domain_lo, domain_hi, dXi, box_lo, box_hi, box_rank, periodic, dim, relax_method):
+    box_lo = np.ascontiguousarray(box_lo, dtype=np.int32)
+    box_hi = np.ascontiguousarray(box_hi, dtype=np.int32)
+    box_rank = np.ascontiguousarray(box_rank if box_rank is not None else np.zeros(len(box_lo)), dtype=np.int32)
+    d = capi.LevelDesc()
+    d.dim = dim
+    d.domain_lo, d.domain_hi, d.periodic = _i3(domain_lo), _i3(domain_hi), _i3(periodic)
+    d.dXi = (C.c_double * 3)(*[float(v) for v in dXi])
+    d.num_boxes = len(box_lo)
+    d.box_lo = box_lo.ctypes.data_as(capi.IP)
+    d.box_hi = box_hi.ctypes.data_as(capi.IP)
+    d.box_rank = box_rank.ctypes.data_as(capi.IP)
+    d.relax_method = relax_method
+    d._keep = (box_lo, box_hi, box_rank)
+    return d
+
+
+def plan_tile(domain_lo, domain_hi, box_lo, box_hi, box_rank, rank, nranks, periodic=(0, 0, 0), dim=3):
+    """Host-only (no GPU): the rectangle `rank` owns and what its six sides touch.
+    Returns (tile_lo, tile_hi, side_kind[6], side_neighbor[6], num_local_boxes); side index = 2*dir + side,
+    kind 0 physical, 1 periodic onto itself, 2 neighbour rank."""
+    d = _level_desc(domain_lo, domain_hi, (1, 1, 1), box_lo, box_hi, box_rank, periodic, dim, RELAX_VERTLINE)
+    lo, hi, kind, nb, n = (C.c_int * 3)(), (C.c_int * 3)(), (C.c_int * 6)(), (C.c_int * 6)(), C.c_int()
+    capi.check(capi.load().sb_plan_tile(C.byref(d), rank, nranks, lo, hi, kind, nb, C.byref(n)))
+    return list(lo), list(hi), list(kind), list(nb), n.value
+
+
+def plan_schedule(domain_lo, domain_hi, dXi, box_lo, box_hi, relax_method=RELAX_VERTLINE, max_depth=-1, dim=3):
+    """Host-only: the MG refinement schedule MGSolver::define would build (MGCoarseningStrategy.cpp)."""
+    d = _level_desc(domain_lo, domain_hi, dXi, box_lo, box_hi, None, (0, 0, 0), dim, relax_method)
+    n = C.c_int()
+    buf = (C.c_int * (3 * 64))()
+    capi.check(capi.load().sb_plan_schedule(C.byref(d), max_depth, buf, 64, C.byref(n)))
+    return [tuple(buf[3 * i:3 * i + 3]) for i in range(n.value)]
+
+
 def default_options(**kw):
     """MGSolver<T>::getDefaultOptions with the reference's proj.* defaults (ProjectorParameters.cpp:124-222)."""
     o = MGOptions()

@@ -100,6 +100,8 @@ PROTOTYPES = {
     "sb_context_profile_get": (C.c_int, [P, C.c_char_p, DP, C.POINTER(C.c_longlong)]),
     "sb_comm_get_unique_id": (C.c_int, [C.c_void_p]),
     "sb_comm_init": (C.c_int, [P, C.c_void_p]),
+    "sb_plan_tile": (C.c_int, [C.POINTER(LevelDesc), C.c_int, C.c_int, IP, IP, IP, IP, IP]),
+    "sb_plan_schedule": (C.c_int, [C.POINTER(LevelDesc), C.c_int, IP, C.c_int, IP]),
     "sb_op_create": (C.c_int, [P, C.POINTER(LevelDesc), PP]),
     "sb_op_set_metric": (C.c_int, [P, C.c_int, C.c_int, DP, IP, IP]),
     "sb_op_finalize": (C.c_int, [P]),

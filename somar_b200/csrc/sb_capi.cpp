@@ -79,6 +79,48 @@ int sb_context_profile_get(sb_context* ctx, const char* key, double* total_ms, l
     SB_END
 }
 
+// Host-only helpers (no CUDA device needed): decomposition plan and MG schedule.
+int sb_plan_tile(const sb_level_desc* d, int rank, int nranks, int tile_lo[3], int tile_hi[3], int side_kind[6],
+                 int side_neighbor[6], int* num_local_boxes)
+{
+    SB_TRY REQ(d); REQ(tile_lo); REQ(tile_hi); REQ(side_kind); REQ(side_neighbor);
+    std::vector<Box3> boxes(d->num_boxes);
+    std::vector<int>  br(d->num_boxes);
+    for (int b = 0; b < d->num_boxes; ++b) {
+        for (int i = 0; i < 3; ++i) { boxes[b].lo[i] = d->box_lo[3 * b + i]; boxes[b].hi[i] = d->box_hi[3 * b + i]; }
+        br[b] = d->box_rank ? d->box_rank[b] : 0;
+    }
+    Box3 dom;
+    for (int i = 0; i < 3; ++i) { dom.lo[i] = d->domain_lo[i]; dom.hi[i] = d->domain_hi[i]; }
+    std::vector<Box3> tiles;
+    std::vector<int>  local;
+    SideBC            side[3][2];
+    planDecomposition(boxes, br, dom, d->periodic, rank, nranks, tiles, local, side);
+    for (int i = 0; i < 3; ++i) { tile_lo[i] = tiles[rank].lo[i]; tile_hi[i] = tiles[rank].hi[i]; }
+    for (int i = 0; i < 3; ++i)
+        for (int s = 0; s < 2; ++s) { side_kind[2 * i + s] = side[i][s].kind; side_neighbor[2 * i + s] = side[i][s].neighbor; }
+    if (num_local_boxes) *num_local_boxes = (int)local.size();
+    SB_END
+}
+int sb_plan_schedule(const sb_level_desc* d, int max_depth, int* schedule, int capacity, int* num_sched)
+{
+    SB_TRY REQ(d); REQ(num_sched);
+    std::vector<Box3> boxes(d->num_boxes);
+    for (int b = 0; b < d->num_boxes; ++b)
+        for (int i = 0; i < 3; ++i) { boxes[b].lo[i] = d->box_lo[3 * b + i]; boxes[b].hi[i] = d->box_hi[3 * b + i]; }
+    Box3 dom;
+    for (int i = 0; i < 3; ++i) { dom.lo[i] = d->domain_lo[i]; dom.hi[i] = d->domain_hi[i]; }
+    const bool horiz = d->relax_method == SB_RELAX_VERTLINE;  // MGSolverI.H:154-167
+    auto sc = createMGRefScheduleBoxes(d->dim, dom, d->dXi, boxes, max_depth, horiz, horiz);
+    *num_sched = (int)sc.size();
+    if (schedule) {
+        if (capacity < (int)sc.size()) SB_FAIL("capacity too small");
+        for (size_t i = 0; i < sc.size(); ++i)
+            for (int k = 0; k < 3; ++k) schedule[3 * i + k] = sc[i][k];
+    }
+    SB_END
+}
+
 // ---- PoissonOp ------------------------------------------------------------------------------
 int sb_op_create(sb_context* ctx, const sb_level_desc* desc, sb_op** op)
 {

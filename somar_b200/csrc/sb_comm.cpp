@@ -112,4 +112,22 @@ void Comm::exchangeFaces(Op& op, double* phi)
             if (op.side[d][s].kind == SIDE_NEIGHBOR) k::unpack_face(ctx->st, op.lay, phi, d, s, op.xbuf[d][s][1]);
 }
 
+// One direction only, optionally extended over the ghosts of the other directions.
+void Comm::exchangeDir(Op& op, double* phi, int d, int ext0, int ext1)
+{
+    bool any = false;
+    for (int s = 0; s < 2; ++s)
+        if (op.side[d][s].kind == SIDE_NEIGHBOR) { k::pack_face(ctx->st, op.lay, phi, d, s, op.xbuf[d][s][0], ext0, ext1); any = true; }
+    if (!any) return;
+    const size_t n = k::face_count(op.lay, d, ext0, ext1);
+    SB_NCCL(api().GroupStart());
+    for (int s = 0; s < 2; ++s)
+        if (op.side[d][s].kind == SIDE_NEIGHBOR) SB_NCCL(api().Send(op.xbuf[d][s][0], n, kNcclFloat64, op.side[d][s].neighbor, comm, ctx->st));
+    for (int s = 1; s >= 0; --s)
+        if (op.side[d][s].kind == SIDE_NEIGHBOR) SB_NCCL(api().Recv(op.xbuf[d][s][1], n, kNcclFloat64, op.side[d][s].neighbor, comm, ctx->st));
+    SB_NCCL(api().GroupEnd());
+    for (int s = 0; s < 2; ++s)
+        if (op.side[d][s].kind == SIDE_NEIGHBOR) k::unpack_face(ctx->st, op.lay, phi, d, s, op.xbuf[d][s][1], ext0, ext1);
+}
+
 }  // namespace sb

@@ -16,6 +16,7 @@ struct Comm {
     static void getUniqueId(void* id128);
     void allreduceHost(double* v, int n, bool isMax);
     void exchangeFaces(Op& op, double* phi);
+    void exchangeDir(Op& op, double* phi, int dir, int ext0, int ext1);
 };
 
 }  // namespace sb

@@ -126,8 +126,11 @@ void fill_ghosts(cudaStream_t st, const Lay& L, double* phi, const SideBC bc[3][
 void fill_ghosts_with_edges(cudaStream_t st, const Lay& L, double* phi, const SideBC bc[3][2], int dim);
 long long launch_count();
 // pack / unpack of one side's face layer for neighbour exchange
-void pack_face(cudaStream_t st, const Lay& L, const double* phi, int dir, int side, double* buf);
-void unpack_face(cudaStream_t st, const Lay& L, double* phi, int dir, int side, const double* buf);
+void fill_ghosts_dir(cudaStream_t st, const Lay& L, double* phi, int dir, const SideBC& lo, const SideBC& hi, int ext0, int ext1);
+void extrap_domain_edges(cudaStream_t st, const Lay& L, double* phi, const SideBC bc[3][2], int dim);
+size_t face_count(const Lay& L, int dir, int ext0, int ext1);
+void pack_face(cudaStream_t st, const Lay& L, const double* phi, int dir, int side, double* buf, int ext0 = 0, int ext1 = 0);
+void unpack_face(cudaStream_t st, const Lay& L, double* phi, int dir, int side, const double* buf, int ext0 = 0, int ext1 = 0);
 
 void apply_op(cudaStream_t st, const Lay& L, const Coef& c, double* lhs, const double* phi);
 void residual(cudaStream_t st, const Lay& L, const Coef& c, double* res, const double* phi, const double* rhs);

@@ -142,6 +142,13 @@ struct Op {
     double* alloc() const;
 };
 
+void planDecomposition(const std::vector<Box3>& boxes, const std::vector<int>& boxRank, const Box3& domain,
+                       const int periodic[3], int rank, int nranks, std::vector<Box3>& tiles, std::vector<int>& local,
+                       SideBC side[3][2]);
+std::vector<std::array<int, 3>> createMGRefScheduleBoxes(int dim, const Box3& domain, const double dXi[3],
+                                                         const std::vector<Box3>& boxes, int maxDepth, bool horizStrategy,
+                                                         bool doVertCoarsening);
+
 // SemicoarseningStrategy / HorizCoarseningStrategy (Elliptic/MGCoarseningStrategy.cpp)
 std::vector<std::array<int, 3>> createMGRefSchedule(const Op& top, int maxDepth, bool horizStrategy, bool doVertCoarsening);
 

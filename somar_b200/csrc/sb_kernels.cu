@@ -180,6 +180,10 @@ void fill_ghosts_with_edges(cudaStream_t st, const Lay& L, double* phi, const Si
     fill_ghosts_dir(st, L, phi, 0, bc[0][0], bc[0][1], 0, 0);
     if (dim == 3) fill_ghosts_dir(st, L, phi, 1, bc[1][0], bc[1][1], 1, 0);
     fill_ghosts_dir(st, L, phi, 2, bc[2][0], bc[2][1], 1, dim == 3 ? 1 : 0);
+    extrap_domain_edges(st, L, phi, bc, dim);
+}
+void extrap_domain_edges(cudaStream_t st, const Lay& L, double* phi, const SideBC bc[3][2], int dim)
+{
     for (int a = 0; a < 3; ++a)
         for (int b = a + 1; b < 3; ++b) {
             if (dim == 2 && (a == 1 || b == 1)) continue;
@@ -196,38 +200,48 @@ void fill_ghosts_with_edges(cudaStream_t st, const Lay& L, double* phi, const Si
 
 // Pack / unpack one face layer (valid cells adjacent to the side -> buffer; buffer -> ghosts).
 // Stands in for Copier motion items of LevelData::exchange (BoxTools/BoxLayoutDataI.H:665-812).
-__global__ void pack_face_k(Lay L, const double* phi, int dir, int layer, double* buf, int unpack, double* phiw)
+// ext0 / ext1 extend the tangential ranges by one ghost on each end (edge exchange before the
+// quadratic prolongation); the buffer is (na + 2 ext0) x (nb + 2 ext1).
+__global__ void pack_face_k(Lay L, const double* phi, int dir, int layer, double* buf, int unpack, double* phiw, int ext0,
+                            int ext1)
 {
     int na, nb;
     long long sa, sb, sn;
     if (dir == 0) { na = L.ny; nb = L.nz; sa = L.sy; sb = L.sz; sn = 1; }
     else if (dir == 1) { na = L.nx; nb = L.nz; sa = 1; sb = L.sz; sn = L.sy; }
     else { na = L.nx; nb = L.ny; sa = 1; sb = L.sy; sn = L.sz; }
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y * blockDim.y + threadIdx.y;
-    if (a >= na || b >= nb) return;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x - ext0;
+    const int b = blockIdx.y * blockDim.y + threadIdx.y - ext1;
+    if (a >= na + ext0 || b >= nb + ext1) return;
     const long long c = L.idx(0, 0, 0) + sa * a + sb * b + sn * layer;
-    if (unpack) phiw[c] = buf[a + (long long)na * b];
-    else buf[a + (long long)na * b] = phi[c];
+    const long long m = (a + ext0) + (long long)(na + 2 * ext0) * (b + ext1);
+    if (unpack) phiw[c] = buf[m];
+    else buf[m] = phi[c];
 }
-void pack_face(cudaStream_t st, const Lay& L, const double* phi, int dir, int side, double* buf)
+size_t face_count(const Lay& L, int dir, int ext0, int ext1)
+{
+    const int na = dir == 0 ? L.ny : L.nx, nb = dir == 2 ? L.ny : L.nz;
+    return (size_t)(na + 2 * ext0) * (nb + 2 * ext1);
+}
+void pack_face(cudaStream_t st, const Lay& L, const double* phi, int dir, int side, double* buf, int ext0, int ext1)
 {
     int na, nb, nn;
     if (dir == 0) { na = L.ny; nb = L.nz; nn = L.nx; }
     else if (dir == 1) { na = L.nx; nb = L.nz; nn = L.ny; }
     else { na = L.nx; nb = L.ny; nn = L.nz; }
     dim3 b(dir == 0 ? 8 : 64, dir == 0 ? 16 : 2, 1);
-    pack_face_k<<<grid3(na, nb, 1, b), b, 0, st>>>(L, phi, dir, side ? nn - 1 : 0, buf, 0, nullptr);
+    pack_face_k<<<grid3(na + 2 * ext0, nb + 2 * ext1, 1, b), b, 0, st>>>(L, phi, dir, side ? nn - 1 : 0, buf, 0, nullptr, ext0, ext1);
     LAUNCHED();
 }
-void unpack_face(cudaStream_t st, const Lay& L, double* phi, int dir, int side, const double* buf)
+void unpack_face(cudaStream_t st, const Lay& L, double* phi, int dir, int side, const double* buf, int ext0, int ext1)
 {
     int na, nb, nn;
     if (dir == 0) { na = L.ny; nb = L.nz; nn = L.nx; }
     else if (dir == 1) { na = L.nx; nb = L.nz; nn = L.ny; }
     else { na = L.nx; nb = L.ny; nn = L.nz; }
     dim3 b(dir == 0 ? 8 : 64, dir == 0 ? 16 : 2, 1);
-    pack_face_k<<<grid3(na, nb, 1, b), b, 0, st>>>(L, nullptr, dir, side ? nn : -1, const_cast<double*>(buf), 1, phi);
+    pack_face_k<<<grid3(na + 2 * ext0, nb + 2 * ext1, 1, b), b, 0, st>>>(L, nullptr, dir, side ? nn : -1, const_cast<double*>(buf), 1,
+                                                                          phi, ext0, ext1);
     LAUNCHED();
 }
 

@@ -60,7 +60,11 @@ IV nextRef(const double dx[3], const std::vector<Box3>& grids, const std::vector
 
 std::vector<IV> createMGRefSchedule(const Op& top, int maxDepth, bool horizStrategy, bool doVertCoarsening)
 {
-    const int       dim = top.dim;
+    return createMGRefScheduleBoxes(top.dim, top.domain, top.dXi, top.boxes, maxDepth, horizStrategy, doVertCoarsening);
+}
+std::vector<IV> createMGRefScheduleBoxes(int dim, const Box3& domain, const double dXi[3], const std::vector<Box3>& boxes,
+                                         int maxDepth, bool horizStrategy, bool doVertCoarsening)
+{
     std::vector<IV> refList;
     if (!horizStrategy) {
         if (dim == 2) refList = {{2, 1, 1}, {1, 1, 2}, {2, 1, 2}};
@@ -72,10 +76,10 @@ std::vector<IV> createMGRefSchedule(const Op& top, int maxDepth, bool horizStrat
     // curDx = L / N with L = N * dXi (MGSolverI.H:148-151, MGCoarseningStrategy.cpp:68)
     double curDx[3];
     for (int d = 0; d < 3; ++d) {
-        const double N = (double)top.domain.size(d);
-        curDx[d]       = (N * top.dXi[d]) / N;
+        const double N = (double)domain.size(d);
+        curDx[d]       = (N * dXi[d]) / N;
     }
-    std::vector<Box3> cur = top.boxes;  // minBoxSize = 1: coarsening by it is a no-op
+    std::vector<Box3> cur = boxes;  // minBoxSize = 1: coarsening by it is a no-op
     std::vector<IV>   sched;
     while (true) {
         if (maxDepth >= 0 && sched.size() == (size_t)maxDepth) break;

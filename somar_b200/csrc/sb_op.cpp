@@ -174,21 +174,26 @@ Op::Op(Context* c, const sb_level_desc& d) : ctx(c)
     fillMetricFromMap();
 }
 
-void Op::setupLayout()
+// Host-only decomposition logic (no CUDA): the rectangle each rank owns and what each of its six
+// sides touches.  Stands in for what DisjointBoxLayout + Copier::exchangeDefine work out per box
+// (BoxTools/Copier.cpp:784); here ranks own rectangles of boxes, so it is per tile.
+void planDecomposition(const std::vector<Box3>& boxes, const std::vector<int>& boxRank, const Box3& domain,
+                       const int periodic[3], int rank, int nr, std::vector<Box3>& tiles, std::vector<int>& local,
+                       SideBC side[3][2])
 {
-    const int nr = ctx->nranks;
     tiles.assign(nr, Box3{{0, 0, 0}, {-1, -1, -1}});
     std::vector<long long> pts(nr, 0);
     std::vector<int>       cnt(nr, 0);
     local.clear();
     for (size_t b = 0; b < boxes.size(); ++b) {
         const int r = boxRank[b];
+        if (r < 0 || r >= nr) SB_FAIL("box_rank out of range");
         Box3&     t = tiles[r];
         if (cnt[r]++ == 0) t = boxes[b];
         else
             for (int i = 0; i < 3; ++i) { t.lo[i] = std::min(t.lo[i], boxes[b].lo[i]); t.hi[i] = std::max(t.hi[i], boxes[b].hi[i]); }
         pts[r] += boxes[b].numPts();
-        if (r == ctx->rank) local.push_back((int)b);
+        if (r == rank) local.push_back((int)b);
     }
     long long total = 0;
     for (int r = 0; r < nr; ++r) {
@@ -197,8 +202,7 @@ void Op::setupLayout()
         total += pts[r];
     }
     if (total != domain.numPts()) SB_FAIL("boxes do not cover the domain (single-level operator)");
-    tile = tiles[ctx->rank];
-    lay  = makeLay(tile);
+    const Box3& tile = tiles[rank];
 
     // What does each side of the tile touch?
     for (int d = 0; d < 3; ++d)
@@ -213,7 +217,7 @@ void Op::setupLayout()
             if (atDom) want = s ? domain.lo[d] : domain.hi[d];
             int found = -1;
             for (int r = 0; r < nr && found < 0; ++r) {
-                if (r == ctx->rank) continue;
+                if (r == rank) continue;
                 const Box3& t = tiles[r];
                 bool ok = s ? t.lo[d] == want : t.hi[d] == want;
                 for (int o = 0; o < 3 && ok; ++o)
@@ -223,6 +227,13 @@ void Op::setupLayout()
             if (found < 0) SB_FAIL("rank tiles do not form a process grid (no neighbour across a tile side)");
             sd.kind = SIDE_NEIGHBOR; sd.neighbor = found;
         }
+}
+
+void Op::setupLayout()
+{
+    planDecomposition(boxes, boxRank, domain, periodic, ctx->rank, ctx->nranks, tiles, local, side);
+    tile = tiles[ctx->rank];
+    lay  = makeLay(tile);
 
     // device-side box list (tile-local indices) and reduction buffers
     const int nl = nlocal();
@@ -248,7 +259,7 @@ void Op::setupLayout()
     for (int d = 0; d < 3; ++d)
         for (int s = 0; s < 2; ++s)
             if (side[d][s].kind == SIDE_NEIGHBOR) {
-                const size_t n = (size_t)(d == 0 ? lay.ny : lay.nx) * (d == 2 ? lay.ny : lay.nz);
+                const size_t n = k::face_count(lay, d, 1, 1);  // room for the edge-extended exchange
                 for (int w = 0; w < 2; ++w) SB_CUDA(cudaMalloc((void**)&xbuf[d][s][w], n * sizeof(double)));
             }
 }
@@ -527,8 +538,17 @@ void Op::applyBCs(double* phi, bool homog)
 }
 void Op::applyBCsWithEdges(double* phi)
 {
-    if (ctx->nranks > 1) SB_FAIL("quadratic prolongation across ranks is not implemented yet");
-    k::fill_ghosts_with_edges(st(), lay, phi, side, dim);
+    if (ctx->nranks == 1) { k::fill_ghosts_with_edges(st(), lay, phi, side, dim); return; }
+    // Direction by direction, each over the ghosts of the lower directions, so that an edge ghost
+    // receives what the neighbouring tile's face ghost holds (the effect of the reference's
+    // CornerCopier exchange, PoissonOp.cpp:1115-1125); then the physical-physical domain edges.
+    for (int d = 0; d < 3; ++d) {
+        if (dim == 2 && d == 1) continue;
+        const int e0 = d == 0 ? 0 : 1, e1 = (d == 2 && dim == 3) ? 1 : 0;
+        k::fill_ghosts_dir(st(), lay, phi, d, side[d][0], side[d][1], e0, e1);
+        ctx->comm->exchangeDir(*this, phi, d, e0, e1);
+    }
+    k::extrap_domain_edges(st(), lay, phi, side, dim);
 }
 
 void Op::applyOp(double* lhs, double* phi, bool homog)

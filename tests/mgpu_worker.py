@@ -1,0 +1,68 @@
+"""Worker for the multi-GPU parity test (launched by torchrun, one rank per GPU): solves one case
+with the box list split over the ranks, gathers the pressure on rank 0 and compares it with the
+oracle and, implicitly, with the single-GPU tests (same tolerances)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import somar_b200 as sb
+from cases import CASES, geometry, rand_field, ref_kwargs, rel_err
+
+
+def main():
+    name, optset, out_path = sys.argv[1], sys.argv[2], sys.argv[3]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = sb.Context(local, rank, world)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(sb.Context.unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx.init_comm(idt.cpu().numpy().tobytes())
+
+    c = CASES[name]
+    nx, L, dXi, lo, hi = geometry(c)
+    blo, bhi = sb.make_base_grids(lo, hi, c["max_box"], (1, 1, 0), c["bf"])
+    ranks = sb.assign_boxes_to_ranks(blo, bhi, world)
+    xmin = lo * dXi
+    kind = sb.MAP_CARTESIAN if c["map"] == "cartesian" else sb.MAP_STRETCHED
+    op = sb.PoissonOp(ctx, lo, hi, dXi, blo, bhi, box_rank=ranks, periodic=c["periodic"], map_kind=kind, map_xmin=xmin,
+                      map_xmax=xmin + L, map_ampl=c["ampl"], relax_method=c["relax"])
+    over = {} if optset == "defaults" else dict(numCycles=1, numSmoothDown=2, numSmoothUp=2, numSmoothBottom=2, prolongOrder=1,
+                                                maxIters=20, relTol=1e-10)
+    solver = sb.LevelHybridSolver(op, sb.default_options(**over))
+    rhs0 = rand_field(c, 4, zero_mean=True)           # every rank builds the global field, uploads its part
+    phi, rhs = op.field(), op.field()
+    rhs.upload(rhs0)                                  # upload clips to this rank's tile (+ghosts)
+    st = solver.solve(phi, rhs)
+    mine = ranks == rank
+    tlo, thi = blo[mine].min(axis=0), bhi[mine].max(axis=0)
+    part = phi.download(tlo, thi)
+    # gather tiles on rank 0 through a shared directory (keeps the test independent of tensor plumbing)
+    np.save(f"{out_path}.phi{rank}.npy", part)
+    np.save(f"{out_path}.box{rank}.npy", np.array([tlo, thi]))
+    dist.barrier()
+    if rank == 0:
+        full = np.zeros(tuple(nx), order="F")
+        for r in range(world):
+            b = np.load(f"{out_path}.box{r}.npy")
+            p = np.load(f"{out_path}.phi{r}.npy")
+            sl = tuple(slice(int(b[0][d] - lo[d]), int(b[1][d] - lo[d]) + 1) for d in range(3))
+            full[sl] = p
+        np.save(f"{out_path}.phi.npy", full)
+        with open(out_path, "w") as f:
+            json.dump({"status": st.status, "norms": st.norms, "max_depth": st.max_depth, "world": world,
+                       "launches": ctx.launch_count()}, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,141 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every declared symbol, and the host
+logic -- box decomposition, MG coarsening schedule -- matches the reference's (values below were
+produced by oracle/_ref, i.e. the reference's own MGCoarseningStrategy / makeBaseLevelMesh)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import somar_b200 as sb
+from somar_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    header = open(os.path.join(ROOT, "include", "somar_b200.h")).read()
+    declared = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"sb_map_fn"}
+    assert len(declared) >= 45
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/somar_b200.h but not exported"
+    assert declared == set(capi.PROTOTYPES), declared ^ set(capi.PROTOTYPES)
+
+
+def test_no_gpu_fails_loudly():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(sb.SomarB200Error, match="no CPU fallback"):
+        sb.Context(0, 0, 1)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "somar_b200")):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower() or f in (), f"{f} mentions the oracle"
+
+
+def test_make_base_grids_matches_reference_layout():
+    # S5: 1024 x 1024 x 256, maxBaseGridSize 128 128 0, blockFactor 16 -> 64 boxes of 128 x 128 x 256
+    lo, hi = sb.make_base_grids((0, 0, -256), (1023, 1023, -1), (128, 128, 0), (1, 1, 0), 16)
+    assert lo.shape == (64, 3)
+    assert np.all(hi - lo + 1 == np.array([128, 128, 256]))
+    assert set(map(tuple, lo)) == {(i, j, -256) for i in range(0, 1024, 128) for j in range(0, 1024, 128)}
+    # uneven split: 96 cells, max 64, bf 16 -> 2 boxes of 48 (AnisotropicAMR.cpp:1520-1540 rounds up evenly)
+    lo, hi = sb.make_base_grids((0, 0, 0), (95, 31, 7), (64, 0, 0), (1, 1, 0), 16)
+    assert sorted((hi - lo + 1)[:, 0].tolist()) == [48, 48]
+
+
+# (nx, L, max_box, bf, relax) -> schedule; produced by oracle/_ref/d3/somar_ref (maxDepth and ref ratios
+# printed by the reference's own coarsening strategies at verbosity 3)
+SCHEDULES = [
+    ((32, 32, 16), (1.0, 1.0, 1.0), (16, 16, 0), 4, 6, [(2, 2, 2)] * 4 + [(1, 1, 1)]),
+    ((1024, 1024, 256), (16.0, 16.0, 1.0), (128, 128, 0), 16, 6, [(2, 2, 2)] * 7 + [(1, 1, 1)]),
+    ((16, 16, 32), (1.0, 1.0, 6.0), (8, 8, 0), 4, 5, None),
+]
+
+
+@pytest.mark.parametrize("nx,L,mb,bf,relax,expect", SCHEDULES)
+def test_schedule(nx, L, mb, bf, relax, expect):
+    lo = np.array([0, 0, -nx[2]])
+    hi = lo + np.array(nx) - 1
+    blo, bhi = sb.make_base_grids(lo, hi, mb, (1, 1, 0), bf)
+    sched = sb.plan_schedule(lo, hi, np.array(L) / np.array(nx), blo, bhi, relax_method=relax)
+    assert sched[-1] == (1, 1, 1)
+    if expect is not None:
+        assert sched == expect
+    # every box stays coarsenable along the schedule
+    cur_lo, cur_hi = blo.copy(), bhi.copy()
+    for r in sched[:-1]:
+        r = np.array(r)
+        assert np.all(cur_lo % r == 0) and np.all((cur_hi + 1) % r == 0)
+        cur_lo, cur_hi = cur_lo // r, (cur_hi + 1) // r - 1
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 4, 8])
+def test_plan_tiles_cover_and_neighbours_are_symmetric(nranks):
+    lo, hi = (0, 0, -256), (1023, 1023, -1)
+    blo, bhi = sb.make_base_grids(lo, hi, (128, 128, 0), (1, 1, 0), 16)
+    ranks = sb.assign_boxes_to_ranks(blo, bhi, nranks)
+    plans = [sb.plan_tile(lo, hi, blo, bhi, ranks, r, nranks, periodic=(1, 0, 0)) for r in range(nranks)]
+    cells = sum(int(np.prod(np.array(p[1]) - np.array(p[0]) + 1)) for p in plans)
+    assert cells == 1024 * 1024 * 256
+    assert sum(p[4] for p in plans) == 64
+    for r, (tlo, thi, kind, nb, _) in enumerate(plans):
+        assert tlo[2] == -256 and thi[2] == -1            # the vertical is never split
+        assert kind[4] == 0 and kind[5] == 0
+        for s in range(4):
+            if kind[s] == 2:
+                other = plans[nb[s]]
+                assert other[2][s ^ 1] == 2 and other[3][s ^ 1] == r   # my lo neighbour sees me on its hi side
+            elif kind[s] == 1:
+                assert s < 2 and tlo[0] == 0 and thi[0] == 1023       # periodic in x onto itself
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = (0, 0, -16), (63, 31, -1)
+    blo, bhi = sb.make_base_grids(lo, hi, (16, 16, 0), (1, 1, 0), 4)
+    ranks = sb.assign_boxes_to_ranks(blo, bhi, world)
+    plan = sb.plan_tile(lo, hi, blo, bhi, ranks, rank, world, periodic=(0, 1, 0))
+    objs = [None] * world
+    dist.all_gather_object(objs, plan)
+    ok = True
+    for s in range(4):
+        if plan[2][s] == 2:
+            o = objs[plan[3][s]]
+            d = s // 2
+            # the two tiles share the face: same extents in the other directions
+            for e in range(3):
+                if e != d:
+                    ok &= o[0][e] == plan[0][e] and o[1][e] == plan[1][e]
+            ok &= o[2][s ^ 1] == 2 and o[3][s ^ 1] == rank
+    q.put((rank, ok, plan))
+    dist.destroy_process_group()
+
+
+def test_two_rank_plan_over_gloo():
+    """world_size-2 gloo run of the host-side decomposition: each rank plans its own tile, the plans
+    are all-gathered and must describe a consistent exchange (who sends which face to whom)."""
+    import torch.multiprocessing as mp
+    ctxmp = mp.get_context("spawn")
+    q = ctxmp.Queue()
+    port = 29400 + os.getpid() % 500
+    procs = [ctxmp.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res)
+    tiles = {r: (tuple(pl[0]), tuple(pl[1])) for r, _, pl in res}
+    assert tiles[0] != tiles[1]

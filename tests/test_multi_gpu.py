@@ -1,0 +1,49 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; run with `gpurun --gpus 2`): the same solves as
+test_parity_gpu.py with the boxes split over 2 ranks (NCCL halo exchange + scalar all-reduces),
+checked against the oracle with the same tolerances."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from _oracle import have_ref, run_ref
+from cases import CASES, rand_field, ref_kwargs, rel_err
+from test_parity_gpu import V_OPTS, _proj_overrides, assert_norms
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs"),
+              pytest.mark.skipif(not have_ref(3), reason="oracle/_ref/d3/somar_ref not built")]
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("name,optset", [("line_cart", "defaults"), ("line_stretch", "defaults"), ("line_perx", "defaults"),
+                                         ("gsrb_cart", "defaults"), ("gsrb_perxy", "vcycle"), ("line_aniso", "vcycle")])
+def test_two_rank_solve(name, optset):
+    c = CASES[name]
+    ref = run_ref("solve", inp=[rand_field(c, 4, zero_mean=True)], extra=_proj_overrides({} if optset == "defaults" else V_OPTS),
+                  **ref_kwargs(c))
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "res.json")
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+               "--master-port", "29517", os.path.join(HERE, "mgpu_worker.py"), name, optset, out]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        res = json.load(open(out))
+        phi = np.load(out + ".phi.npy")
+    assert res["status"] == int(ref.kv["status"])
+    assert res["max_depth"] == int(ref.kv["maxDepth"])
+    assert_norms(res["norms"], ref["norms"][1:])
+    assert rel_err(phi, ref["phi"]) <= 1e-9
