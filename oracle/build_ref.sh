@@ -42,11 +42,12 @@ echo "$SRCS" | xargs -P "$JOBS" -I{} bash -c '
 
 # 4. our pieces.
 g++ $CXXFLAGS $INC -c "$HERE/fort_leaves.cpp" -o "$OBJ/_fort_leaves.o"
+gcc -O3 -ffp-contract=off -fPIC -c "$HERE/dgtsv.c" -o "$OBJ/_dgtsv.o"
 g++ $CXXFLAGS $INC -c "$HERE/ref_driver.cpp" -o "$OBJ/_ref_driver.o"
 
 # 5. link; any Fortran leaf the driver never reaches becomes an aborting stub.
 OBJS=$(for s in $SRCS; do echo "$OBJ/$(basename "$s" .cpp).o"; done)
-link() { g++ -o "$OUT/somar_ref" $OBJS "$OBJ/_fort_leaves.o" "$OBJ/_ref_driver.o" $1 -lpthread 2>&1; }
+link() { g++ -o "$OUT/somar_ref" $OBJS "$OBJ/_fort_leaves.o" "$OBJ/_dgtsv.o" "$OBJ/_ref_driver.o" $1 -lpthread 2>&1; }
 if ! link "" > "$OUT/link1.log"; then
   grep -o "undefined reference to \`[A-Za-z0-9_]*'" "$OUT/link1.log" | sed "s/.*\`//; s/'//" | sort -u > "$OUT/undefined.txt"
   { echo '#include <stdio.h>'; echo '#include <stdlib.h>';

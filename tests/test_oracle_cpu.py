@@ -1,0 +1,57 @@
+"""CPU tests of the oracle itself (run where oracle/_ref is built): it must reproduce the committed
+golden vectors bit for bit (guards against drift of the restated Fortran leaves), solve the
+authors' own manufactured-solution test (AMRNSLevelProject.cpp:385-412, disabled in the reference)
+and satisfy the run-time invariants the reference prints (L[1] = 0, |Div U| drop)."""
+import ast
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from _oracle import have_ref, run_ref
+from cases import ref_kwargs
+
+pytestmark = pytest.mark.skipif(not have_ref(3), reason="oracle/_ref/d3/somar_ref not built")
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-4] for p in FIXTURES])
+def test_oracle_reproduces_golden(path):
+    z = np.load(path)
+    c = ast.literal_eval(str(z["case"]))
+    r = run_ref("solve", inp=[z["solve_rhs"]], **ref_kwargs(c))
+    assert np.array_equal(r["phi"], z["solve_phi"].ravel(order="F"))
+    assert np.array_equal(r["norms"], z["solve_norms"])
+    r = run_ref("applyop", inp=[z["apply_in"]], **ref_kwargs(c))
+    assert np.array_equal(r["lhs"], z["apply_out"].ravel(order="F"))
+
+
+@pytest.mark.parametrize("relax", [5, 6])
+def test_manufactured_solution(relax):
+    # sol = cos(kx x) cos(ky y) 16 z^2 (z+1)^2 on [0,L]^2 x [-1,0]; rhs = L[sol]; solve; compare up to a constant
+    nx, L = (32, 32, 32), (1.0, 1.0, 1.0)
+    c = dict(nx=nx, L=L, max_box=(16, 16, 0), bf=4, periodic=(0, 0, 0), relax=relax, map="cartesian", ampl=(0, 0, 0))
+    x = (np.arange(nx[0]) + 0.5) / nx[0]
+    y = (np.arange(nx[1]) + 0.5) / nx[1]
+    z = (np.arange(-nx[2], 0) + 0.5) / nx[2]
+    k = 2 * 2 * np.pi
+    sol = np.cos(k * x)[:, None, None] * np.cos(k * y)[None, :, None] * (16 * z**2 * (z + 1) ** 2)[None, None, :]
+    sol -= sol.mean()
+    rhs = run_ref("applyop", inp=[sol], **ref_kwargs(c))["lhs"]
+    assert abs(rhs.sum()) <= 1e-9 * np.abs(rhs).sum()          # solvability: Sum[rhs] = 0 (PoissonOp.cpp:853-885)
+    r = run_ref("solve", inp=[rhs], extra={"proj.relTol": 1e-12, "proj.absTol": 1e-14, "proj.maxIters": 20}, **ref_kwargs(c))
+    assert int(r.kv["status"]) in (1, 4)
+    phi = r["phi"].reshape(nx, order="F")
+    phi -= phi.mean()
+    assert np.max(np.abs(phi - sol)) <= 1e-9 * np.max(np.abs(sol))
+
+
+def test_null_space_and_projection_invariants():
+    c = dict(nx=(16, 16, 8), L=(1.0, 1.0, 1.0), max_box=(8, 8, 0), bf=4, periodic=(0, 0, 0), relax=6, map="cartesian", ampl=(0, 0, 0))
+    r = run_ref("applyop", inp=[np.ones(c["nx"])], **ref_kwargs(c))
+    assert np.max(np.abs(r["lhs"])) <= 1e4 * np.finfo(float).eps     # L[1] = 0 to smallReal (PoissonOp.cpp:670-696)
+    assert int(r.kv["hasNullSpace"]) == 1
+    z = np.load(os.path.join(HERE, "golden", "g_line_cart.npz"))
+    assert float(z["proj_finalDivNorm"]) <= 1e-5 * float(z["proj_initDivNorm"])

@@ -1,0 +1,102 @@
+"""Size-independent properties at sizes the CPU oracle cannot reach in seconds, up to
+BASELINE.json's full S5 grid (1024 x 1024 x 256): linearity, null space, restriction/prolongation
+identities, a manufactured solution, and the projection's divergence drop."""
+import numpy as np
+import pytest
+
+import somar_b200 as sb
+
+pytestmark = pytest.mark.gpu
+
+
+def _op(ctx, nx, L=(16.0, 16.0, 1.0), box=(128, 128, 0), bf=16, relax=sb.RELAX_VERTLINE, ampl=None):
+    nx = np.array(nx)
+    dXi = np.array(L) / nx
+    lo = np.array([0, 0, -nx[2]])
+    hi = lo + nx - 1
+    blo, bhi = sb.make_base_grids(lo, hi, box, (1, 1, 0), bf)
+    kw = {}
+    if ampl is not None:
+        xmin = lo * dXi
+        kw = dict(map_kind=sb.MAP_STRETCHED, map_xmin=xmin, map_xmax=xmin + np.array(L), map_ampl=ampl)
+    return sb.PoissonOp(ctx, lo, hi, dXi, blo, bhi, relax_method=relax, **kw)
+
+
+def test_linearity_and_null_space(ctx):
+    nx = (256, 256, 64)
+    op = _op(ctx, nx, L=(4.0, 4.0, 1.0), ampl=(0.0, 0.0, -0.1))
+    rng = np.random.default_rng(3)
+    x, y = rng.standard_normal(nx), rng.standard_normal(nx)
+    fx, fy, fz, out = op.field(data=x), op.field(data=y), op.field(data=2.5 * x - 0.75 * y), op.field()
+    op.applyOp(out, fx); Lx = out.download()
+    op.applyOp(out, fy); Ly = out.download()
+    op.applyOp(out, fz); Lz = out.download()
+    scale = np.max(np.abs(Lx))
+    assert np.max(np.abs(Lz - (2.5 * Lx - 0.75 * Ly))) <= 1e-12 * scale
+    ones = op.field(data=np.ones(nx))
+    op.applyOp(out, ones)
+    assert np.max(np.abs(out.download())) <= 1e-9 * scale       # L[1] = 0 up to rounding of 1/(1/x)
+    op.free()
+
+
+def test_restrict_of_constant_prolong_is_identity(ctx):
+    nx = (128, 128, 64)
+    op = _op(ctx, nx, L=(2.0, 2.0, 1.0), box=(64, 64, 0))
+    crse = op.new_mg_operator((2, 2, 2))
+    rng = np.random.default_rng(5)
+    c0 = rng.standard_normal((64, 64, 32))
+    c, f, c2 = crse.field(data=c0), op.field(), crse.field()
+    op.setToZero(f)
+    # order-0 prolongation (+ removeKernel, which only shifts by the mean) then block averaging
+    op.MGProlong(f, c, crse, 0)
+    op.MGRestrict(c2, f, crse)
+    got = c2.download()
+    assert np.max(np.abs((got - got.mean()) - (c0 - c0.mean()))) <= 1e-13
+    crse.free()
+    op.free()
+
+
+def test_manufactured_solution_256(ctx):
+    nx = (256, 256, 64)
+    L = (4.0, 4.0, 1.0)
+    op = _op(ctx, nx, L=L)
+    x = (np.arange(nx[0]) + 0.5) * L[0] / nx[0]
+    y = (np.arange(nx[1]) + 0.5) * L[1] / nx[1]
+    z = (np.arange(-nx[2], 0) + 0.5) / nx[2]
+    k = 4 * 2 * np.pi / L[0]
+    sol = np.cos(k * x)[:, None, None] * np.cos(k * y)[None, :, None] * (16 * z**2 * (z + 1) ** 2)[None, None, :]
+    sol -= sol.mean()
+    phi, rhs = op.field(data=sol), op.field()
+    op.applyOp(rhs, phi)
+    solver = sb.LevelHybridSolver(op, sb.default_options(relTol=1e-12, absTol=1e-14, maxIters=20))
+    out = op.field()
+    st = solver.solve(out, rhs)
+    assert st.status in (1, 4)
+    got = out.download()
+    got -= got.mean()
+    assert np.max(np.abs(got - sol)) <= 1e-8 * np.max(np.abs(sol))
+    solver.free()
+    op.free()
+
+
+@pytest.mark.parametrize("nx", [(512, 512, 128), (1024, 1024, 256)])
+def test_projection_reduces_divergence_full_size(ctx, nx):
+    import bench
+    nxa = np.array(nx)
+    L = np.array([16.0, 16.0, 1.0]) * nxa / np.array([1024, 1024, 256])
+    op = _op(ctx, nx, L=tuple(L))
+    dXi = L / nxa
+    lo = np.array([0, 0, -nx[2]])
+    bench.NX = tuple(nx)
+    res = bench.synthetic_residual(lo, lo + nxa - 1, dXi, 7)
+    rhs, phi, chk = op.field(data=res), op.field(), op.field()
+    del res
+    solver = sb.LevelHybridSolver(op, sb.default_options())
+    st = solver.solve(phi, rhs)
+    assert st.status == 1                                  # CONVERGED within maxIters = 10 FMG cycles
+    assert st.final_res_norm <= 1e-6 * st.norms[0]
+    assert all(b < a for a, b in zip(st.norms[:-1], st.norms[1:]))   # monotone, like the reference's hang/diverge tests demand
+    op.residual(chk, phi, rhs)
+    assert abs(op.norm(chk, 2) - st.final_res_norm) <= 1e-9 * st.norms[0]
+    solver.free()
+    op.free()
