@@ -81,6 +81,38 @@ inline Lay makeLay(const Box3& tile)
     return L;
 }
 
+// Colour-split ("checkerboard-compact") storage of a cell field, used inside the vertical line
+// relaxation.  A colour pass reads only cells of the other colour and writes only its own, so in
+// the natural layout every 32-byte sector moved is half wasted (stride-2 access in x).  Here the
+// two colours (i + j + lo0 + lo1) & 1 of the tile live in two separate arrays; cell (i, j, k) sits
+// at index SOX + floor(i / 2) of row (j, k) of its colour's array, so every access of a colour pass
+// is unit-stride.  One ghost in x and y, none in z (the line solve folds the vertical BCs).
+constexpr int SOX = 4;
+struct SLay {
+    int nx, ny, nz;
+    int par;           // (lo0 + lo1) & 1
+    int px, py;        // allocated extents of one colour array
+    long long sy, sz;  // strides (elements)
+    long long n;       // elements of one colour array
+    __host__ __device__ long long idx(int i, int j, int k) const
+    {
+        return (long long)(SOX + (i >> 1)) + sy * (long long)(1 + j) + sz * (long long)k;
+    }
+    __host__ __device__ int colour(int i, int j) const { return (par + i + j) & 1; }
+};
+inline SLay makeSLay(const Lay& L)
+{
+    SLay S;
+    S.nx = L.nx; S.ny = L.ny; S.nz = L.nz;
+    S.par = (L.lo0 + L.lo1) & 1;
+    S.px = ((SOX + (L.nx + 1) / 2 + 2 + 3) / 4) * 4;
+    S.py = L.ny + 2;
+    S.sy = S.px;
+    S.sz = (long long)S.px * S.py;
+    S.n  = S.sz * L.nz;
+    return S;
+}
+
 // What a side of the tile touches.
 enum SideKind { SIDE_PHYS = 0, SIDE_PERIODIC_SELF = 1, SIDE_NEIGHBOR = 2 };
 
@@ -144,6 +176,16 @@ void vertline_pass(cudaStream_t st, const Lay& L, const Coef& c, double* phi, co
 // shared-matrix fast path (see sb_kernels.cu); tab = [4][nz]
 size_t vertline_smem_bytes(int nz);
 void vertline_smem_pass(cudaStream_t st, const Lay& L, const Coef& c, const double* tab, double* phi, const double* rhs, int pass);
+// colour-split storage (SLay): conversion, ghost fill / face pack of directions x and y, and the
+// line relaxation on it.  s[c] = array of colour c.
+void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1);
+void unsplit_field(cudaStream_t st, const Lay& L, const SLay& S, double* nat, const double* s0, const double* s1);
+void fill_ghosts_split(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC bc[3][2], int dim, bool physToo);
+void pack_face_split(cudaStream_t st, const SLay& S, const double* s0, const double* s1, int dir, int side, double* buf);
+void unpack_face_split(cudaStream_t st, const SLay& S, double* s0, double* s1, int dir, int side, const double* buf);
+void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const double* tab, double* own, const double* oth,
+                         const double* rhs, int pass);
+bool vertline_split_fits(int nz);
 void j_deviation(cudaStream_t st, const Lay& L, const double* J, const double* jcol, double* out);
 
 void restrict_avg(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* crse, const double* fine);
