@@ -112,6 +112,29 @@ void Comm::exchangeFaces(Op& op, double* phi)
             if (op.side[d][s].kind == SIDE_NEIGHBOR) k::unpack_face(ctx->st, op.lay, phi, d, s, op.xbuf[d][s][1]);
 }
 
+void Comm::exchangeFacesSplit(Op& op, double* s0, double* s1)
+{
+    bool any = false;
+    for (int d = 0; d < 2; ++d)
+        for (int s = 0; s < 2; ++s)
+            if (op.side[d][s].kind == SIDE_NEIGHBOR) { k::pack_face_split(ctx->st, op.slay, s0, s1, d, s, op.xbuf[d][s][0]); any = true; }
+    if (!any) return;
+    SB_NCCL(api().GroupStart());
+    for (int d = 0; d < 2; ++d) {
+        const size_t n = (size_t)(d == 0 ? op.lay.ny : op.lay.nx) * op.lay.nz;
+        for (int s = 0; s < 2; ++s)
+            if (op.side[d][s].kind == SIDE_NEIGHBOR)
+                SB_NCCL(api().Send(op.xbuf[d][s][0], n, kNcclFloat64, op.side[d][s].neighbor, comm, ctx->st));
+        for (int s = 1; s >= 0; --s)
+            if (op.side[d][s].kind == SIDE_NEIGHBOR)
+                SB_NCCL(api().Recv(op.xbuf[d][s][1], n, kNcclFloat64, op.side[d][s].neighbor, comm, ctx->st));
+    }
+    SB_NCCL(api().GroupEnd());
+    for (int d = 0; d < 2; ++d)
+        for (int s = 0; s < 2; ++s)
+            if (op.side[d][s].kind == SIDE_NEIGHBOR) k::unpack_face_split(ctx->st, op.slay, s0, s1, d, s, op.xbuf[d][s][1]);
+}
+
 // One direction only, optionally extended over the ghosts of the other directions.
 void Comm::exchangeDir(Op& op, double* phi, int d, int ext0, int ext1)
 {

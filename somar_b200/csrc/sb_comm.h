@@ -17,6 +17,7 @@ struct Comm {
     void allreduceHost(double* v, int n, bool isMax);
     void exchangeFaces(Op& op, double* phi);
     void exchangeDir(Op& op, double* phi, int dir, int ext0, int ext1);
+    void exchangeFacesSplit(Op& op, double* s0, double* s1);  // same, on colour-split storage (x and y sides)
 };
 
 }  // namespace sb

@@ -178,7 +178,7 @@ size_t vertline_smem_bytes(int nz);
 void vertline_smem_pass(cudaStream_t st, const Lay& L, const Coef& c, const double* tab, double* phi, const double* rhs, int pass);
 // colour-split storage (SLay): conversion, ghost fill / face pack of directions x and y, and the
 // line relaxation on it.  s[c] = array of colour c.
-void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1);
+void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1, const double* scale);
 void unsplit_field(cudaStream_t st, const Lay& L, const SLay& S, double* nat, const double* s0, const double* s1);
 void fill_ghosts_split(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC bc[3][2], int dim, bool physToo);
 void pack_face_split(cudaStream_t st, const SLay& S, const double* s0, const double* s1, int dir, int side, double* buf);
@@ -186,6 +186,7 @@ void unpack_face_split(cudaStream_t st, const SLay& S, double* s0, double* s1, i
 void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const double* tab, double* own, const double* oth,
                          const double* rhs, int pass);
 bool vertline_split_fits(int nz);
+int  vertline_split_chunk(int nz);  // levels per warp chunk (the P/Q tables depend on it)
 void j_deviation(cudaStream_t st, const Lay& L, const double* J, const double* jcol, double* out);
 
 void restrict_avg(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* crse, const double* fine);

@@ -99,6 +99,12 @@ struct Op {
     int*    pivotFlag = nullptr;
     double* lineTab = nullptr;   // [4][nz] tables of the shared-matrix line relaxation (s, f, g, MzR)
     bool    lineFast = false;
+    // colour-split line relaxation (sb_line.cu): layout, tables [6][nz], scratch (cor0, cor1, res0, res1)
+    SLay    slay;
+    double* lineTabS = nullptr;
+    bool    lineSplit = false;
+    double* sp[4] = {nullptr, nullptr, nullptr, nullptr};
+    const double* splitResSrc = nullptr;  // natural-layout field whose split copy sp[2], sp[3] hold
     std::vector<double> hM[3];  // host copies of the 1-D tables over the whole domain (2*N_d)
     double* xbuf[3][2][2] = {};  // exchange buffers [dir][side][send/recv]
 
@@ -124,7 +130,8 @@ struct Op {
     void   exchange(double* phi);
     void   applyOp(double* lhs, double* phi, bool homog);
     void   residual(double* res, double* phi, const double* rhs, bool homog);
-    void   relax(double* cor, const double* res, int iters);
+    void   relax(double* cor, const double* res, int iters, bool resUnchanged = false);
+    void   relaxLineSplit(double* cor, const double* res, int iters, bool resUnchanged);
     void   preCond(double* phi, const double* rhs, int relaxIters);
     void   removeKernel(double* phi);
     double norm(const double* x, int p, double powScale = 1.0);

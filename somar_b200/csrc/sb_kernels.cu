@@ -14,6 +14,7 @@ namespace k {
 static long long g_launches = 0;
 long long launch_count() { return g_launches; }
 #define LAUNCHED() (++g_launches)
+void note_launch() { ++g_launches; }
 
 static inline dim3 grid3(int nx, int ny, int nz, dim3 b)
 {

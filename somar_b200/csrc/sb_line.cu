@@ -1,0 +1,316 @@
+// sb_line.cu -- vertical line relaxation on colour-split storage (sm_100a, fp64).
+//
+// Reference: PoissonOp::vertLineGSRB_relax (Grade3_Calculus/Elliptic/PoissonOp.cpp:1927-2010),
+// FORT_POISSONOP_VERTLINEGSRB_3D (Elliptic/PoissonOpF.ChF:851-1019) + LAPACK dgtsv.
+//
+// Why a second layout.  A colour pass reads only cells of the other colour and writes only its
+// own.  In the natural layout (x contiguous) that is stride-2 access: every 32-byte sector that
+// moves is half wasted, and the measured DRAM traffic of a pass was 7.1 GB against 3.2 GB of
+// bytes that are actually needed (profiles/r1_v2_summary.md).  Here the two colours
+// (i + j) & 1 (global indices) of a field live in two arrays (sb_core.h: SLay); cell (i, j, k) is
+// element SOX + (i >> 1) of row (j, k) of its colour's array, so every access of a pass is
+// unit-stride and every sector moved is fully used.  Op::relax converts cor/res once per call
+// (split_field_k / unsplit_field_k) and runs all its iterations on the split arrays.
+//
+// Why a chunked Thomas.  All columns of a depth share one tridiagonal matrix (see
+// Op::buildLineTables), so the two sweeps are first-order linear recurrences with known
+// coefficients, y_k = b_k + a_k y_{k-1} and x_k = z_k + c_k x_{k+1}.  Each of the NW warps of a
+// CTA owns a chunk of CL = ceil(nz / NW) levels of the CTA's 32 columns: it runs the recurrence
+// locally from a zero start and the true value is local + (prefix product of the coefficients)
+// * (carry from the neighbouring chunk); prefix products are 1-D tables, |a_k|, |c_k| < 1 for
+// the diagonally dominant matrices of this operator, so the correction is stable.  This makes
+// the sweeps NW times shorter than a thread-per-column Thomas and keeps every warp loading.
+// Same mathematics as dgtsv's no-interchange branch; rounding differs at the 1e-16 level.
+#include "sb_core.h"
+
+namespace sb {
+namespace k {
+
+void note_launch();  // sb_kernels.cu (launch counter)
+
+// cell (i, j, k) of a colour-split field: which array, which element
+__device__ __forceinline__ double* scell(const SLay& S, double* s0, double* s1, int i, int j, int k)
+{
+    return (S.colour(i, j) ? s1 : s0) + S.idx(i, j, k);
+}
+
+// ------------------------------------------------------------------------------------------
+// natural -> split (valid cells).  One thread moves the pair (2t, 2t+1) of a row; scale (may be
+// null) multiplies level k by scale[k] (the 1/(beta J_k) of the row-scaled system, applied to the
+// right-hand side once instead of in every pass).
+// ------------------------------------------------------------------------------------------
+__global__ void split_field_k(Lay L, SLay S, const double* __restrict__ nat, double* __restrict__ s0, double* __restrict__ s1,
+                              const double* __restrict__ scale)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    const int i = 2 * t;
+    if (i >= L.nx || j >= L.ny) return;
+    const double    f = scale ? scale[k] : 1.0;
+    const long long q = L.idx(i, j, k);
+    double          e, o = 0.0;
+    const bool      two = i + 1 < L.nx;
+    if (two) { const double2 v = *reinterpret_cast<const double2*>(nat + q); e = v.x; o = v.y; }
+    else e = nat[q];
+    if (scale) { e = e * f; o = o * f; }
+    const int       ce = S.colour(i, j);
+    const long long d  = S.idx(i, j, k);
+    (ce ? s1 : s0)[d] = e;
+    if (two) (ce ? s0 : s1)[d] = o;  // (i+1) >> 1 == i >> 1 for even i
+}
+__global__ void unsplit_field_k(Lay L, SLay S, double* __restrict__ nat, const double* __restrict__ s0,
+                                const double* __restrict__ s1)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    const int i = 2 * t;
+    if (i >= L.nx || j >= L.ny) return;
+    const long long q  = L.idx(i, j, k);
+    const int       ce = S.colour(i, j);
+    const long long d  = S.idx(i, j, k);
+    const double    e  = (ce ? s1 : s0)[d];
+    if (i + 1 < L.nx) {
+        const double o = (ce ? s0 : s1)[d];
+        *reinterpret_cast<double2*>(nat + q) = make_double2(e, o);
+    } else nat[q] = e;
+}
+void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1, const double* scale)
+{
+    const dim3 b(64, 4, 1);
+    const dim3 g(((L.nx + 1) / 2 + 63) / 64, (L.ny + 3) / 4, L.nz);
+    split_field_k<<<g, b, 0, st>>>(L, S, nat, s0, s1, scale);
+    note_launch();
+}
+void unsplit_field(cudaStream_t st, const Lay& L, const SLay& S, double* nat, const double* s0, const double* s1)
+{
+    const dim3 b(64, 4, 1);
+    const dim3 g(((L.nx + 1) / 2 + 63) / 64, (L.ny + 3) / 4, L.nz);
+    unsplit_field_k<<<g, b, 0, st>>>(L, S, nat, s0, s1);
+    note_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// Ghost fill of the x and y sides on split storage, one launch: the same Robin / periodic
+// formulas as fill_ghosts_dir_k (BCToolsF.ChF:222-337).  physToo = false refreshes only the
+// periodic images (what LevelData::exchange does between the colours, PoissonOp.cpp:1957-1965).
+// blockIdx.y = k; threads [0, ny) do the two x sides of row j, threads [ny, ny + nx) the two y
+// sides of column i.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ghost_one(const SLay& S, double* s0, double* s1, int dir, int side, int t, int k,
+                                          const SideBC& bc, bool physToo)
+{
+    const int nn = dir == 0 ? S.nx : S.ny;
+    int       g[2], p0[2], p1[2], w[2];  // (i, j) of ghost, first and second interior, periodic source
+    const int a = dir, b = 1 - dir;
+    g[a]  = side ? nn : -1;         g[b] = t;
+    p0[a] = side ? nn - 1 : 0;      p0[b] = t;
+    p1[a] = side ? nn - 2 : 1;      p1[b] = t;
+    w[a]  = side ? 0 : nn - 1;      w[b] = t;
+    if (bc.kind == SIDE_PHYS) {
+        if (!physToo) return;
+        double v;
+        if (bc.twoCells) {
+            const double cg = 3.0 * bc.a + bc.bb;
+            const double c0 = 6.0 * bc.a - bc.bb;
+            const double c1 = -1.0 * bc.a;
+            v = -(c0 * *scell(S, s0, s1, p0[0], p0[1], k) + c1 * *scell(S, s0, s1, p1[0], p1[1], k)) / cg;
+        } else {
+            const double cg = bc.a + bc.bb;
+            const double c0 = bc.a - bc.bb;
+            v = -(c0 * *scell(S, s0, s1, p0[0], p0[1], k)) / cg;
+        }
+        *scell(S, s0, s1, g[0], g[1], k) = v;
+    } else if (bc.kind == SIDE_PERIODIC_SELF) {
+        *scell(S, s0, s1, g[0], g[1], k) = *scell(S, s0, s1, w[0], w[1], k);
+    }
+}
+__global__ void fill_ghosts_split_k(SLay S, double* s0, double* s1, SideBC xlo, SideBC xhi, SideBC ylo, SideBC yhi, int doY,
+                                    int physToo)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (t < S.ny) {
+        ghost_one(S, s0, s1, 0, 0, t, k, xlo, physToo);
+        ghost_one(S, s0, s1, 0, 1, t, k, xhi, physToo);
+    } else if (doY && t < S.ny + S.nx) {
+        ghost_one(S, s0, s1, 1, 0, t - S.ny, k, ylo, physToo);
+        ghost_one(S, s0, s1, 1, 1, t - S.ny, k, yhi, physToo);
+    }
+}
+void fill_ghosts_split(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC bc[3][2], int dim, bool physToo)
+{
+    auto idle = [&](const SideBC& b) { return b.kind == SIDE_NEIGHBOR || b.kind < 0 || (b.kind == SIDE_PHYS && !physToo); };
+    const bool doY = dim == 3;
+    if (idle(bc[0][0]) && idle(bc[0][1]) && (!doY || (idle(bc[1][0]) && idle(bc[1][1])))) return;
+    const int n = S.ny + (doY ? S.nx : 0);
+    fill_ghosts_split_k<<<dim3((n + 127) / 128, S.nz), 128, 0, st>>>(S, s0, s1, bc[0][0], bc[0][1], bc[1][0], bc[1][1], doY,
+                                                                    physToo);
+    note_launch();
+}
+
+// Face layer pack / unpack for the neighbour exchange on split storage; buffer order as
+// pack_face_k: (tangential index, k), tangential = j for dir 0, i for dir 1.
+__global__ void pack_face_split_k(SLay S, double* s0, double* s1, int dir, int layer, double* buf, int unpack)
+{
+    const int t  = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k  = blockIdx.y;
+    const int nt = dir == 0 ? S.ny : S.nx;
+    if (t >= nt) return;
+    double* c = dir == 0 ? scell(S, s0, s1, layer, t, k) : scell(S, s0, s1, t, layer, k);
+    const long long m = t + (long long)nt * k;
+    if (unpack) *c = buf[m];
+    else buf[m] = *c;
+}
+void pack_face_split(cudaStream_t st, const SLay& S, const double* s0, const double* s1, int dir, int side, double* buf)
+{
+    const int nt = dir == 0 ? S.ny : S.nx, nn = dir == 0 ? S.nx : S.ny;
+    pack_face_split_k<<<dim3((nt + 127) / 128, S.nz), 128, 0, st>>>(S, const_cast<double*>(s0), const_cast<double*>(s1), dir,
+                                                                    side ? nn - 1 : 0, buf, 0);
+    note_launch();
+}
+void unpack_face_split(cudaStream_t st, const SLay& S, double* s0, double* s1, int dir, int side, const double* buf)
+{
+    const int nt = dir == 0 ? S.ny : S.nx, nn = dir == 0 ? S.nx : S.ny;
+    pack_face_split_k<<<dim3((nt + 127) / 128, S.nz), 128, 0, st>>>(S, s0, s1, dir, side ? nn : -1, const_cast<double*>(buf), 1);
+    note_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// The relaxation pass.  tab = [6][N]: s (unused here: folded into the split right-hand side),
+// a_k = -MzL_k / d'_{k-1}, P_k = prod_{m = chunk start..k} a_m, g_k = 1 / d'_k,
+// c_k = -MzR_k g_k, Q_k = prod_{m = k..chunk end} c_m.   own / oth: the colour being updated and
+// the other one; rhs: this colour's right-hand side, already multiplied by s_k.
+// ------------------------------------------------------------------------------------------
+constexpr int VL_NW = 8;  // warps per CTA = chunks per column (the tables are built for this)
+int vertline_split_chunk(int nz) { return (nz + VL_NW - 1) / VL_NW; }
+size_t vertline_split_smem(int nz) { return ((size_t)nz * 32 + 5 * (size_t)nz + 2 * VL_NW * 32) * sizeof(double); }
+bool vertline_split_fits(int nz) { return vertline_split_smem(nz) <= 110 * 1024; }
+
+template <int NW, int U, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+    vertline_split_k(SLay S, const double* __restrict__ mx, const double* __restrict__ my, const double* __restrict__ tab,
+                     double* __restrict__ own, const double* __restrict__ oth, const double* __restrict__ rhs, int pass, int CL)
+{
+    extern __shared__ double sm[];
+    const int     N  = S.nz;
+    double* const sy = sm;                     // [N][32] local sweeps, in place
+    double* const ta = sm + (size_t)N * 32;    // a
+    double* const tP = ta + N;
+    double* const tg = tP + N;
+    double* const tc = tg + N;
+    double* const tQ = tc + N;
+    double* const cy = tQ + N;                 // [NW][32] chunk-end values of the forward sweep
+    double* const cx = cy + NW * 32;           // [NW][32] chunk-start values of the backward sweep
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int j    = blockIdx.y;
+    const int i0   = (pass + S.par + j) & 1;   // own cells of this row: i = 2 m + i0
+    const int m    = blockIdx.x * 32 + lane;
+    const bool act = 2 * m + i0 < S.nx;
+    const int  mm  = act ? m : 0;
+    const int  ii  = 2 * mm + i0;
+    // tile-local 1-D tables: mx = [mxl | mxr] (nx each), my = [myl | myr] (ny each)
+    const double mxl = mx[ii], mxr = mx[S.nx + ii], myl = my[j], myr = my[S.ny + j];
+    for (int k = threadIdx.x; k < 5 * N; k += NW * 32) ta[k] = tab[N + k];
+    const long long sz = S.sz, sy_ = S.sy;
+    const long long base = (long long)(SOX + mm) + sy_ * (long long)(1 + j);
+    const double*   pw = oth + base + (i0 - 1);  // west neighbour (east = pw[1])
+    const double*   pc = oth + base;             // south = pc[-sy_], north = pc[+sy_]
+    const double*   pr = rhs + base;
+
+    const int k0 = w * CL, k1 = min(N, k0 + CL);
+    double    a0[U][5], a1[U][5];
+    auto issue = [&](double(&a)[U][5], int kk) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long o = (long long)min(kk + u, N - 1) * sz;
+            a[u][0] = pw[o]; a[u][1] = pw[o + 1]; a[u][2] = pc[o - sy_]; a[u][3] = pc[o + sy_]; a[u][4] = pr[o];
+        }
+    };
+    if (k0 < k1) issue(a0, k0);
+    __syncthreads();  // tables visible
+
+    // P1: right-hand sides and the local forward sweep of this warp's chunk.
+    double yl = 0.0;
+    auto consume = [&](double(&a)[U][5], int kk) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = kk + u;
+            if (k < k1) {
+                const double lphi = mxl * a[u][0] + mxr * a[u][1] + myl * a[u][2] + myr * a[u][3];
+                const double b    = act ? a[u][4] - lphi : 0.0;
+                yl                = fma(ta[k], yl, b);
+                sy[k * 32 + lane] = yl;
+            }
+        }
+    };
+    for (int kk = k0; kk < k1;) {
+        if (kk + U < k1) issue(a1, kk + U);
+        consume(a0, kk);
+        kk += U;
+        if (kk >= k1) break;
+        if (kk + U < k1) issue(a0, kk + U);
+        consume(a1, kk);
+        kk += U;
+    }
+    cy[w * 32 + lane] = yl;
+    __syncthreads();
+
+    // P2: true forward values from the carry, scaled, and the local backward sweep.
+    if (k0 < k1) {
+        double Y = 0.0;
+        for (int v = 0; v < w; ++v) Y = fma(tP[min(N, (v + 1) * CL) - 1], Y, cy[v * 32 + lane]);
+        double xl = 0.0;
+#pragma unroll 4
+        for (int k = k1 - 1; k >= k0; --k) {
+            const double y = fma(tP[k], Y, sy[k * 32 + lane]);
+            xl             = fma(tc[k], xl, y * tg[k]);
+            sy[k * 32 + lane] = xl;
+        }
+        cx[w * 32 + lane] = xl;
+    }
+    __syncthreads();
+
+    // P3: true solution from the backward carry; store.
+    if (k0 < k1) {
+        const int nch = (N + CL - 1) / CL;
+        double    X   = 0.0;
+        for (int v = nch - 1; v > w; --v) X = fma(tQ[v * CL], X, cx[v * 32 + lane]);
+        double* po = own + base;
+        if (act) {
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k) po[(long long)k * sz] = fma(tQ[k], X, sy[k * 32 + lane]);
+        }
+    }
+}
+
+void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const double* tab, double* own, const double* oth,
+                         const double* rhs, int pass)
+{
+    const size_t sh = vertline_split_smem(S.nz);
+    const int    CL = vertline_split_chunk(S.nz);
+    const dim3   g(((S.nx + 1) / 2 + 31) / 32, S.ny);
+    static int   variant = -1;
+    if (variant < 0) {
+        const char* e = getenv("SB_LINE_VARIANT");  // development knob
+        variant       = e ? atoi(e) : 0;
+    }
+#define SB_LAUNCH(U, MB)                                                                                              \
+    {                                                                                                                 \
+        static size_t configured = 0;                                                                                 \
+        if (sh > configured) {                                                                                        \
+            cudaFuncSetAttribute(vertline_split_k<VL_NW, U, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); \
+            configured = sh;                                                                                          \
+        }                                                                                                             \
+        vertline_split_k<VL_NW, U, MB><<<g, VL_NW * 32, sh, st>>>(S, c.mxl, c.myl, tab, own, oth, rhs, pass, CL);     \
+    }
+    if (variant == 1) SB_LAUNCH(2, 2)
+    else if (variant == 2) SB_LAUNCH(8, 1)
+    else SB_LAUNCH(4, 2)
+#undef SB_LAUNCH
+    note_launch();
+}
+
+}  // namespace k
+}  // namespace sb

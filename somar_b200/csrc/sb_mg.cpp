@@ -368,7 +368,7 @@ void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth)
     const int numCycles = std::abs(opt.numCycles);
     for (int i = 0; i < numCycles; ++i) vCycle_residualEq(crseCor, crseRes, depth + 1);
     op.MGProlong(crseOp, a_cor, crseCor, opt.prolongOrder);
-    op.relax(a_cor, a_res, opt.numSmoothUp);
+    op.relax(a_cor, a_res, opt.numSmoothUp, /*resUnchanged since the down-relax*/ opt.numSmoothDown >= 2);
 }
 
 // MGSolver<T>::fmg_residualEq (MGSolverI.H:758-820)

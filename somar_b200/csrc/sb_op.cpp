@@ -268,7 +268,8 @@ Op::~Op()
 {
     cudaFree(J); cudaFree(Dinv);
     for (int i = 0; i < 3; ++i) cudaFree(Jgup[i]);
-    cudaFree(lineTab);
+    cudaFree(lineTab); cudaFree(lineTabS);
+    for (double* q : sp) cudaFree(q);
     cudaFree(mtab); cudaFree(loBC); cudaFree(hiBC); cudaFree(boxLoHi); cudaFree(redPartial); cudaFree(redOut); cudaFree(pivotFlag);
     for (int d = 0; d < 3; ++d)
         for (int s = 0; s < 2; ++s)
@@ -485,6 +486,30 @@ void Op::buildLineTables(double sLo, double sHi)
     t[N + (N - 1)] = 0.0;
     SB_CUDA(cudaMemcpy(lineTab, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
     lineFast = true;
+
+    // Tables of the chunked sweeps on colour-split storage (sb_line.cu): s, a, P, g, c, Q.
+    lineSplit = false;
+    if (force && std::string(force) == "smem") return;
+    if (!k::vertline_split_fits(N)) return;
+    const int           CL = k::vertline_split_chunk(N);
+    std::vector<double> u(6 * (size_t)N);
+    for (int k = 0; k < N; ++k) {
+        u[k]         = t[k];
+        u[N + k]     = k > 0 ? t[N + (k - 1)] : 0.0;
+        u[3 * N + k] = t[2 * N + k];
+        u[4 * N + k] = k < N - 1 ? t[3 * N + k] : 0.0;
+    }
+    for (int k0 = 0; k0 < N; k0 += CL) {
+        const int k1 = std::min(N, k0 + CL);
+        double    p  = 1.0;
+        for (int k = k0; k < k1; ++k) { p *= u[N + k]; u[2 * N + k] = p; }
+        p = 1.0;
+        for (int k = k1 - 1; k >= k0; --k) { p *= u[4 * N + k]; u[5 * N + k] = p; }
+    }
+    if (!lineTabS) SB_CUDA(cudaMalloc((void**)&lineTabS, u.size() * sizeof(double)));
+    SB_CUDA(cudaMemcpy(lineTabS, u.data(), u.size() * sizeof(double), cudaMemcpyHostToDevice));
+    slay      = makeSLay(lay);
+    lineSplit = true;
 }
 
 // PoissonOp::checkForNullSpace (PoissonOp.cpp:670-696): L[1] == 0 to smallReal?
@@ -578,7 +603,40 @@ void Op::checkPivot()
 }
 
 // PoissonOp::relax (PoissonOp.cpp:917-955) and the relaxers behind it.
-void Op::relax(double* cor, const double* res, int iters)
+// Line relaxation on colour-split storage: convert once, iterate, convert back.  The call order
+// of the reference is kept: physical + exchange ghosts before the first colour, exchange ghosts
+// only before the second (PoissonOp.cpp:1957-1965).
+void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUnchanged)
+{
+    if (!sp[0]) {
+        for (double*& q : sp) {
+            SB_CUDA(cudaMalloc((void**)&q, slay.n * sizeof(double)));
+            SB_CUDA(cudaMemsetAsync(q, 0, slay.n * sizeof(double), ctx->st));
+        }
+        splitResSrc = nullptr;
+    }
+    cudaEvent_t e0;
+    ctx->profBegin("linesplit_convert", depth, &e0);
+    if (!(resUnchanged && splitResSrc == res)) {
+        k::split_field(st(), lay, slay, res, sp[2], sp[3], lineTabS);  // rhs_k / (beta J_k)
+        splitResSrc = res;
+    }
+    k::split_field(st(), lay, slay, cor, sp[0], sp[1], nullptr);
+    ctx->profEnd("linesplit_convert", depth, e0);
+    for (int it = 0; it < iters; ++it)
+        for (int pass = 0; pass < 2; ++pass) {
+            k::fill_ghosts_split(st(), slay, sp[0], sp[1], side, dim, pass == 0);
+            if (ctx->nranks > 1) ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1]);
+            ctx->profBegin("vertline", depth, &e0);
+            k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass);
+            ctx->profEnd("vertline", depth, e0);
+        }
+    ctx->profBegin("linesplit_convert", depth, &e0);
+    k::unsplit_field(st(), lay, slay, cor, sp[0], sp[1]);
+    ctx->profEnd("linesplit_convert", depth, e0);
+}
+
+void Op::relax(double* cor, const double* res, int iters, bool resUnchanged)
 {
     switch (relaxMethod) {
         case SB_RELAX_NONE: break;
@@ -597,6 +655,7 @@ void Op::relax(double* cor, const double* res, int iters)
             break;
         case SB_RELAX_VERTLINE: {  // PoissonOp.cpp:1927-2010
             if (iters == 0) return;
+            if (lineSplit && iters >= 2) { relaxLineSplit(cor, res, iters, resUnchanged); return; }
             const size_t n  = (size_t)((lay.nx + 1) / 2) * lay.ny * lay.nz;
             double*      wd = lineFast ? nullptr : (double*)ctx->getScratch(2 * n * sizeof(double));
             double*      wb = wd + (lineFast ? 0 : n);
