@@ -114,25 +114,28 @@ void Comm::exchangeFaces(Op& op, double* phi)
 
 void Comm::exchangeFacesSplit(Op& op, double* s0, double* s1)
 {
-    bool any = false;
+    double* snd[2][2];
+    double* rcv[2][2];
+    bool    any = false;
     for (int d = 0; d < 2; ++d)
-        for (int s = 0; s < 2; ++s)
-            if (op.side[d][s].kind == SIDE_NEIGHBOR) { k::pack_face_split(ctx->st, op.slay, s0, s1, d, s, op.xbuf[d][s][0]); any = true; }
+        for (int s = 0; s < 2; ++s) {
+            const bool nb = op.side[d][s].kind == SIDE_NEIGHBOR;
+            snd[d][s] = nb ? op.xbuf[d][s][0] : nullptr;
+            rcv[d][s] = nb ? op.xbuf[d][s][1] : nullptr;
+            any = any || nb;
+        }
     if (!any) return;
+    k::pack_faces_split(ctx->st, op.slay, s0, s1, snd, false);
     SB_NCCL(api().GroupStart());
     for (int d = 0; d < 2; ++d) {
         const size_t n = (size_t)(d == 0 ? op.lay.ny : op.lay.nx) * op.lay.nz;
         for (int s = 0; s < 2; ++s)
-            if (op.side[d][s].kind == SIDE_NEIGHBOR)
-                SB_NCCL(api().Send(op.xbuf[d][s][0], n, kNcclFloat64, op.side[d][s].neighbor, comm, ctx->st));
+            if (snd[d][s]) SB_NCCL(api().Send(snd[d][s], n, kNcclFloat64, op.side[d][s].neighbor, comm, ctx->st));
         for (int s = 1; s >= 0; --s)
-            if (op.side[d][s].kind == SIDE_NEIGHBOR)
-                SB_NCCL(api().Recv(op.xbuf[d][s][1], n, kNcclFloat64, op.side[d][s].neighbor, comm, ctx->st));
+            if (rcv[d][s]) SB_NCCL(api().Recv(rcv[d][s], n, kNcclFloat64, op.side[d][s].neighbor, comm, ctx->st));
     }
     SB_NCCL(api().GroupEnd());
-    for (int d = 0; d < 2; ++d)
-        for (int s = 0; s < 2; ++s)
-            if (op.side[d][s].kind == SIDE_NEIGHBOR) k::unpack_face_split(ctx->st, op.slay, s0, s1, d, s, op.xbuf[d][s][1]);
+    k::pack_faces_split(ctx->st, op.slay, s0, s1, rcv, true);
 }
 
 // One direction only, optionally extended over the ghosts of the other directions.
@@ -151,6 +154,95 @@ void Comm::exchangeDir(Op& op, double* phi, int d, int ext0, int ext1)
     SB_NCCL(api().GroupEnd());
     for (int s = 0; s < 2; ++s)
         if (op.side[d][s].kind == SIDE_NEIGHBOR) k::unpack_face(ctx->st, op.lay, phi, d, s, op.xbuf[d][s][1], ext0, ext1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Agglomeration traffic.  A tile region (valid cells, plus the far face for face-centred data) is
+// copied into a dense staging buffer with a device-to-device 3-D copy, sent to / received from
+// rank 0 with ncclSend/ncclRecv in one group, and copied into place on the other side.
+namespace {
+void tileExtent(const Box3& t, int centering, int n[3])
+{
+    for (int d = 0; d < 3; ++d) n[d] = t.size(d) + (d == centering ? 1 : 0);
+}
+// dense [n0][n1][n2] (x fastest) <-> layout L at tile-local offset off (cells)
+void copyDense(cudaStream_t st, const Lay& L, double* field, const int off[3], const int n[3], double* dense, bool toDense)
+{
+    cudaMemcpy3DParms p;
+    std::memset(&p, 0, sizeof(p));
+    cudaPitchedPtr hp = make_cudaPitchedPtr(dense, (size_t)n[0] * sizeof(double), (size_t)n[0], (size_t)n[1]);
+    cudaPitchedPtr dp = make_cudaPitchedPtr(field, (size_t)L.px * sizeof(double), (size_t)L.px, (size_t)L.py);
+    cudaPos        dpos = make_cudaPos((size_t)(OX + off[0]) * sizeof(double), (size_t)(1 + off[1]), (size_t)(1 + off[2]));
+    p.extent = make_cudaExtent((size_t)n[0] * sizeof(double), (size_t)n[1], (size_t)n[2]);
+    p.kind   = cudaMemcpyDeviceToDevice;
+    if (toDense) { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; }
+    else { p.srcPtr = hp; p.dstPtr = dp; p.dstPos = dpos; }
+    SB_CUDA(cudaMemcpy3DAsync(&p, st));
+}
+}  // namespace
+
+void Comm::gatherTiles(const Op& dist, const double* tileField, const Lay* full, double* fullField, int centering, double* buf)
+{
+    const int zero[3] = {0, 0, 0};
+    int       n[3];
+    if (ctx->rank != 0) {
+        tileExtent(dist.tile, centering, n);
+        copyDense(ctx->st, dist.lay, const_cast<double*>(tileField), zero, n, buf, true);
+        SB_NCCL(api().Send(buf, (size_t)n[0] * n[1] * n[2], kNcclFloat64, 0, comm, ctx->st));
+        return;
+    }
+    std::vector<size_t> at(ctx->nranks, 0);
+    size_t              o = 0;
+    SB_NCCL(api().GroupStart());
+    for (int r = 1; r < ctx->nranks; ++r) {
+        tileExtent(dist.tiles[r], centering, n);
+        at[r] = o;
+        SB_NCCL(api().Recv(buf + o, (size_t)n[0] * n[1] * n[2], kNcclFloat64, r, comm, ctx->st));
+        o += (size_t)n[0] * n[1] * n[2];
+    }
+    SB_NCCL(api().GroupEnd());
+    for (int r = 0; r < ctx->nranks; ++r) {
+        const Box3& t = dist.tiles[r];
+        tileExtent(t, centering, n);
+        const int off[3] = {t.lo[0] - full->lo0, t.lo[1] - full->lo1, t.lo[2] - full->lo2};
+        if (r == 0) {  // own tile: straight from the tile array, through the head of the staging buffer
+            double* own = buf + o;
+            copyDense(ctx->st, dist.lay, const_cast<double*>(tileField), zero, n, own, true);
+            copyDense(ctx->st, *full, fullField, off, n, own, false);
+        } else {
+            copyDense(ctx->st, *full, fullField, off, n, buf + at[r], false);
+        }
+    }
+}
+
+void Comm::scatterTiles(const Op& dist, double* tileField, const Lay* full, const double* fullField, double* buf)
+{
+    const int zero[3] = {0, 0, 0};
+    int       n[3];
+    if (ctx->rank != 0) {
+        tileExtent(dist.tile, SB_CELL, n);
+        SB_NCCL(api().Recv(buf, (size_t)n[0] * n[1] * n[2], kNcclFloat64, 0, comm, ctx->st));
+        copyDense(ctx->st, dist.lay, tileField, zero, n, buf, false);
+        return;
+    }
+    std::vector<size_t> at(ctx->nranks, 0);
+    size_t              o = 0;
+    for (int r = 0; r < ctx->nranks; ++r) {
+        const Box3& t = dist.tiles[r];
+        tileExtent(t, SB_CELL, n);
+        const int off[3] = {t.lo[0] - full->lo0, t.lo[1] - full->lo1, t.lo[2] - full->lo2};
+        at[r] = o;
+        copyDense(ctx->st, *full, const_cast<double*>(fullField), off, n, buf + o, true);
+        o += (size_t)n[0] * n[1] * n[2];
+    }
+    SB_NCCL(api().GroupStart());
+    for (int r = 1; r < ctx->nranks; ++r) {
+        tileExtent(dist.tiles[r], SB_CELL, n);
+        SB_NCCL(api().Send(buf + at[r], (size_t)n[0] * n[1] * n[2], kNcclFloat64, r, comm, ctx->st));
+    }
+    SB_NCCL(api().GroupEnd());
+    tileExtent(dist.tiles[0], SB_CELL, n);
+    copyDense(ctx->st, dist.lay, tileField, zero, n, buf + at[0], false);
 }
 
 }  // namespace sb

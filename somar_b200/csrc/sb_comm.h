@@ -18,6 +18,11 @@ struct Comm {
     void exchangeFaces(Op& op, double* phi);
     void exchangeDir(Op& op, double* phi, int dir, int ext0, int ext1);
     void exchangeFacesSplit(Op& op, double* s0, double* s1);  // same, on colour-split storage (x and y sides)
+    // Agglomeration: the tiles of `dist` (every rank) <-> one array over the whole domain on rank 0
+    // (layout `full`, meaningful on rank 0 only).  buf: staging, sum over ranks of tile sizes on
+    // rank 0, one tile elsewhere.  centering: SB_CELL or the face direction.
+    void gatherTiles(const Op& dist, const double* tileField, const Lay* full, double* fullField, int centering, double* buf);
+    void scatterTiles(const Op& dist, double* tileField, const Lay* full, const double* fullField, double* buf);
 };
 
 }  // namespace sb

@@ -181,8 +181,7 @@ void vertline_smem_pass(cudaStream_t st, const Lay& L, const Coef& c, const doub
 void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1, const double* scale);
 void unsplit_field(cudaStream_t st, const Lay& L, const SLay& S, double* nat, const double* s0, const double* s1);
 void fill_ghosts_split(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC bc[3][2], int dim, bool physToo);
-void pack_face_split(cudaStream_t st, const SLay& S, const double* s0, const double* s1, int dir, int side, double* buf);
-void unpack_face_split(cudaStream_t st, const SLay& S, double* s0, double* s1, int dir, int side, const double* buf);
+void pack_faces_split(cudaStream_t st, const SLay& S, double* s0, double* s1, double* const bufs[2][2], bool unpack);
 void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const double* tab, double* own, const double* oth,
                          const double* rhs, int pass);
 bool vertline_split_fits(int nz);

@@ -19,6 +19,7 @@ struct Context {
     void*        scratch = nullptr;  // device scratch shared by all depths (line-relax workspace)
     size_t       scratchBytes = 0;
     Comm*        comm = nullptr;
+    Context*     parent = nullptr;  // set on the single-rank view used by agglomerated MG depths: stream and profile are the parent's
     long long    launches0 = 0;
     // optional per-kernel timing (CUDA events on `st` around selected launches)
     bool         profiling = false;
@@ -30,6 +31,7 @@ struct Context {
     void profResolve();
 
     Context(int dev, int rank, int nranks);
+    explicit Context(Context& parent);  // single-rank view on the parent's device and stream
     ~Context();
     void* getScratch(size_t bytes);
     void  sync() { SB_CUDA(cudaStreamSynchronize(st)); }
@@ -110,6 +112,7 @@ struct Op {
 
     Op(Context* ctx, const sb_level_desc& d);
     Op(const Op& fine, const int ref[3]);  // coarsening ctor, PoissonOp.cpp:334-405
+    Op(Context* single, const Op& dist);   // same depth, every box on the one rank of `single` (agglomeration); J/Jgup left to the caller
     ~Op();
     Op& operator=(const Op&) = delete;
 
@@ -189,6 +192,18 @@ struct MGSolver {
     SolverStatus                     status;
     std::vector<double>              absResNorms;  // history of the last solve
     int                              lastIters = 0;
+    // Agglomeration: with more than one rank, depths >= aggDepth live on rank 0 only.
+    // ops[aggDepth] stays distributed (restriction target / prolongation source); rank 0 also
+    // owns aggTop (the same depth, all boxes) and `agg`, the solver of the remaining hierarchy.
+    int                              aggDepth = -1;
+    std::unique_ptr<Context>         aggCtx;
+    std::unique_ptr<Op>              aggTop;
+    std::unique_ptr<MGSolver>        agg;
+    double *                         aggRes = nullptr, *aggCor = nullptr, *aggBuf = nullptr;
+    void defineAgglomeration();
+    void aggGather(const double* tileField, double* fullField, int centering, const Op& distOp);
+    void aggScatter(double* tileField, const double* fullField, const Op& distOp);
+    void checkPivotAll();
 
     void define(Op& top, const sb_mg_options& opt, std::vector<std::array<int, 3>> sched, bool useBottomSolver = true);
     ~MGSolver();

@@ -152,28 +152,32 @@ void fill_ghosts_split(cudaStream_t st, const SLay& S, double* s0, double* s1, c
 
 // Face layer pack / unpack for the neighbour exchange on split storage; buffer order as
 // pack_face_k: (tangential index, k), tangential = j for dir 0, i for dir 1.
-__global__ void pack_face_split_k(SLay S, double* s0, double* s1, int dir, int layer, double* buf, int unpack)
+struct FaceBufs { double* b[2][2]; };  // [dir][side], null = side not exchanged
+__global__ void pack_face_split_k(SLay S, double* s0, double* s1, FaceBufs fb, int unpack)
 {
+    const int dir = blockIdx.z >> 1, side = blockIdx.z & 1;
+    double*   buf = fb.b[dir][side];
+    if (!buf) return;
     const int t  = blockIdx.x * blockDim.x + threadIdx.x;
     const int k  = blockIdx.y;
-    const int nt = dir == 0 ? S.ny : S.nx;
+    const int nt = dir == 0 ? S.ny : S.nx, nn = dir == 0 ? S.nx : S.ny;
     if (t >= nt) return;
+    const int layer = unpack ? (side ? nn : -1) : (side ? nn - 1 : 0);
     double* c = dir == 0 ? scell(S, s0, s1, layer, t, k) : scell(S, s0, s1, t, layer, k);
     const long long m = t + (long long)nt * k;
     if (unpack) *c = buf[m];
     else buf[m] = *c;
 }
-void pack_face_split(cudaStream_t st, const SLay& S, const double* s0, const double* s1, int dir, int side, double* buf)
+// all exchanged sides in one launch; bufs[dir][side] (x and y only), null where there is no neighbour
+void pack_faces_split(cudaStream_t st, const SLay& S, double* s0, double* s1, double* const bufs[2][2], bool unpack)
 {
-    const int nt = dir == 0 ? S.ny : S.nx, nn = dir == 0 ? S.nx : S.ny;
-    pack_face_split_k<<<dim3((nt + 127) / 128, S.nz), 128, 0, st>>>(S, const_cast<double*>(s0), const_cast<double*>(s1), dir,
-                                                                    side ? nn - 1 : 0, buf, 0);
-    note_launch();
-}
-void unpack_face_split(cudaStream_t st, const SLay& S, double* s0, double* s1, int dir, int side, const double* buf)
-{
-    const int nt = dir == 0 ? S.ny : S.nx, nn = dir == 0 ? S.nx : S.ny;
-    pack_face_split_k<<<dim3((nt + 127) / 128, S.nz), 128, 0, st>>>(S, s0, s1, dir, side ? nn : -1, const_cast<double*>(buf), 1);
+    FaceBufs fb;
+    bool     any = false;
+    for (int d = 0; d < 2; ++d)
+        for (int sd = 0; sd < 2; ++sd) { fb.b[d][sd] = bufs[d][sd]; any = any || bufs[d][sd]; }
+    if (!any) return;
+    const int nt = S.nx > S.ny ? S.nx : S.ny;
+    pack_face_split_k<<<dim3((nt + 127) / 128, S.nz, 4), 128, 0, st>>>(S, s0, s1, fb, unpack ? 1 : 0);
     note_launch();
 }
 
@@ -183,12 +187,34 @@ void unpack_face_split(cudaStream_t st, const SLay& S, double* s0, double* s1, i
 // c_k = -MzR_k g_k, Q_k = prod_{m = k..chunk end} c_m.   own / oth: the colour being updated and
 // the other one; rhs: this colour's right-hand side, already multiplied by s_k.
 // ------------------------------------------------------------------------------------------
-constexpr int VL_NW = 8;  // warps per CTA = chunks per column (the tables are built for this)
-int vertline_split_chunk(int nz) { return (nz + VL_NW - 1) / VL_NW; }
-size_t vertline_split_smem(int nz) { return ((size_t)nz * 32 + 5 * (size_t)nz + 2 * VL_NW * 32) * sizeof(double); }
+// Launch shape (development knob SB_LINE_VARIANT, read once): warps per CTA = chunks per column
+// (the P/Q tables are built for it), loads in flight per thread, CTAs per SM, tables in shared
+// memory or read through L1.
+struct LineVariant { int nw, u, minb, tg; };
+static LineVariant line_variant()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SB_LINE_VARIANT"); v = e ? atoi(e) : 0; }
+    switch (v) {
+        case 1: return {8, 2, 2, 0};
+        case 2: return {8, 8, 1, 0};
+        case 3: return {8, 2, 3, 1};
+        case 4: return {16, 2, 2, 0};
+        case 5: return {16, 1, 2, 0};
+        case 6: return {8, 4, 3, 1};
+        case 7: return {16, 2, 2, 1};
+        default: return {8, 4, 2, 0};
+    }
+}
+int vertline_split_chunk(int nz) { const int nw = line_variant().nw; return (nz + nw - 1) / nw; }
+size_t vertline_split_smem(int nz)
+{
+    const LineVariant v = line_variant();
+    return ((size_t)nz * 32 + (v.tg ? 0 : 5 * (size_t)nz) + 2 * (size_t)v.nw * 32) * sizeof(double);
+}
 bool vertline_split_fits(int nz) { return vertline_split_smem(nz) <= 110 * 1024; }
 
-template <int NW, int U, int MINB>
+template <int NW, int U, int MINB, bool TG>
 __global__ void __launch_bounds__(NW * 32, MINB)
     vertline_split_k(SLay S, const double* __restrict__ mx, const double* __restrict__ my, const double* __restrict__ tab,
                      double* __restrict__ own, const double* __restrict__ oth, const double* __restrict__ rhs, int pass, int CL)
@@ -196,13 +222,14 @@ __global__ void __launch_bounds__(NW * 32, MINB)
     extern __shared__ double sm[];
     const int     N  = S.nz;
     double* const sy = sm;                     // [N][32] local sweeps, in place
-    double* const ta = sm + (size_t)N * 32;    // a
-    double* const tP = ta + N;
-    double* const tg = tP + N;
-    double* const tc = tg + N;
-    double* const tQ = tc + N;
-    double* const cy = tQ + N;                 // [NW][32] chunk-end values of the forward sweep
+    double* const cy = sm + (size_t)N * 32;    // [NW][32] chunk-end values of the forward sweep
     double* const cx = cy + NW * 32;           // [NW][32] chunk-start values of the backward sweep
+    double* const ts = cx + NW * 32;           // tables a, P, g, c, Q staged here unless TG
+    const double* const ta = TG ? tab + N : ts;
+    const double* const tP = ta + N;
+    const double* const tg = tP + N;
+    const double* const tc = tg + N;
+    const double* const tQ = tc + N;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int j    = blockIdx.y;
     const int i0   = (pass + S.par + j) & 1;   // own cells of this row: i = 2 m + i0
@@ -212,7 +239,7 @@ __global__ void __launch_bounds__(NW * 32, MINB)
     const int  ii  = 2 * mm + i0;
     // tile-local 1-D tables: mx = [mxl | mxr] (nx each), my = [myl | myr] (ny each)
     const double mxl = mx[ii], mxr = mx[S.nx + ii], myl = my[j], myr = my[S.ny + j];
-    for (int k = threadIdx.x; k < 5 * N; k += NW * 32) ta[k] = tab[N + k];
+    if (!TG) for (int k = threadIdx.x; k < 5 * N; k += NW * 32) ts[k] = tab[N + k];
     const long long sz = S.sz, sy_ = S.sy;
     const long long base = (long long)(SOX + mm) + sy_ * (long long)(1 + j);
     const double*   pw = oth + base + (i0 - 1);  // west neighbour (east = pw[1])
@@ -291,23 +318,24 @@ void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const do
     const size_t sh = vertline_split_smem(S.nz);
     const int    CL = vertline_split_chunk(S.nz);
     const dim3   g(((S.nx + 1) / 2 + 31) / 32, S.ny);
-    static int   variant = -1;
-    if (variant < 0) {
-        const char* e = getenv("SB_LINE_VARIANT");  // development knob
-        variant       = e ? atoi(e) : 0;
-    }
-#define SB_LAUNCH(U, MB)                                                                                              \
+    const LineVariant v = line_variant();
+#define SB_LAUNCH(NWv, U, MB, TGv)                                                                                    \
     {                                                                                                                 \
         static size_t configured = 0;                                                                                 \
         if (sh > configured) {                                                                                        \
-            cudaFuncSetAttribute(vertline_split_k<VL_NW, U, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); \
+            cudaFuncSetAttribute(vertline_split_k<NWv, U, MB, TGv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); \
             configured = sh;                                                                                          \
         }                                                                                                             \
-        vertline_split_k<VL_NW, U, MB><<<g, VL_NW * 32, sh, st>>>(S, c.mxl, c.myl, tab, own, oth, rhs, pass, CL);     \
+        vertline_split_k<NWv, U, MB, TGv><<<g, NWv * 32, sh, st>>>(S, c.mxl, c.myl, tab, own, oth, rhs, pass, CL);    \
     }
-    if (variant == 1) SB_LAUNCH(2, 2)
-    else if (variant == 2) SB_LAUNCH(8, 1)
-    else SB_LAUNCH(4, 2)
+    if (v.nw == 8 && v.u == 2 && v.minb == 2) SB_LAUNCH(8, 2, 2, false)
+    else if (v.nw == 8 && v.u == 8) SB_LAUNCH(8, 8, 1, false)
+    else if (v.nw == 8 && v.u == 2 && v.minb == 3) SB_LAUNCH(8, 2, 3, true)
+    else if (v.nw == 8 && v.u == 4 && v.minb == 3) SB_LAUNCH(8, 4, 3, true)
+    else if (v.nw == 16 && v.u == 2 && !v.tg) SB_LAUNCH(16, 2, 2, false)
+    else if (v.nw == 16 && v.u == 2 && v.tg) SB_LAUNCH(16, 2, 2, true)
+    else if (v.nw == 16 && v.u == 1) SB_LAUNCH(16, 1, 2, false)
+    else SB_LAUNCH(8, 4, 2, false)
 #undef SB_LAUNCH
     note_launch();
 }

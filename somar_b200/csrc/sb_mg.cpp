@@ -8,6 +8,7 @@
 #include <cmath>
 #include <limits>
 
+#include "sb_comm.h"
 #include "sb_host.h"
 
 namespace sb {
@@ -248,27 +249,87 @@ void MGSolver::define(Op& top, const sb_mg_options& a_opt, std::vector<IV> sched
     }
     if (refSchedule.empty() || refSchedule.back() != IV{1, 1, 1}) SB_FAIL("the MG ref schedule must end with (1,1,1)");
     opt.maxDepth = (int)refSchedule.size() - 1;
-    ops.assign(opt.maxDepth + 1, nullptr);
+    // Agglomeration: the first depth >= 1 whose whole domain has at most SB_AGG_CELLS cells
+    // (default 4 Mi; 0 disables) and everything below it run on rank 0 alone.  The arithmetic is
+    // decomposition-independent (colours use global indices, ghosts are refreshed between
+    // colours), so this changes where the work runs, not its result.
+    aggDepth = -1;
+    if (top.ctx->nranks > 1 && opt.maxDepth >= 1) {
+        const char* e     = getenv("SB_AGG_CELLS");
+        long long   limit = e ? atoll(e) : (4LL << 20);
+        Box3        dom   = top.domain;
+        for (int d = 1; d <= opt.maxDepth && limit > 0; ++d) {
+            dom = coarsen(dom, refSchedule[d - 1].data());
+            if (dom.numPts() <= limit) { aggDepth = d; break; }
+        }
+    }
+    const int lastDist = aggDepth >= 0 ? aggDepth : opt.maxDepth;  // deepest depth held in ops[]
+    ops.assign(lastDist + 1, nullptr);
     ops[0] = &top;
-    for (int d = 1; d <= opt.maxDepth; ++d) {
+    for (int d = 1; d <= lastDist; ++d) {
         owned.emplace_back(new Op(*ops[d - 1], refSchedule[d - 1].data()));
         ops[d] = owned.back().get();
     }
-    tmpRes.assign(opt.maxDepth + 1, nullptr);
-    cor.assign(opt.maxDepth + 1, nullptr);
-    res.assign(opt.maxDepth + 1, nullptr);
-    for (int d = 0; d <= opt.maxDepth; ++d) {
-        tmpRes[d] = ops[d]->alloc();
+    tmpRes.assign(lastDist + 1, nullptr);
+    cor.assign(lastDist + 1, nullptr);
+    res.assign(lastDist + 1, nullptr);
+    for (int d = 0; d <= lastDist; ++d) {
+        if (d != aggDepth) tmpRes[d] = ops[d]->alloc();
         if (d > 0) { cor[d] = ops[d]->alloc(); res[d] = ops[d]->alloc(); }
     }
     topRes = top.alloc();
     topCor = top.alloc();
-    if (useBottomSolver) {
+    if (aggDepth >= 0) defineAgglomeration();
+    else if (useBottomSolver) {
         bottom.reset(new BiCGStabSolver);
         bottom->define(ops[opt.maxDepth]);
         bottom->opt = opt.bottom;
     }
     status.clear();
+}
+void MGSolver::defineAgglomeration()
+{
+    Op&      dist = *ops[aggDepth];
+    Context* ctx  = dist.ctx;
+    // staging: every tile with room for its far faces
+    auto ext = [](const Box3& t) { return (size_t)(t.size(0) + 1) * (t.size(1) + 1) * (t.size(2) + 1); };
+    size_t n = ext(dist.tile);
+    if (ctx->rank == 0) for (const Box3& t : dist.tiles) n += ext(t);
+    SB_CUDA(cudaMalloc((void**)&aggBuf, n * sizeof(double)));
+    if (ctx->rank == 0) {
+        aggCtx.reset(new Context(*ctx));
+        aggTop.reset(new Op(aggCtx.get(), dist));
+    }
+    const Lay* full = aggTop ? &aggTop->lay : nullptr;
+    ctx->comm->gatherTiles(dist, dist.J, full, aggTop ? aggTop->J : nullptr, SB_CELL, aggBuf);
+    for (int d = 0; d < 3; ++d) {
+        if (dist.dim == 2 && d == 1) continue;
+        ctx->comm->gatherTiles(dist, dist.Jgup[d], full, aggTop ? aggTop->Jgup[d] : nullptr, d, aggBuf);
+    }
+    ctx->sync();
+    if (ctx->rank != 0) return;
+    aggTop->cacheMatrixElements();
+    aggTop->finalized = true;
+    aggRes = aggTop->alloc();
+    aggCor = aggTop->alloc();
+    agg.reset(new MGSolver);
+    sb_mg_options o = opt;
+    o.maxDepth      = opt.maxDepth - aggDepth;
+    agg->define(*aggTop, o, std::vector<IV>(refSchedule.begin() + aggDepth, refSchedule.end()), true);
+    agg->bottom->opt = opt.bottom;
+}
+void MGSolver::aggGather(const double* tileField, double* fullField, int centering, const Op& distOp)
+{
+    distOp.ctx->comm->gatherTiles(distOp, tileField, aggTop ? &aggTop->lay : nullptr, fullField, centering, aggBuf);
+}
+void MGSolver::aggScatter(double* tileField, const double* fullField, const Op& distOp)
+{
+    distOp.ctx->comm->scatterTiles(distOp, tileField, aggTop ? &aggTop->lay : nullptr, fullField, aggBuf);
+}
+void MGSolver::checkPivotAll()
+{
+    for (Op* o : ops) o->checkPivot();
+    if (agg) agg->checkPivotAll();
 }
 MGSolver::~MGSolver()
 {
@@ -277,6 +338,12 @@ MGSolver::~MGSolver()
     for (auto* q : res) if (q) cudaFree(q);
     if (topRes) cudaFree(topRes);
     if (topCor) cudaFree(topCor);
+    if (aggRes) cudaFree(aggRes);
+    if (aggCor) cudaFree(aggCor);
+    if (aggBuf) cudaFree(aggBuf);
+    agg.reset();     // before the ops and the context it uses
+    aggTop.reset();
+    aggCtx.reset();
 }
 void MGSolver::modifyOptionsExceptMaxDepth(const sb_mg_options& o)
 {
@@ -284,6 +351,7 @@ void MGSolver::modifyOptionsExceptMaxDepth(const sb_mg_options& o)
     opt           = o;
     opt.maxDepth  = old;
     if (bottom) bottom->opt = o.bottom;
+    if (agg) { sb_mg_options a = o; a.maxDepth = agg->opt.maxDepth; agg->opt = a; agg->bottom->opt = o.bottom; }
 }
 
 SolverStatus MGSolver::solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double metric)
@@ -343,14 +411,21 @@ SolverStatus MGSolver::cycle(bool fmgMode, double* phi, const double* rhs, bool 
         if (relResNorms[iter] > (1.0 - opt.hang) * relResNorms[iter - 1]) { status.status = SB_STATUS_HANG; break; }
     }
     status.finalResNorm = absResNorms.back();
-    if (op.relaxMethod == SB_RELAX_VERTLINE)
-        for (Op* o : ops) o->checkPivot();
+    if (op.relaxMethod == SB_RELAX_VERTLINE) checkPivotAll();
     return status;
 }
 
 // MGSolver<T>::vCycle_residualEq (MGSolverI.H:617-754)
 void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth)
 {
+    if (depth == aggDepth) {  // the rest of the hierarchy runs on rank 0
+        Op& dist = *ops[depth];
+        aggGather(a_res, aggRes, SB_CELL, dist);
+        aggGather(a_cor, aggCor, SB_CELL, dist);
+        if (agg) agg->vCycle_residualEq(aggCor, aggRes, 0);
+        aggScatter(a_cor, aggCor, dist);
+        return;
+    }
     Op& op = *ops[depth];
     if (depth == opt.maxDepth) {
         op.relax(a_cor, a_res, opt.numSmoothBottom);
@@ -374,6 +449,13 @@ void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth)
 // MGSolver<T>::fmg_residualEq (MGSolverI.H:758-820)
 void MGSolver::fmg_residualEq(double* a_cor, const double* a_res, int depth)
 {
+    if (depth == aggDepth) {
+        Op& dist = *ops[depth];
+        aggGather(a_res, aggRes, SB_CELL, dist);
+        if (agg) agg->fmg_residualEq(aggCor, aggRes, 0);
+        aggScatter(a_cor, aggCor, dist);
+        return;
+    }
     Op& op = *ops[depth];
     op.setToZero(a_cor);
     if (depth < opt.maxDepth) {

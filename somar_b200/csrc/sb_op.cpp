@@ -23,15 +23,22 @@ Context::Context(int dev, int rank_, int nranks_) : device(dev), rank(rank_), nr
     SB_CUDA(cudaMallocHost((void**)&hpin, hpinLen * sizeof(double)));
     launches0 = k::launch_count();
 }
+Context::Context(Context& p) : device(p.device), rank(0), nranks(1), st(p.st), parent(&p)
+{
+    hpinLen = 1 << 16;
+    SB_CUDA(cudaMallocHost((void**)&hpin, hpinLen * sizeof(double)));
+    launches0 = k::launch_count();
+}
 Context::~Context()
 {
     delete comm;
     if (scratch) cudaFree(scratch);
     if (hpin) cudaFreeHost(hpin);
-    if (st) cudaStreamDestroy(st);
+    if (st && !parent) cudaStreamDestroy(st);
 }
-void Context::profBegin(const char*, int, cudaEvent_t* e0)
+void Context::profBegin(const char* key, int depth, cudaEvent_t* e0)
 {
+    if (parent) { parent->profBegin(key, depth, e0); return; }
     *e0 = nullptr;
     if (!profiling) return;
     SB_CUDA(cudaEventCreate(e0));
@@ -39,6 +46,7 @@ void Context::profBegin(const char*, int, cudaEvent_t* e0)
 }
 void Context::profEnd(const char* key, int depth, cudaEvent_t e0)
 {
+    if (parent) { parent->profEnd(key, depth, e0); return; }
     if (!profiling || !e0) return;
     cudaEvent_t e1;
     SB_CUDA(cudaEventCreate(&e1));
@@ -348,6 +356,26 @@ Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
     hasNullSpace = f.hasNullSpace;
     cacheMatrixElements();
     finalized = true;
+}
+
+// Agglomerated copy of a distributed depth: same geometry and boxes, all owned by the single rank
+// of `single`.  The caller gathers J and Jgup from the tiles (they were block-averaged from the
+// finer depth, PoissonOp.cpp:368-395, so they cannot be rebuilt from the map) and then calls
+// cacheMatrixElements().
+Op::Op(Context* single, const Op& f) : ctx(single)
+{
+    dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth;
+    std::memcpy(periodic, f.periodic, sizeof(periodic));
+    std::memcpy(bcAlpha, f.bcAlpha, sizeof(bcAlpha));
+    std::memcpy(bcBeta, f.bcBeta, sizeof(bcBeta));
+    std::memcpy(dXi, f.dXi, sizeof(dXi));
+    domain = f.domain;
+    boxes  = f.boxes;
+    boxRank.assign(boxes.size(), 0);
+    setupLayout();
+    J = alloc();
+    for (int d = 0; d < 3; ++d) Jgup[d] = alloc();
+    hasNullSpace = f.hasNullSpace;
 }
 
 // PoissonOp::cacheMatrixElements (PoissonOp.cpp:510-665).

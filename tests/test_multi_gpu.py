@@ -23,23 +23,36 @@ def _ngpu():
         return 0
 
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs"),
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(_ngpu() < int(os.environ.get("SB_TEST_WORLD", "2")), reason="needs SB_TEST_WORLD (default 2) GPUs"),
               pytest.mark.skipif(not have_ref(3), reason="oracle/_ref/d3/somar_ref not built")]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+WORLD = int(os.environ.get("SB_TEST_WORLD", "2"))  # ranks = GPUs used by the worker
 
 
-@pytest.mark.parametrize("name,optset", [("line_cart", "defaults"), ("line_stretch", "defaults"), ("line_perx", "defaults"),
-                                         ("gsrb_cart", "defaults"), ("gsrb_perxy", "vcycle"), ("line_aniso", "vcycle")])
-def test_two_rank_solve(name, optset):
+# agg: SB_AGG_CELLS, the size below which MG depths are agglomerated onto rank 0 (None = library default, which puts every
+# depth >= 1 of these small cases on rank 0; "0" = every depth distributed; a number in between = a deeper switch-over).
+@pytest.mark.parametrize("name,optset,agg", [("line_cart", "defaults", None), ("line_stretch", "defaults", None),
+                                             ("line_perx", "defaults", None), ("gsrb_cart", "defaults", None),
+                                             ("gsrb_perxy", "vcycle", None), ("line_aniso", "vcycle", None),
+                                             ("line_cart", "defaults", "0"), ("line_stretch", "defaults", "0"),
+                                             ("line_perx", "defaults", "0"), ("gsrb_cart", "defaults", "0"),
+                                             ("gsrb_perxy", "vcycle", "0"), ("line_aniso", "vcycle", "0"),
+                                             ("line_stretch", "defaults", "300"), ("line_aniso", "vcycle", "1100"),
+                                             ("gsrb_cart", "vcycle", "600")])
+def test_two_rank_solve(name, optset, agg):
     c = CASES[name]
     ref = run_ref("solve", inp=[rand_field(c, 4, zero_mean=True)], extra=_proj_overrides({} if optset == "defaults" else V_OPTS),
                   **ref_kwargs(c))
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, "res.json")
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={WORLD}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", os.path.join(HERE, "mgpu_worker.py"), name, optset, out]
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        env = dict(os.environ)
+        env.pop("SB_AGG_CELLS", None)
+        if agg is not None:
+            env["SB_AGG_CELLS"] = agg
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
         res = json.load(open(out))
         phi = np.load(out + ".phi.npy")
