@@ -88,7 +88,8 @@ typedef struct sb_solver_status {
     double init_res_norm;                 /* SolverStatus::getInitResNorm                       */
     double final_res_norm;                /* SolverStatus::getFinalResNorm                      */
     int    num_norms;                     /* entries of res_norms                               */
-    double res_norms[SB_MAX_HISTORY];     /* absResNorms of MGSolverI.H:281,360 in call order   */
+    double res_norms[SB_MAX_HISTORY];     /* MG mode: absResNorms of MGSolverI.H:281,360 in call order; leptic modes:
+                                             LevelHybridSolver's m_resNorms (LevelHybridSolver.cpp:312-400) */
     int    solve_mode;                    /* SB_MODE_* (hybrid solver only)                     */
     int    max_depth;                     /* MGSolver::Options::maxDepth after define           */
     double device_ms;                     /* CUDA-event time of the solve on this rank          */

@@ -340,7 +340,11 @@ main(int argc, char* argv[])
     }
 
     // Solver.
-    Elliptic::LevelHybridSolver          hybrid;
+    // LevelHybridSolver keeps its residual-norm history (initial, then one entry per leptic order /
+    // V-cycle, LevelHybridSolver.cpp:312-400) in a protected member; expose it.
+    struct HybridPeek : Elliptic::LevelHybridSolver {
+        const std::vector<Real>& resNorms() const { return m_resNorms; }
+    } hybrid;
     Elliptic::MGSolver<LDFAB>            mg;
     Elliptic::LevelHybridSolver::Options hopt = Elliptic::LevelHybridSolver::getDefaultOptions();
     if (useMGSolver) {
@@ -433,6 +437,7 @@ main(int argc, char* argv[])
     }
     out.put("phi", gather(phi, domBox));
     out.put("norms", firstNorms);
+    if (!useMGSolver) out.put("hybridNorms", hybrid.resNorms());
     out.put("solveTimes", times);
     out.kv("status", status.getSolverStatus());
     out.kv("initResNorm", status.getInitResNorm());

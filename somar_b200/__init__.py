@@ -466,7 +466,8 @@ class MGSolver(_SolverBase):
 
 
 class LevelHybridSolver(_SolverBase):
-    """Elliptic::LevelHybridSolver::define(mgOp, opts): picks the mode by lepticity (MG only here)."""
+    """Elliptic::LevelHybridSolver::define(mgOp, opts): picks MG, Leptic or Leptic_MG by lepticity
+    (LevelHybridSolver.cpp:457-498); status.solve_mode says which."""
 
     def __init__(self, op, opt=None):
         super().__init__(op)

@@ -408,7 +408,9 @@ static void fillStatus(sb_solver* s, const SolverStatus& st, sb_solver_status* o
     out->num_iters      = s->s.mg.lastIters;
     out->init_res_norm  = st.initResNorm;
     out->final_res_norm = st.finalResNorm;
-    const auto& h       = s->s.mg.absResNorms;
+    // MG mode: MGSolver's own history; leptic modes: LevelHybridSolver's m_resNorms (initial norm,
+    // then one entry per leptic order / V-cycle, LevelHybridSolver.cpp:312-400)
+    const auto& h       = s->s.mode == SB_MODE_MG || !s->s.isHybrid ? s->s.mg.absResNorms : s->s.resNorms;
     out->num_norms      = (int)std::min<size_t>(h.size(), SB_MAX_HISTORY);
     for (int i = 0; i < out->num_norms; ++i) out->res_norms[i] = h[i];
     out->solve_mode = s->s.mode;
@@ -438,6 +440,7 @@ int sb_solver_vcycle(sb_solver* s, sb_field* cor, sb_field* res)
     SB_TRY REQ(s); REQ(cor); REQ(res);
     Op& o = *s->s.op;
     if (cor->f.op != &o || res->f.op != &o) SB_FAIL("fields do not live on the solver's top operator");
+    if (s->s.mg.ops.empty()) SB_FAIL("this hybrid solver runs in pure leptic mode: it has no MGSolver to V-cycle with");
     s->s.mg.vCycle_residualEq(D(cor), D(res), 0);
     SB_END
 }

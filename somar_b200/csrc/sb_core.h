@@ -207,6 +207,15 @@ void divergence(cudaStream_t st, const Lay& L, double* div, const double* u0, co
 void gradient(cudaStream_t st, const Lay& L, double* g, const double* phi, const double* Jgup, int dir, double oneOnDx,
               double beta, int scaleBeta);
 
+// Leptic solver leaves.  F is the layout of the flattened (one-layer) fields.
+// excess = hiBC - sum_k rhs*dz, k ascending (LevelLepticSolver.cpp:725-770, SubspaceF.ChF:33-58)
+void vert_excess(cudaStream_t st, const Lay& L, const Lay& F, double* excess, const double* hiBC, const double* rhs, double dzScale);
+// FORT_TRIDIAGPOISSONNN1DFAB (PoissonOpF.ChF:1329-1410); gam: cell-sized scratch
+void tridiag_nn(cudaStream_t st, const Lay& L, const Lay& F, double* phi, const double* rhs, const double* upperBC,
+                const double* sigma, double* gam, double dx);
+// FORT_ADDVERTICALEXTRUSION (SubspaceF.ChF:66-110)
+void add_vertical_extrusion(cudaStream_t st, const Lay& L, const Lay& F, double* dest, const double* flat);
+
 // Reductions.  op: 0 max|x|, 1 sum|x|, 2 sum x^2, 3 sum x*y, 4 sum (J*dv)*x and sum J*dv (2 outputs).
 // One result per box (or 2 for op 4) lands in out[] (device); partial is scratch.
 void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, const double* x, const double* y,

@@ -77,6 +77,7 @@ struct Op {
     MapSpec  map;
     double   bcAlpha[3][2], bcBeta[3][2];
     int      depth = 0;
+    bool     flatZ = false;  // horizontal-only operator of the leptic solver (PoissonOp.cpp:411-505): one layer, no vertical coupling
 
     std::vector<Box3> boxes;    // all ranks
     std::vector<int>  boxRank;
@@ -113,6 +114,8 @@ struct Op {
     Op(Context* ctx, const sb_level_desc& d);
     Op(const Op& fine, const int ref[3]);  // coarsening ctor, PoissonOp.cpp:334-405
     Op(Context* single, const Op& dist);   // same depth, every box on the one rank of `single` (agglomeration); J/Jgup left to the caller
+    struct HorizTag {};
+    Op(const Op& full, HorizTag);          // PoissonOp::createHorizontalMGOperator (PoissonOp.cpp:1647-1686, 411-505)
     ~Op();
     Op& operator=(const Op&) = delete;
 
@@ -214,13 +217,38 @@ struct MGSolver {
     void modifyOptionsExceptMaxDepth(const sb_mg_options& o);
 };
 
-// Elliptic::LevelHybridSolver (Elliptic/LevelHybridSolver.cpp); only SolveMode::MG is built.
+// Elliptic::LevelLepticSolver (Elliptic/LevelLepticSolver.cpp): vertical Neumann-Neumann line
+// solves + one horizontal (flattened) MG solve per call, iterated over "orders".
+struct LepticSolver {
+    Op*                 op = nullptr;
+    std::unique_ptr<Op> hOp;   // horizontal operator on the flattened grids
+    MGSolver            hmg;   // m_horizSolverPtr
+    // LevelLepticSolver::Options (LevelLepticSolver.cpp:22-60)
+    double              absTol = 0, relTol = 0, hang = 0;
+    int                 maxOrder = 0, normType = 2, maxDivergingOrders = 2;
+    sb_mg_options       horizOptions;
+    bool                horizRemoveAvg = true;
+    std::vector<double> resNorms;
+    double *corTotal = nullptr, *cor = nullptr, *rhsA = nullptr, *rhsB = nullptr, *gam = nullptr;  // on op
+    double *excess = nullptr, *hiBC = nullptr, *hPhi = nullptr, *hRhs = nullptr, *ones = nullptr; // on hOp
+    void define(Op& top, const sb_mg_options& proj);
+    ~LepticSolver();
+    SolverStatus solve(double* phi, const double* rhs, bool homog, bool setPhiToZero);
+    void computeVerticalExcess(const double* rhs);
+    void verticalLineSolver(double* vertPhi, const double* vertRhs);
+    SolverStatus horizontalSolver();
+    void setZeroAvg(double* hphi);
+};
+
+// Elliptic::LevelHybridSolver (Elliptic/LevelHybridSolver.cpp).
 struct HybridSolver {
     Op*                 op = nullptr;
     int                 mode = 0;
     bool                isHybrid = false;  // false: plain MGSolver behind the same handle
     MGSolver            mg;
-    double *            cor = nullptr, *res = nullptr;
+    std::unique_ptr<LepticSolver> leptic;
+    int                 maxSolverSwaps = 10;  // LevelHybridSolver.cpp:18
+    double *            cor = nullptr, *res = nullptr, *localRes = nullptr;
     std::vector<double> resNorms;
     sb_mg_options       opt;
     static int computeSolveMode(const Op& op);  // LevelHybridSolver.cpp:457-498

@@ -769,6 +769,92 @@ void fill_metric_box(cudaStream_t st, const Lay& L, const int blo[3], const int 
 }
 
 // ------------------------------------------------------------------------------------------
+// Leaves of the leptic solver (Elliptic/LevelLepticSolver.cpp).  One thread per column; the
+// vertical loops keep the reference's order, so the results agree operation for operation.
+// ------------------------------------------------------------------------------------------
+// computeVerticalExcess (:725-770): excess = hiBC - loBC (identically 0: never modified after
+// bdryData.setVal(0)) and then FORT_UNMAPPEDVERTINTEGRAL with dz = -dXi_z (SubspaceF.ChF:33-58).
+__global__ void vert_excess_k(Lay L, Lay F, double* __restrict__ excess, const double* __restrict__ hiBC,
+                              const double* __restrict__ rhs, double dzScale)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= L.nx || j >= L.ny) return;
+    const long long f = F.idx(i, j, 0);
+    double          e = hiBC[f];
+    for (int k = 0; k < L.nz; ++k) e = e + rhs[L.idx(i, j, k)] * dzScale;
+    excess[f] = e;
+}
+void vert_excess(cudaStream_t st, const Lay& L, const Lay& F, double* excess, const double* hiBC, const double* rhs, double dzScale)
+{
+    const dim3 b(64, 4, 1);
+    vert_excess_k<<<grid3(L.nx, L.ny, 1, b), b, 0, st>>>(L, F, excess, hiBC, rhs, dzScale);
+    LAUNCHED();
+}
+// FORT_TRIDIAGPOISSONNN1DFAB (PoissonOpF.ChF:1329-1410): Neumann-Neumann Thomas solve with the
+// reference's special-cased last row (a(r-1) and the plain b(r)), zero-mean solution.  sigma is
+// Jg^{zz} on vertical faces (face r = lower face of cell r); x lives in phi, gam in scratch.
+__global__ void tridiag_nn_k(Lay L, Lay F, double* __restrict__ phi, const double* __restrict__ rhs,
+                             const double* __restrict__ upperBC, const double* __restrict__ sigma, double* __restrict__ gam,
+                             double dx)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= L.nx || j >= L.ny) return;
+    const int       N    = L.nz;
+    const double    dxsq = dx * dx;
+    const long long q0   = L.idx(i, j, 0), sz = L.sz;
+    double c = sigma[q0 + sz];
+    double b = -c;
+    double x = rhs[q0] * dxsq;
+    double bet = b;
+    x          = x / bet;
+    double g   = c / bet;
+    phi[q0] = x; gam[q0] = g;
+    double aPrev = 1.2345e10;  // a(0), PoissonOpF.ChF:1356
+    int    r;
+    for (r = 1; r <= N - 2; ++r) {
+        const long long q = q0 + r * sz;
+        const double    a = sigma[q];
+        c                 = sigma[q + sz];
+        b                 = -(a + c);
+        bet               = b - a * g;
+        x                 = (rhs[q] * dxsq - a * x) / bet;
+        g                 = c / bet;
+        phi[q] = x; gam[q] = g;
+        aPrev = a;
+    }
+    {
+        const long long q = q0 + r * sz;  // r == N - 1
+        const double    a = sigma[q];
+        b                 = -a;
+        const double xr   = rhs[q] * dxsq - upperBC[F.idx(i, j, 0)] * dx;
+        x                 = (xr - aPrev * x) / b;
+        phi[q]            = x;
+    }
+    double avg = x;
+    for (r = N - 2; r >= 0; --r) {
+        const long long q = q0 + r * sz;
+        x                 = phi[q] - gam[q] * x;
+        phi[q]            = x;
+        avg               = avg + x;
+    }
+    avg = avg / (double)N;
+    for (r = 0; r <= N - 1; ++r) phi[q0 + r * sz] = phi[q0 + r * sz] - avg;
+}
+void tridiag_nn(cudaStream_t st, const Lay& L, const Lay& F, double* phi, const double* rhs, const double* upperBC,
+                const double* sigma, double* gam, double dx)
+{
+    const dim3 b(64, 4, 1);
+    tridiag_nn_k<<<grid3(L.nx, L.ny, 1, b), b, 0, st>>>(L, F, phi, rhs, upperBC, sigma, gam, dx);
+    LAUNCHED();
+}
+void add_vertical_extrusion(cudaStream_t st, const Lay& L, const Lay& F, double* dest, const double* flat)
+{
+    launch_valid(st, L, -1, [=] __device__(long long c, int i, int j, int) { dest[c] = dest[c] + flat[F.idx(i, j, 0)]; });
+}
+
+// ------------------------------------------------------------------------------------------
 // Divergence of the advecting velocity (FiniteDiffF.ChF:42-115) and the face gradient
 // Jg^{dd} * (phi(i) - phi(i-e_d)) / dXi_d (FiniteDiffF.ChF:123-147 + FArrayBox::mult,
 // PoissonOp.cpp:1508-1534; the optional *beta of :1537-1541).

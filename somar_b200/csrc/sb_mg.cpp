@@ -483,28 +483,39 @@ int HybridSolver::computeSolveMode(const Op& op)
     if (lept > 0.2) return SB_MODE_LEPTIC_MG;
     return SB_MODE_MG;
 }
+// LevelHybridSolver::define (LevelHybridSolver.cpp:127-186)
 void HybridSolver::define(Op& top, const sb_mg_options& o)
 {
     op   = &top;
     opt  = o;
-    mode = computeSolveMode(top);
-    if (isHybrid && mode != SB_MODE_MG)
-        SB_FAIL("LevelHybridSolver would pick the leptic solver for this grid (lepticity > 0.2); only SolveMode::MG is "
-                "implemented on the B200 path");
-    mg.define(top, o, {}, true);
-    opt.maxDepth = mg.opt.maxDepth;
+    mode = isHybrid ? computeSolveMode(top) : SB_MODE_MG;
+    const bool useLeptic = mode == SB_MODE_LEPTIC || mode == SB_MODE_LEPTIC_MG;
+    const bool useMG     = mode == SB_MODE_MG || mode == SB_MODE_LEPTIC_MG;
+    if (useLeptic) {
+        leptic.reset(new LepticSolver);
+        leptic->define(top, o);
+    }
+    if (useMG) {
+        mg.define(top, o, {}, true);
+        opt.maxDepth = mg.opt.maxDepth;
+    } else {
+        opt.maxDepth = -1;  // the MG options keep proj.maxDepth: no MGSolver is defined in pure leptic mode
+        mg.opt       = opt;
+    }
     cor = top.alloc();
     res = top.alloc();
+    if (mode == SB_MODE_LEPTIC_MG) localRes = top.alloc();
 }
 HybridSolver::~HybridSolver()
 {
     if (cor) cudaFree(cor);
     if (res) cudaFree(res);
+    if (localRes) cudaFree(localRes);
 }
 SolverStatus HybridSolver::solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double metric)
 {
     if (!isHybrid) return mg.solve(phi, rhs, homog, setPhiToZero, metric);
-    // LevelHybridSolver::solve (:266-292) + solveResidualEq, SolveMode::MG branch (:296-452)
+    // LevelHybridSolver::solve (:266-292) + solveResidualEq (:296-452)
     Op& o = *op;
     if (setPhiToZero) o.setToZero(phi);
     o.residual(res, phi, rhs, homog);
@@ -512,9 +523,32 @@ SolverStatus HybridSolver::solve(double* phi, const double* rhs, bool homog, boo
     resNorms.clear();
     resNorms.push_back(o.norm(res, opt.normType));
     if (metric > 0.0) resNorms[0] = metric;
-    SolverStatus st = mg.solve(cor, res, true, false, -1.0);
-    resNorms.push_back(st.finalResNorm);
-    st.initResNorm  = resNorms[0];
+    SolverStatus st;
+    st.initResNorm = resNorms.back();
+    if (mode == SB_MODE_LEPTIC) {
+        st = leptic->solve(cor, res, true, false);  // replaces the status wholesale, as the reference's assignment does
+        resNorms.insert(resNorms.end(), leptic->resNorms.begin() + 1, leptic->resNorms.end());
+    } else if (mode == SB_MODE_LEPTIC_MG) {
+        for (int swaps = 0; swaps < maxSolverSwaps; ++swaps) {
+            const double preLepticResNorm = resNorms.back();
+            leptic->solve(cor, res, true, false);
+            resNorms.insert(resNorms.end(), leptic->resNorms.begin() + 1, leptic->resNorms.end());
+            if (resNorms.back() <= opt.absTol) { st.status = SB_STATUS_CONVERGED; break; }
+            if (resNorms.back() <= opt.relTol * resNorms[0]) { st.status = SB_STATUS_CONVERGED; break; }
+            mg.vCycle_residualEq(cor, res, 0);
+            o.residual(localRes, cor, res, true);
+            resNorms.push_back(o.norm(localRes, opt.normType));
+            if (resNorms.back() <= opt.absTol) { st.status = SB_STATUS_CONVERGED; break; }
+            if (resNorms.back() <= opt.relTol * resNorms[0]) { st.status = SB_STATUS_CONVERGED; break; }
+            if (resNorms.back() > preLepticResNorm) { st.status = SB_STATUS_DIVERGED; break; }
+            if (swaps == maxSolverSwaps - 1) { st.status = SB_STATUS_MAXITERS; break; }
+        }
+        if (o.relaxMethod == SB_RELAX_VERTLINE) mg.checkPivotAll();
+    } else {
+        st = mg.solve(cor, res, true, false, -1.0);
+        resNorms.push_back(st.finalResNorm);
+        st.initResNorm = resNorms[0];
+    }
     st.finalResNorm = resNorms.back();
     o.incr(phi, cor, 1.0);
     return st;

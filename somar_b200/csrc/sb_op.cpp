@@ -242,6 +242,7 @@ void Op::setupLayout()
     planDecomposition(boxes, boxRank, domain, periodic, ctx->rank, ctx->nranks, tiles, local, side);
     tile = tiles[ctx->rank];
     lay  = makeLay(tile);
+    if (flatZ) side[2][0].kind = side[2][1].kind = -1;  // inactive direction: no BCs, no exchange (activeSides, PoissonOp.cpp:483-487)
 
     // device-side box list (tile-local indices) and reduction buffers
     const int nl = nlocal();
@@ -333,7 +334,7 @@ void Op::fillMetricFromMap()
 // depth, matrix elements recomputed from the map at the coarse dXi.
 Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
 {
-    dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth + 1;
+    dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth + 1; flatZ = f.flatZ;
     std::memcpy(periodic, f.periodic, sizeof(periodic));
     std::memcpy(bcAlpha, f.bcAlpha, sizeof(bcAlpha));
     std::memcpy(bcBeta, f.bcBeta, sizeof(bcBeta));
@@ -364,7 +365,7 @@ Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
 // cacheMatrixElements().
 Op::Op(Context* single, const Op& f) : ctx(single)
 {
-    dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth;
+    dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth; flatZ = f.flatZ;
     std::memcpy(periodic, f.periodic, sizeof(periodic));
     std::memcpy(bcAlpha, f.bcAlpha, sizeof(bcAlpha));
     std::memcpy(bcBeta, f.bcBeta, sizeof(bcBeta));
@@ -386,7 +387,7 @@ void Op::cacheMatrixElements()
     for (int d = 0; d < 3; ++d) {
         const int N = domain.size(d);
         hM[d].assign(2 * (size_t)N, 0.0);
-        if (!(dim == 2 && d == 1)) {
+        if (!(dim == 2 && d == 1) && !(flatZ && d == 2)) {  // inactive directions: m_M[d].setVal(0) (PoissonOp.cpp:535-537)
             // fill_dXidx = 1 / fill_dxdXi (GeoSourceInterface.cpp:228-243) over the flattened domain box
             std::vector<double> fc = map.dxdXi(d, dXi[d], domain.lo[d], N + 1, 1);
             std::vector<double> cc = map.dxdXi(d, dXi[d], domain.lo[d], N, 0);
@@ -416,7 +417,7 @@ void Op::cacheMatrixElements()
     for (int d = 0; d < 3; ++d)
         for (int s = 0; s < 2; ++s) {
             SideBC& sd = side[d][s];
-            if (sd.kind != SIDE_PHYS || (dim == 2 && d == 1)) continue;
+            if (sd.kind != SIDE_PHYS || (dim == 2 && d == 1) || (flatZ && d == 2)) continue;
             const int face = s ? domain.hi[d] + 1 : domain.lo[d];
             const double dx = map.dxdXi(d, dXi[d], face, 1, 1, dXi[d])[0];
             int minSize = std::numeric_limits<int>::max();

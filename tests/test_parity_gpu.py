@@ -6,15 +6,17 @@ projected velocity 1e-9 relative in max-norm, identical cycle counts and solver 
 per-cycle norms are compared the way the solver itself monitors them, as relative residuals
 |r_i|/|r_0| (MGSolverI.H:361): |norm_i - ref_i| <= 1e-10 |r_0|, and additionally to 1e-6 of their
 own value (a residual that has dropped 8 orders of magnitude is itself only defined to ~1e-8
-relative in fp64, whatever the summation order).  The element-wise kernels are written to agree
-far more tightly; those bounds are stated per test."""
+relative in fp64, whatever the summation order; and rhs - L[phi] has a rounding floor of about
+eps * |L| * |phi| -- 5e-11 |r_0| on the strongly anisotropic DJL grid -- below which a norm is
+noise, hence the absolute term 1e-11 |r_0|, ten times tighter than the north-star bound).  The
+element-wise kernels are written to agree far more tightly; those bounds are stated per test."""
 
 
 def assert_norms(got, ref):
     got, ref = np.asarray(got), np.asarray(ref)
     assert got.shape == ref.shape
     assert np.all(np.abs(got - ref) <= 1e-10 * ref[0]), (got, ref)
-    assert np.all(np.abs(got - ref) <= 1e-6 * ref), (got, ref)
+    assert np.all(np.abs(got - ref) <= 1e-6 * ref + 1e-11 * ref[0]), (got, ref)
 import numpy as np
 import pytest
 
