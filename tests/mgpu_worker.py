@@ -27,7 +27,11 @@ def main():
     dist.broadcast(idt, 0)
     ctx.init_comm(idt.cpu().numpy().tobytes())
 
-    c = CASES[name]
+    if name in CASES:
+        c = CASES[name]
+    else:
+        from test_leptic_gpu import LEPTIC3D  # leptic / leptic-MG modes of the hybrid solver
+        c = LEPTIC3D[name][0]
     nx, L, dXi, lo, hi = geometry(c)
     blo, bhi = sb.make_base_grids(lo, hi, c["max_box"], (1, 1, 0), c["bf"])
     ranks = sb.assign_boxes_to_ranks(blo, bhi, world)
@@ -58,7 +62,7 @@ def main():
             full[sl] = p
         np.save(f"{out_path}.phi.npy", full)
         with open(out_path, "w") as f:
-            json.dump({"status": st.status, "norms": st.norms, "max_depth": st.max_depth, "world": world,
+            json.dump({"status": st.status, "norms": st.norms, "max_depth": st.max_depth, "solve_mode": st.solve_mode, "world": world,
                        "launches": ctx.launch_count()}, f)
     dist.barrier()
     dist.destroy_process_group()

@@ -39,9 +39,14 @@ WORLD = int(os.environ.get("SB_TEST_WORLD", "2"))  # ranks = GPUs used by the wo
                                              ("line_perx", "defaults", "0"), ("gsrb_cart", "defaults", "0"),
                                              ("gsrb_perxy", "vcycle", "0"), ("line_aniso", "vcycle", "0"),
                                              ("line_stretch", "defaults", "300"), ("line_aniso", "vcycle", "1100"),
-                                             ("gsrb_cart", "vcycle", "600")])
+                                             ("gsrb_cart", "vcycle", "600"),
+                                             ("lep3d_cart", "defaults", None), ("lep3d_perx", "defaults", "0"),
+                                             ("lepmg3d_cart", "defaults", None), ("lepmg3d_zstretch", "defaults", "0")])
 def test_two_rank_solve(name, optset, agg):
-    c = CASES[name]
+    leptic = name not in CASES
+    if leptic:
+        from test_leptic_gpu import LEPTIC3D
+    c = LEPTIC3D[name][0] if leptic else CASES[name]
     ref = run_ref("solve", inp=[rand_field(c, 4, zero_mean=True)], extra=_proj_overrides({} if optset == "defaults" else V_OPTS),
                   **ref_kwargs(c))
     with tempfile.TemporaryDirectory() as td:
@@ -58,5 +63,9 @@ def test_two_rank_solve(name, optset, agg):
         phi = np.load(out + ".phi.npy")
     assert res["status"] == int(ref.kv["status"])
     assert res["max_depth"] == int(ref.kv["maxDepth"])
-    assert_norms(res["norms"], ref["norms"][1:])
+    if leptic:
+        assert res["solve_mode"] == int(ref.kv["solveMode"]) == LEPTIC3D[name][1]
+        assert_norms(res["norms"], ref["hybridNorms"])
+    else:
+        assert_norms(res["norms"], ref["norms"][1:])
     assert rel_err(phi, ref["phi"]) <= 1e-9
