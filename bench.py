@@ -36,8 +36,18 @@ BOX = (128, 128, 0)
 BLOCK_FACTOR = 16
 METRIC = "pressure-solve DOF/s per V-cycle"
 UNIT = "DOF/s"
-# algorithmic bytes per cell of one full line-relaxation iteration (both colours): SURVEY.md 8(d)
-RELAX_BYTES_PER_CELL_ITER = 40.0
+# Bytes per cell of one full line-relaxation iteration (both colours).
+#  * SURVEY.md 8(d) counts the reference's operand set: phi r+w, rhs, J, Dinv = 40 B.
+#  * The kernel that runs (sb_line.cu) has no J / Dinv operand at all (one shared tridiagonal matrix,
+#    DESIGN.md section 4): what one colour pass must move is phi of the other colour (read), rhs and
+#    phi of its own colour (read, write) = 12 B per cell of the grid, 24 B per iteration.  The
+#    roofline is reported against THAT figure (it is also what ncu measures as DRAM traffic); the
+#    survey-convention number is given next to it.
+RELAX_BYTES_PER_CELL_ITER_SURVEY = 40.0
+RELAX_BYTES_PER_CELL_ITER = 24.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one depth-0 launch on one GPU, from the ncu --set full
+# capture summarised in profiles/r1_v4_summary.md
+NCU_TRAFFIC_PER_LAUNCH_N1 = 3.2286e9
 
 
 def read_peaks():
@@ -186,13 +196,11 @@ def run_ours(args):
             dist.barrier()
 
     def step():
-        op.preCond(cor, res, 0)
-        solver.vcycle(cor, res)
+        solver.precond_vcycle(cor, res)   # op.preCond(cor, res, 0); vCycle_residualEq(cor, res, 0)
 
     def step_e2e():
         res.upload_ptr(res_h.data_ptr(), tlo, thi)
-        op.preCond(cor, res, 0)
-        solver.vcycle(cor, res)
+        solver.precond_vcycle(cor, res)
         cor.download_ptr(cor_h.data_ptr(), tlo, thi)
 
     def timed(fn, steps):
@@ -246,6 +254,7 @@ def run_ours(args):
         cells_per_launch = ncell_tile  # one colour pass sweeps the whole tile (half the columns are solved)
         launch_ms = k_ms / max(k_n, 1)
         achieved = (RELAX_BYTES_PER_CELL_ITER / 2.0) * cells_per_launch / (launch_ms * 1e-3) / 1e9
+        survey = (RELAX_BYTES_PER_CELL_ITER_SURVEY / 2.0) * cells_per_launch / (launch_ms * 1e-3) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -260,8 +269,14 @@ def run_ours(args):
                     "what": "residual from pinned host -> device, preCond + V-cycle, correction -> pinned host"},
             "gpu_launches": launches,
             "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": {"bound": "hbm", "kernel": "vertline_k (one colour pass of vertical line relaxation, depth 0)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "vertline_split_k (one colour pass of vertical line relaxation, depth 0)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_PER_LAUNCH_N1 if world == 1 else None,
+                         "bytes_counted": "12 B per grid cell per colour pass: phi(other colour) read, rhs + phi(own colour) read/write; "
+                                          "the kernel has no J/Dinv operands",
+                         "survey_convention": {"bytes_per_cell_per_pass": RELAX_BYTES_PER_CELL_ITER_SURVEY / 2.0, "achieved": survey,
+                                               "frac": survey / peak,
+                                               "note": "SURVEY.md 8(d) counts the reference's operand set (phi, rhs, J, Dinv)"},
                          "peak_source": peak_src, "launch_ms": launch_ms, "launches_timed": k_n,
                          "algorithmic_bytes_per_launch": (RELAX_BYTES_PER_CELL_ITER / 2.0) * cells_per_launch,
                          "share_of_step": tot_line / (ms_per_step if ms_per_step > 0 else 1.0),

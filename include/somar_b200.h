@@ -191,6 +191,10 @@ int sb_solver_solve(sb_solver* s, sb_field* phi, sb_field* rhs, int homog, int s
                     double convergence_metric, sb_solver_status* status);
 /* One vCycle_residualEq(cor, res, depth 0) (MGSolverI.H:617) -- the unit of the headline metric. */
 int sb_solver_vcycle(sb_solver* s, sb_field* cor, sb_field* res);
+/* The body of one outer iteration of MGSolver::vCycle (MGSolverI.H:342-347): op.preCond(cor, res, 0)
+ * followed by vCycle_residualEq(cor, res, depth 0); same result as sb_op_precond + sb_solver_vcycle,
+ * with the preconditioning pass fused into the first relaxation. */
+int sb_solver_precond_vcycle(sb_solver* s, sb_field* cor, sb_field* res);
 
 /* ---- the projection bracket, host buffers in and out --------------------------------------- */
 /* AMRNSLevel::projectCorrect, single level (AMRNSLevelProject.cpp:247-373): vel is the advecting

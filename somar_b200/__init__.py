@@ -421,6 +421,10 @@ class _SolverBase:
     def vcycle(self, cor, res):
         capi.check(self.lib.sb_solver_vcycle(self.h, cor.h, res.h))
 
+    def precond_vcycle(self, cor, res):
+        """op.preCond(cor, res, 0); vCycle_residualEq(cor, res, 0) -- MGSolverI.H:342-347."""
+        capi.check(self.lib.sb_solver_precond_vcycle(self.h, cor.h, res.h))
+
     def set_options(self, opt):
         capi.check(self.lib.sb_solver_set_options(self.h, C.byref(opt)))
 

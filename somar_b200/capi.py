@@ -141,6 +141,7 @@ PROTOTYPES = {
     "sb_solver_set_options": (C.c_int, [P, C.POINTER(MGOptions)]),
     "sb_solver_solve": (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_double, C.POINTER(SolverStatus)]),
     "sb_solver_vcycle": (C.c_int, [P, P, P]),
+    "sb_solver_precond_vcycle": (C.c_int, [P, P, P]),
     "sb_project_host": (C.c_int, [P, DP * 3, DP, DP, C.c_double, DP, DP, C.POINTER(SolverStatus)]),
 }
 

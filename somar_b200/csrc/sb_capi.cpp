@@ -445,6 +445,16 @@ int sb_solver_vcycle(sb_solver* s, sb_field* cor, sb_field* res)
     SB_END
 }
 
+int sb_solver_precond_vcycle(sb_solver* s, sb_field* cor, sb_field* res)
+{
+    SB_TRY REQ(s); REQ(cor); REQ(res);
+    Op& o = *s->s.op;
+    if (cor->f.op != &o || res->f.op != &o) SB_FAIL("fields do not live on the solver's top operator");
+    if (s->s.mg.ops.empty()) SB_FAIL("this hybrid solver runs in pure leptic mode: it has no MGSolver to V-cycle with");
+    s->s.mg.vCycle_residualEq(D(cor), D(res), 0, true);
+    SB_END
+}
+
 // AMRNSLevel::projectCorrect, single level (Grade5_SOMAR/AMRNSLevelProject.cpp:247-373).
 int sb_project_host(sb_solver* s, double* const vel[3], double* phi, double* p, double proj_dt, double* init_div_norm,
                     double* final_div_norm, sb_solver_status* status)

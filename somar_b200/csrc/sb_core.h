@@ -140,6 +140,7 @@ struct BoxList {  // boxes of this rank in tile-local coordinates, on the device
     int  n;
     int* lo;  // [n][3]
     int* hi;  // [n][3]
+    int  maxnx;  // widest box (host-side hint for the reduction's thread shape)
 };
 
 // ---- kernel launchers (sb_kernels.cu).  All asynchronous on `st`. -------------------------
@@ -178,12 +179,15 @@ size_t vertline_smem_bytes(int nz);
 void vertline_smem_pass(cudaStream_t st, const Lay& L, const Coef& c, const double* tab, double* phi, const double* rhs, int pass);
 // colour-split storage (SLay): conversion, ghost fill / face pack of directions x and y, and the
 // line relaxation on it.  s[c] = array of colour c.
-void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1, const double* scale);
+void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1, const double* scale,
+                 const double* shift = nullptr);
+void split_precond(cudaStream_t st, const Lay& L, const SLay& S, const double* res, const double* Dinv, const double* scale,
+                   double* c0, double* c1, double* r0, double* r1);
 void unsplit_field(cudaStream_t st, const Lay& L, const SLay& S, double* nat, const double* s0, const double* s1);
 void fill_ghosts_split(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC bc[3][2], int dim, bool physToo);
 void pack_faces_split(cudaStream_t st, const SLay& S, double* s0, double* s1, double* const bufs[2][2], bool unpack);
 void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const double* tab, double* own, const double* oth,
-                         const double* rhs, int pass);
+                         const double* rhs, int pass, int region = 0, int nbMask = 0);
 bool vertline_split_fits(int nz);
 int  vertline_split_chunk(int nz);  // levels per warp chunk (the P/Q tables depend on it)
 void j_deviation(cudaStream_t st, const Lay& L, const double* J, const double* jcol, double* out);

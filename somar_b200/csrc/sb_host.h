@@ -14,6 +14,8 @@ struct Comm;  // NCCL wrapper (sb_comm.cpp)
 struct Context {
     int          device = 0, rank = 0, nranks = 1;
     cudaStream_t st     = nullptr;
+    cudaStream_t commSt = nullptr;          // halo exchanges that overlap interior work (multi-rank line relaxation)
+    cudaEvent_t  evEdge = nullptr, evHalo = nullptr;
     double*      hpin   = nullptr;  // pinned host scratch (scalars coming back from reductions)
     size_t       hpinLen = 0;
     void*        scratch = nullptr;  // device scratch shared by all depths (line-relax workspace)
@@ -99,6 +101,7 @@ struct Op {
     int*    boxLoHi = nullptr;  // [2][nlocal][3]
     double* redPartial = nullptr;
     double* redOut = nullptr;
+    double* shiftBuf = nullptr;  // (sum, vol) of the last removeKernel
     int*    pivotFlag = nullptr;
     double* lineTab = nullptr;   // [4][nz] tables of the shared-matrix line relaxation (s, f, g, MzR)
     bool    lineFast = false;
@@ -136,10 +139,14 @@ struct Op {
     void   exchange(double* phi);
     void   applyOp(double* lhs, double* phi, bool homog);
     void   residual(double* res, double* phi, const double* rhs, bool homog);
-    void   relax(double* cor, const double* res, int iters, bool resUnchanged = false);
-    void   relaxLineSplit(double* cor, const double* res, int iters, bool resUnchanged);
+    // pre: work fused into the start of the relaxation -- RELAX_PRE_PRECOND: cor = res * Dinv first
+    // (preCond(cor, res, 0)); RELAX_PRE_SHIFT: cor -= sum / vol of shiftBuf first (the tail of a
+    // removeKernel deferred by MGProlong).  Both are applied even when iters == 0.
+    enum { RELAX_PRE_NONE = 0, RELAX_PRE_PRECOND = 1, RELAX_PRE_SHIFT = 2 };
+    void   relax(double* cor, const double* res, int iters, bool resUnchanged = false, int pre = RELAX_PRE_NONE);
+    void   relaxLineSplit(double* cor, const double* res, int iters, bool resUnchanged, int pre);
     void   preCond(double* phi, const double* rhs, int relaxIters);
-    void   removeKernel(double* phi);
+    bool   removeKernel(double* phi, bool defer = false);  // true: the subtraction is left to relax(RELAX_PRE_SHIFT)
     double norm(const double* x, int p, double powScale = 1.0);
     double dotProduct(const double* a, const double* b);
     void   incr(double* lhs, const double* x, double scale) { k::incr_valid(st(), lay, lhs, x, scale, -1); }
@@ -148,7 +155,7 @@ struct Op {
     void   setToZero(double* lhs) { k::fill(st(), lhs, lay.n, 0.0); }
     void   assignLocal(double* dst, const double* src) { k::copy_valid(st(), lay, dst, src); }
     void   MGRestrict(Op& crse, double* crseRes, const double* fineRes);
-    void   MGProlong(Op& crse, double* finePhi, double* crseCor, int order);
+    bool   MGProlong(Op& crse, double* finePhi, double* crseCor, int order, bool deferKernel = false);  // returns removeKernel's
     void   levelDivergence(double* div, double* const vel[3]);
     void   levelGradient(double* const grad[3], double* phi, bool homog);
     void   checkPivot();
@@ -212,7 +219,9 @@ struct MGSolver {
     ~MGSolver();
     SolverStatus solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double convergenceMetric = -1.0);
     SolverStatus cycle(bool fmgMode, double* phi, const double* rhs, bool homog, bool setPhiToZero, double convergenceMetric);
-    void vCycle_residualEq(double* cor, const double* res, int depth);
+    // corIsPreCond: cor still has to be set to preCond(res) -- the caller skipped that pass so that
+    // the first relaxation can fuse it
+    void vCycle_residualEq(double* cor, const double* res, int depth, bool corIsPreCond = false);
     void fmg_residualEq(double* cor, const double* res, int depth);
     void modifyOptionsExceptMaxDepth(const sb_mg_options& o);
 };

@@ -682,20 +682,82 @@ __global__ void prolong_quad2_k(Lay Lf, Lay Lc, int r0, int r1, int r2, double* 
         fine[qf]         = fine[qf] + dxf1 * dxf2 * mm0 + dxf2 * dxf0 * mm1 + dxf0 * dxf1 * mm2;
     }
 }
+// Fast path for refinement ratios of 1 or 2 (all the MG schedules use): one thread per coarse
+// cell of a plane updates its R0 x r1 children, so the coarse stencil and the slopes are formed
+// once; the expression per fine cell is the one of prolong_k, operation for operation.
+template <int R0>
+__global__ void prolong_c_k(Lay Lf, Lay Lc, int r1, int r2, double* __restrict__ fine, const double* __restrict__ crse, int order)
+{
+    const int ic = blockIdx.x * blockDim.x + threadIdx.x;
+    const int jc = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k  = blockIdx.z;
+    if (ic >= Lc.nx || jc >= Lc.ny) return;
+    const int       kc = r2 == 2 ? (k >> 1) : k;
+    const long long qc = Lc.idx(ic, jc, kc);
+    const double    c  = crse[qc];
+    double          m0 = 0.0, m1 = 0.0, m2 = 0.0;
+    const double    sc0 = R0 == 1 ? 0.0 : 1.0 / R0, sc1 = r1 == 1 ? 0.0 : 1.0 / r1, sc2 = r2 == 1 ? 0.0 : 1.0 / r2;
+    if (order == 1) {
+        const long long s0 = R0 == 1 ? 0 : 1, s1 = r1 == 1 ? 0 : Lc.sy, s2 = r2 == 1 ? 0 : Lc.sz;
+        m0 = 0.5 * (crse[qc + s0] - crse[qc - s0]);
+        m1 = 0.5 * (crse[qc + s1] - crse[qc - s1]);
+        m2 = 0.5 * (crse[qc + s2] - crse[qc - s2]);
+    } else if (order == 2) {
+        const double mid = -2.0 * c;
+        m0 = 0.25 * (crse[qc + 1] + mid + crse[qc - 1]);
+        m1 = 0.25 * (crse[qc + Lc.sy] + mid + crse[qc - Lc.sy]);
+        m2 = 0.25 * (crse[qc + Lc.sz] + mid + crse[qc - Lc.sz]);
+    }
+    const int    kk   = k - kc * r2;
+    const double dxf2 = order == 2 ? -0.5 + ((kk + 0.5) / r2) : -0.5 + ((kk + 0.5) * sc2);
+    for (int jj = 0; jj < r1; ++jj) {
+        const double    dxf1 = order == 2 ? -0.5 + ((jj + 0.5) / r1) : -0.5 + ((jj + 0.5) * sc1);
+        const long long qf   = Lf.idx(ic * R0, jc * r1 + jj, k);
+        double          f[R0];
+        if (R0 == 2) { const double2 v = *reinterpret_cast<const double2*>(fine + qf); f[0] = v.x; f[R0 - 1] = v.y; }
+        else f[0] = fine[qf];
+#pragma unroll
+        for (int ii = 0; ii < R0; ++ii) {
+            double g = f[ii];
+            if (order == 0 || order == 1) g = g + c;
+            if (order == 1) {
+                const double dxf0 = -0.5 + ((ii + 0.5) * sc0);
+                g                 = g + dxf0 * m0 + dxf1 * m1 + dxf2 * m2;
+            }
+            if (order == 2) {
+                const double dxf0 = -0.5 + ((ii + 0.5) / R0);
+                g                 = g + dxf0 * dxf0 * m0 + dxf1 * dxf1 * m1 + dxf2 * dxf2 * m2;
+            }
+            f[ii] = g;
+        }
+        if (R0 == 2) *reinterpret_cast<double2*>(fine + qf) = make_double2(f[0], f[R0 - 1]);
+        else fine[qf] = f[0];
+    }
+}
+static void launch_prolong(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse, int order)
+{
+    const bool fast = (ref[0] == 1 || ref[0] == 2) && (ref[1] == 1 || ref[1] == 2) && (ref[2] == 1 || ref[2] == 2) &&
+                      Lc.nx * ref[0] == Lf.nx && Lc.ny * ref[1] == Lf.ny;
+    if (!fast) {
+        prolong_k<<<grid3(Lf.nx, Lf.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[0], ref[1], ref[2], fine, crse, order);
+    } else if (ref[0] == 2) {
+        prolong_c_k<2><<<grid3(Lc.nx, Lc.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[1], ref[2], fine, crse, order);
+    } else {
+        prolong_c_k<1><<<grid3(Lc.nx, Lc.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[1], ref[2], fine, crse, order);
+    }
+    LAUNCHED();
+}
 void prolong_const(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse)
 {
-    prolong_k<<<grid3(Lf.nx, Lf.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[0], ref[1], ref[2], fine, crse, 0);
-    LAUNCHED();
+    launch_prolong(st, Lf, Lc, ref, fine, crse, 0);
 }
 void prolong_linear(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse)
 {
-    prolong_k<<<grid3(Lf.nx, Lf.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[0], ref[1], ref[2], fine, crse, 1);
-    LAUNCHED();
+    launch_prolong(st, Lf, Lc, ref, fine, crse, 1);
 }
 void prolong_quad1(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse)
 {
-    prolong_k<<<grid3(Lf.nx, Lf.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[0], ref[1], ref[2], fine, crse, 2);
-    LAUNCHED();
+    launch_prolong(st, Lf, Lc, ref, fine, crse, 2);
 }
 void prolong_quad2(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse, int dim)
 {
@@ -924,25 +986,43 @@ __device__ __forceinline__ double block_reduce(double v, int op, double* sm)
     __syncthreads();
     return v;  // valid in thread 0
 }
+// Threads are arranged as bxw columns (a power of two >= 32 covering the box width, at most the
+// block) by blockDim.x / bxw rows, and every thread keeps four rows in flight; the assignment of
+// cells to threads is fixed, so the result is reproducible run to run.
 __global__ void reduce1_k(Lay L, BoxList bl, int op, const double* __restrict__ x, const double* __restrict__ y, double dv,
-                          double* __restrict__ partial)
+                          double* __restrict__ partial, int bxw)
 {
     __shared__ double sm[32];
     const int bx = blockIdx.y, ch = blockIdx.x;
     const int lo0 = bl.lo[3 * bx], lo1 = bl.lo[3 * bx + 1], lo2 = bl.lo[3 * bx + 2];
     const int n0 = bl.hi[3 * bx] - lo0 + 1, n1 = bl.hi[3 * bx + 1] - lo1 + 1, n2 = bl.hi[3 * bx + 2] - lo2 + 1;
     const long long rows = (long long)n1 * n2;
-    double          a = 0.0, b = 0.0;
-    for (long long r = ch; r < rows; r += RCH) {
-        const int       j = lo1 + (int)(r % n1), k = lo2 + (int)(r / n1);
-        const long long q = L.idx(lo0, j, k);
-        for (int i = threadIdx.x; i < n0; i += blockDim.x) {
-            const double v = x[q + i];
-            if (op == 0) a = fmax(a, fabs(v));
-            else if (op == 1) a = a + fabs(v);
-            else if (op == 2) a = a + v * v;
-            else if (op == 3) a = a + v * y[q + i];
-            else { const double s = y[q + i] * dv; a = a + s * v; b = b + s; }  // IntegralF.ChF:37-58
+    const int tx = threadIdx.x & (bxw - 1), ty = threadIdx.x / bxw, by = blockDim.x / bxw;
+    double    a = 0.0, b = 0.0;
+    auto acc = [&](double v, double w) {
+        if (op == 0) a = fmax(a, fabs(v));
+        else if (op == 1) a = a + fabs(v);
+        else if (op == 2) a = a + v * v;
+        else if (op == 3) a = a + v * w;
+        else { const double s = w * dv; a = a + s * v; b = b + s; }  // IntegralF.ChF:37-58
+    };
+    const bool two = op >= 3;
+    for (long long r0 = ch + (long long)RCH * ty; r0 < rows; r0 += (long long)RCH * by * 4) {
+        for (int i = tx; i < n0; i += bxw) {
+            double v[4], w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long r = r0 + (long long)RCH * by * u;
+                v[u] = 0.0; w[u] = 0.0;
+                if (r < rows) {
+                    const long long q = L.idx(lo0 + i, lo1 + (int)(r % n1), lo2 + (int)(r / n1));
+                    v[u] = x[q];
+                    if (two) w[u] = y[q];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + (long long)RCH * by * u < rows) acc(v[u], w[u]);
         }
     }
     a = block_reduce(a, op, sm);
@@ -972,7 +1052,9 @@ int  reduce_partial_len(int nboxes) { return 2 * RCH * nboxes; }
 void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, const double* x, const double* y, double dv,
                   double* partial, double* out)
 {
-    reduce1_k<<<dim3(RCH, boxes.n), 256, 0, st>>>(L, boxes, op, x, y, dv, partial);
+    int bxw = 32;
+    while (bxw < 256 && bxw < boxes.maxnx) bxw <<= 1;
+    reduce1_k<<<dim3(RCH, boxes.n), 256, 0, st>>>(L, boxes, op, x, y, dv, partial, bxw);
     LAUNCHED();
     reduce2_k<<<boxes.n, 64, 0, st>>>(op, partial, out);
     LAUNCHED();

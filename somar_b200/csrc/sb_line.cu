@@ -39,8 +39,11 @@ __device__ __forceinline__ double* scell(const SLay& S, double* s0, double* s1, 
 // null) multiplies level k by scale[k] (the 1/(beta J_k) of the row-scaled system, applied to the
 // right-hand side once instead of in every pass).
 // ------------------------------------------------------------------------------------------
+// shift (may be null): device pair (sum, vol); the field is reduced by sum / vol on the way -- the
+// null-space removal of PoissonOp::removeKernel (PoissonOp.cpp:838-842) that would otherwise be a
+// pass of its own.
 __global__ void split_field_k(Lay L, SLay S, const double* __restrict__ nat, double* __restrict__ s0, double* __restrict__ s1,
-                              const double* __restrict__ scale)
+                              const double* __restrict__ scale, const double* __restrict__ shift)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -54,10 +57,38 @@ __global__ void split_field_k(Lay L, SLay S, const double* __restrict__ nat, dou
     if (two) { const double2 v = *reinterpret_cast<const double2*>(nat + q); e = v.x; o = v.y; }
     else e = nat[q];
     if (scale) { e = e * f; o = o * f; }
+    if (shift) { const double avg = shift[0] / shift[1]; e = e - avg; o = o - avg; }
     const int       ce = S.colour(i, j);
     const long long d  = S.idx(i, j, k);
     (ce ? s1 : s0)[d] = e;
     if (two) (ce ? s0 : s1)[d] = o;  // (i+1) >> 1 == i >> 1 for even i
+}
+// PoissonOp::preCond(cor, res, 0) (cor = res * Dinv, PoissonOp.cpp:893-911) fused with the two
+// conversions that start a relaxation: writes split(cor) and split(res * scale) from one read of
+// res and Dinv.
+__global__ void split_precond_k(Lay L, SLay S, const double* __restrict__ res, const double* __restrict__ Dinv,
+                                const double* __restrict__ scale, double* __restrict__ c0, double* __restrict__ c1,
+                                double* __restrict__ r0, double* __restrict__ r1)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    const int i = 2 * t;
+    if (i >= L.nx || j >= L.ny) return;
+    const double    f = scale[k];
+    const long long q = L.idx(i, j, k);
+    double          re, ro = 0.0, de, dd = 0.0;
+    const bool      two = i + 1 < L.nx;
+    if (two) {
+        const double2 v = *reinterpret_cast<const double2*>(res + q);
+        const double2 w = *reinterpret_cast<const double2*>(Dinv + q);
+        re = v.x; ro = v.y; de = w.x; dd = w.y;
+    } else { re = res[q]; de = Dinv[q]; }
+    const int       ce = S.colour(i, j);
+    const long long d  = S.idx(i, j, k);
+    (ce ? c1 : c0)[d] = re * de;
+    (ce ? r1 : r0)[d] = re * f;
+    if (two) { (ce ? c0 : c1)[d] = ro * dd; (ce ? r0 : r1)[d] = ro * f; }
 }
 __global__ void unsplit_field_k(Lay L, SLay S, double* __restrict__ nat, const double* __restrict__ s0,
                                 const double* __restrict__ s1)
@@ -76,11 +107,20 @@ __global__ void unsplit_field_k(Lay L, SLay S, double* __restrict__ nat, const d
         *reinterpret_cast<double2*>(nat + q) = make_double2(e, o);
     } else nat[q] = e;
 }
-void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1, const double* scale)
+void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1, const double* scale,
+                 const double* shift)
 {
     const dim3 b(64, 4, 1);
     const dim3 g(((L.nx + 1) / 2 + 63) / 64, (L.ny + 3) / 4, L.nz);
-    split_field_k<<<g, b, 0, st>>>(L, S, nat, s0, s1, scale);
+    split_field_k<<<g, b, 0, st>>>(L, S, nat, s0, s1, scale, shift);
+    note_launch();
+}
+void split_precond(cudaStream_t st, const Lay& L, const SLay& S, const double* res, const double* Dinv, const double* scale,
+                   double* c0, double* c1, double* r0, double* r1)
+{
+    const dim3 b(64, 4, 1);
+    const dim3 g(((L.nx + 1) / 2 + 63) / 64, (L.ny + 3) / 4, L.nz);
+    split_precond_k<<<g, b, 0, st>>>(L, S, res, Dinv, scale, c0, c1, r0, r1);
     note_launch();
 }
 void unsplit_field(cudaStream_t st, const Lay& L, const SLay& S, double* nat, const double* s0, const double* s1)
@@ -217,8 +257,17 @@ bool vertline_split_fits(int nz) { return vertline_split_smem(nz) <= 110 * 1024;
 template <int NW, int U, int MINB, bool TG>
 __global__ void __launch_bounds__(NW * 32, MINB)
     vertline_split_k(SLay S, const double* __restrict__ mx, const double* __restrict__ my, const double* __restrict__ tab,
-                     double* __restrict__ own, const double* __restrict__ oth, const double* __restrict__ rhs, int pass, int CL)
+                     double* __restrict__ own, const double* __restrict__ oth, const double* __restrict__ rhs, int pass, int CL,
+                     int region, int nbMask)
 {
+    // region 1 / 2: only the CTAs that do / do not own cells of a face layer that is sent to a
+    // neighbouring tile (nbMask bits: x-lo, x-hi, y-lo, y-hi), so that the exchange of those layers
+    // can overlap the rest of the pass (Op::relaxLineSplit).
+    if (region != 0) {
+        const bool edge = ((nbMask & 1) && blockIdx.x == 0) || ((nbMask & 2) && blockIdx.x == gridDim.x - 1) ||
+                          ((nbMask & 4) && blockIdx.y == 0) || ((nbMask & 8) && blockIdx.y == gridDim.y - 1);
+        if (edge != (region == 1)) return;
+    }
     extern __shared__ double sm[];
     const int     N  = S.nz;
     double* const sy = sm;                     // [N][32] local sweeps, in place
@@ -313,7 +362,7 @@ __global__ void __launch_bounds__(NW * 32, MINB)
 }
 
 void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const double* tab, double* own, const double* oth,
-                         const double* rhs, int pass)
+                         const double* rhs, int pass, int region, int nbMask)
 {
     const size_t sh = vertline_split_smem(S.nz);
     const int    CL = vertline_split_chunk(S.nz);
@@ -326,7 +375,7 @@ void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const do
             cudaFuncSetAttribute(vertline_split_k<NWv, U, MB, TGv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); \
             configured = sh;                                                                                          \
         }                                                                                                             \
-        vertline_split_k<NWv, U, MB, TGv><<<g, NWv * 32, sh, st>>>(S, c.mxl, c.myl, tab, own, oth, rhs, pass, CL);    \
+        vertline_split_k<NWv, U, MB, TGv><<<g, NWv * 32, sh, st>>>(S, c.mxl, c.myl, tab, own, oth, rhs, pass, CL, region, nbMask); \
     }
     if (v.nw == 8 && v.u == 2 && v.minb == 2) SB_LAUNCH(8, 2, 2, false)
     else if (v.nw == 8 && v.u == 8) SB_LAUNCH(8, 8, 1, false)

@@ -389,8 +389,7 @@ SolverStatus MGSolver::cycle(bool fmgMode, double* phi, const double* rhs, bool 
         if (fmgMode) {
             fmg_residualEq(c, r, 0);  // allFMG = true (MGSolverI.H:444, 517)
         } else {
-            op.preCond(c, r, 0);
-            vCycle_residualEq(c, r, 0);
+            vCycle_residualEq(c, r, 0, /*corIsPreCond: op.preCond(c, r, 0) fused into the first relaxation*/ true);
         }
         op.incr(phi, c, 1.0);
         op.residual(r, phi, rhs, homog);
@@ -416,19 +415,20 @@ SolverStatus MGSolver::cycle(bool fmgMode, double* phi, const double* rhs, bool 
 }
 
 // MGSolver<T>::vCycle_residualEq (MGSolverI.H:617-754)
-void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth)
+void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth, bool corIsPreCond)
 {
+    const int pre = corIsPreCond ? Op::RELAX_PRE_PRECOND : Op::RELAX_PRE_NONE;
     if (depth == aggDepth) {  // the rest of the hierarchy runs on rank 0
         Op& dist = *ops[depth];
         aggGather(a_res, aggRes, SB_CELL, dist);
-        aggGather(a_cor, aggCor, SB_CELL, dist);
-        if (agg) agg->vCycle_residualEq(aggCor, aggRes, 0);
+        if (!corIsPreCond) aggGather(a_cor, aggCor, SB_CELL, dist);
+        if (agg) agg->vCycle_residualEq(aggCor, aggRes, 0, corIsPreCond);
         aggScatter(a_cor, aggCor, dist);
         return;
     }
     Op& op = *ops[depth];
     if (depth == opt.maxDepth) {
-        op.relax(a_cor, a_res, opt.numSmoothBottom);
+        op.relax(a_cor, a_res, opt.numSmoothBottom, false, pre);
         if (bottom) bottom->solve(a_cor, a_res, true, false);
         return;
     }
@@ -436,14 +436,15 @@ void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth)
     double* crseCor = cor[depth + 1];
     double* crseRes = res[depth + 1];
     double* tmp     = tmpRes[depth];
-    op.relax(a_cor, a_res, opt.numSmoothDown);
+    op.relax(a_cor, a_res, opt.numSmoothDown, false, pre);
     op.residual(tmp, a_cor, a_res, true);
     op.MGRestrict(crseOp, crseRes, tmp);
-    crseOp.preCond(crseCor, crseRes, 0);
     const int numCycles = std::abs(opt.numCycles);
-    for (int i = 0; i < numCycles; ++i) vCycle_residualEq(crseCor, crseRes, depth + 1);
-    op.MGProlong(crseOp, a_cor, crseCor, opt.prolongOrder);
-    op.relax(a_cor, a_res, opt.numSmoothUp, /*resUnchanged since the down-relax*/ opt.numSmoothDown >= 2);
+    if (numCycles == 0) crseOp.preCond(crseCor, crseRes, 0);
+    for (int i = 0; i < numCycles; ++i) vCycle_residualEq(crseCor, crseRes, depth + 1, /*crseOp.preCond(crseCor, crseRes, 0)*/ i == 0);
+    const bool shiftPending = op.MGProlong(crseOp, a_cor, crseCor, opt.prolongOrder, /*deferKernel*/ true);
+    op.relax(a_cor, a_res, opt.numSmoothUp, /*resUnchanged since the down-relax*/ opt.numSmoothDown >= 2,
+             shiftPending ? Op::RELAX_PRE_SHIFT : Op::RELAX_PRE_NONE);
 }
 
 // MGSolver<T>::fmg_residualEq (MGSolverI.H:758-820)
@@ -464,8 +465,8 @@ void MGSolver::fmg_residualEq(double* a_cor, const double* a_res, int depth)
         double* crseRes = res[depth + 1];
         op.MGRestrict(crseOp, crseRes, a_res);
         fmg_residualEq(crseCor, crseRes, depth + 1);
-        op.MGProlong(crseOp, a_cor, crseCor, opt.prolongOrderFMG);
-        op.relax(a_cor, a_res, opt.numSmoothUpFMG);
+        const bool shiftPending = op.MGProlong(crseOp, a_cor, crseCor, opt.prolongOrderFMG, /*deferKernel*/ true);
+        op.relax(a_cor, a_res, opt.numSmoothUpFMG, false, shiftPending ? Op::RELAX_PRE_SHIFT : Op::RELAX_PRE_NONE);
     }
     const int numCycles = std::abs(opt.numCycles);
     for (int i = 0; i < numCycles; ++i) vCycle_residualEq(a_cor, a_res, depth);

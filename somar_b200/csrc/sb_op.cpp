@@ -34,6 +34,9 @@ Context::~Context()
     delete comm;
     if (scratch) cudaFree(scratch);
     if (hpin) cudaFreeHost(hpin);
+    if (evEdge) cudaEventDestroy(evEdge);
+    if (evHalo) cudaEventDestroy(evHalo);
+    if (commSt) cudaStreamDestroy(commSt);
     if (st && !parent) cudaStreamDestroy(st);
 }
 void Context::profBegin(const char* key, int depth, cudaEvent_t* e0)
@@ -256,6 +259,7 @@ void Op::setupLayout()
     SB_CUDA(cudaMemcpy(boxLoHi, lh.data(), lh.size() * sizeof(int), cudaMemcpyHostToDevice));
     SB_CUDA(cudaMalloc((void**)&redPartial, k::reduce_partial_len(nl) * sizeof(double)));
     SB_CUDA(cudaMalloc((void**)&redOut, 2 * nl * sizeof(double)));
+    SB_CUDA(cudaMalloc((void**)&shiftBuf, 2 * sizeof(double)));
     SB_CUDA(cudaMalloc((void**)&pivotFlag, sizeof(int)));
     SB_CUDA(cudaMemset(pivotFlag, 0, sizeof(int)));
     if ((size_t)2 * nl + 16 > ctx->hpinLen) SB_FAIL("too many boxes per rank for the pinned scalar buffer");
@@ -279,7 +283,7 @@ Op::~Op()
     for (int i = 0; i < 3; ++i) cudaFree(Jgup[i]);
     cudaFree(lineTab); cudaFree(lineTabS);
     for (double* q : sp) cudaFree(q);
-    cudaFree(mtab); cudaFree(loBC); cudaFree(hiBC); cudaFree(boxLoHi); cudaFree(redPartial); cudaFree(redOut); cudaFree(pivotFlag);
+    cudaFree(mtab); cudaFree(loBC); cudaFree(hiBC); cudaFree(boxLoHi); cudaFree(redPartial); cudaFree(redOut); cudaFree(shiftBuf); cudaFree(pivotFlag);
     for (int d = 0; d < 3; ++d)
         for (int s = 0; s < 2; ++s)
             for (int w = 0; w < 2; ++w) cudaFree(xbuf[d][s][w]);
@@ -295,7 +299,12 @@ Coef Op::coef() const
     c.loBC = loBC; c.hiBC = hiBC; c.beta = beta;
     return c;
 }
-BoxList Op::boxlist() const { return BoxList{nlocal(), boxLoHi, boxLoHi + 3 * nlocal()}; }
+BoxList Op::boxlist() const
+{
+    int w = 1;
+    for (int lb : local) w = std::max(w, boxes[lb].size(0));
+    return BoxList{nlocal(), boxLoHi, boxLoHi + 3 * nlocal(), w};
+}
 
 // LevelGeometry::createMetricCache (LevelGeometry.cpp:238-277): per box, FABs grown by 4 ghosts,
 // each filled by GeoSourceInterface::fill_J / fill_Jgup, i.e. from 1-D dx/dXi tables whose xi is
@@ -635,7 +644,7 @@ void Op::checkPivot()
 // Line relaxation on colour-split storage: convert once, iterate, convert back.  The call order
 // of the reference is kept: physical + exchange ghosts before the first colour, exchange ghosts
 // only before the second (PoissonOp.cpp:1957-1965).
-void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUnchanged)
+void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUnchanged, int pre)
 {
     if (!sp[0]) {
         for (double*& q : sp) {
@@ -646,16 +655,54 @@ void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUncha
     }
     cudaEvent_t e0;
     ctx->profBegin("linesplit_convert", depth, &e0);
-    if (!(resUnchanged && splitResSrc == res)) {
-        k::split_field(st(), lay, slay, res, sp[2], sp[3], lineTabS);  // rhs_k / (beta J_k)
+    if (pre == RELAX_PRE_PRECOND) {
+        k::split_precond(st(), lay, slay, res, Dinv, lineTabS, sp[0], sp[1], sp[2], sp[3]);
         splitResSrc = res;
+    } else {
+        if (!(resUnchanged && splitResSrc == res)) {
+            k::split_field(st(), lay, slay, res, sp[2], sp[3], lineTabS);  // rhs_k / (beta J_k)
+            splitResSrc = res;
+        }
+        k::split_field(st(), lay, slay, cor, sp[0], sp[1], nullptr, pre == RELAX_PRE_SHIFT ? shiftBuf : nullptr);
     }
-    k::split_field(st(), lay, slay, cor, sp[0], sp[1], nullptr);
     ctx->profEnd("linesplit_convert", depth, e0);
+    if (ctx->nranks > 1) {
+        // Neighbouring tiles: the CTAs that own cells of an exchanged face layer run first; their
+        // layers travel on a second stream while the interior of the pass is computed.  Ghost
+        // values and their consumers are the same as in the serial order below.
+        if (!ctx->commSt) {
+            SB_CUDA(cudaStreamCreateWithFlags(&ctx->commSt, cudaStreamNonBlocking));
+            SB_CUDA(cudaEventCreateWithFlags(&ctx->evEdge, cudaEventDisableTiming));
+            SB_CUDA(cudaEventCreateWithFlags(&ctx->evHalo, cudaEventDisableTiming));
+        }
+        int nbMask = 0;
+        for (int d = 0; d < 2; ++d)
+            for (int s = 0; s < 2; ++s)
+                if (side[d][s].kind == SIDE_NEIGHBOR) nbMask |= 1 << (2 * d + s);
+        const int last = 2 * iters - 1;
+        for (int n = 0; n <= last; ++n) {
+            const int pass = n & 1;
+            k::fill_ghosts_split(st(), slay, sp[0], sp[1], side, dim, pass == 0);
+            if (n == 0) ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1]);
+            else SB_CUDA(cudaStreamWaitEvent(st(), ctx->evHalo, 0));
+            ctx->profBegin("vertline", depth, &e0);
+            if (nbMask && n < last) {
+                k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass, 1, nbMask);
+                SB_CUDA(cudaEventRecord(ctx->evEdge, st()));
+                SB_CUDA(cudaStreamWaitEvent(ctx->commSt, ctx->evEdge, 0));
+                ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1], ctx->commSt);
+                SB_CUDA(cudaEventRecord(ctx->evHalo, ctx->commSt));
+                k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass, 2, nbMask);
+            } else {
+                k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass);
+                if (n < last) SB_CUDA(cudaEventRecord(ctx->evHalo, st()));
+            }
+            ctx->profEnd("vertline", depth, e0);
+        }
+    } else
     for (int it = 0; it < iters; ++it)
         for (int pass = 0; pass < 2; ++pass) {
             k::fill_ghosts_split(st(), slay, sp[0], sp[1], side, dim, pass == 0);
-            if (ctx->nranks > 1) ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1]);
             ctx->profBegin("vertline", depth, &e0);
             k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass);
             ctx->profEnd("vertline", depth, e0);
@@ -665,8 +712,13 @@ void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUncha
     ctx->profEnd("linesplit_convert", depth, e0);
 }
 
-void Op::relax(double* cor, const double* res, int iters, bool resUnchanged)
+void Op::relax(double* cor, const double* res, int iters, bool resUnchanged, int pre)
 {
+    if (pre != RELAX_PRE_NONE) {
+        if (relaxMethod == SB_RELAX_VERTLINE && lineSplit && iters >= 2) { relaxLineSplit(cor, res, iters, resUnchanged, pre); return; }
+        if (pre == RELAX_PRE_PRECOND) k::mult_valid(st(), lay, cor, res, Dinv);
+        else k::add_scalar_valid(st(), lay, cor, shiftBuf);
+    }
     switch (relaxMethod) {
         case SB_RELAX_NONE: break;
         case SB_RELAX_GSRB:  // PoissonOp.cpp:1833-1870
@@ -684,7 +736,7 @@ void Op::relax(double* cor, const double* res, int iters, bool resUnchanged)
             break;
         case SB_RELAX_VERTLINE: {  // PoissonOp.cpp:1927-2010
             if (iters == 0) return;
-            if (lineSplit && iters >= 2) { relaxLineSplit(cor, res, iters, resUnchanged); return; }
+            if (lineSplit && iters >= 2) { relaxLineSplit(cor, res, iters, resUnchanged, RELAX_PRE_NONE); return; }
             const size_t n  = (size_t)((lay.nx + 1) / 2) * lay.ny * lay.nz;
             double*      wd = lineFast ? nullptr : (double*)ctx->getScratch(2 * n * sizeof(double));
             double*      wb = wd + (lineFast ? 0 : n);
@@ -729,25 +781,27 @@ void Op::preCond(double* phi, const double* rhs, int relaxIters)
 }
 
 // PoissonOp::removeKernel (PoissonOp.cpp:821-846) -> Integral::sum (Integral.cpp:249-267)
-void Op::removeKernel(double* phi)
+bool Op::removeKernel(double* phi, bool defer)
 {
-    if (!hasNullSpace) return;
+    if (!hasNullSpace) return false;
     const double dv = dXi[0] * dXi[1] * dXi[2];
     k::reduce_boxes(st(), lay, boxlist(), 4, phi, J, dim == 2 ? dXi[0] * dXi[2] : dv, redPartial, redOut);
     const int nl = nlocal();
     if (ctx->nranks == 1 && nl == 1) {
-        k::add_scalar_valid(st(), lay, phi, redOut);
-        return;
+        SB_CUDA(cudaMemcpyAsync(shiftBuf, redOut, 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->st));
+    } else {
+        SB_CUDA(cudaMemcpyAsync(ctx->hpin, redOut, 2 * nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+        ctx->sync();
+        double sv[2] = {0.0, 0.0};
+        for (int b = 0; b < nl; ++b) { sv[0] += ctx->hpin[2 * b]; sv[1] += ctx->hpin[2 * b + 1]; }
+        ctx->allreduceSum(sv, 2);
+        ctx->hpin[0] = sv[0]; ctx->hpin[1] = sv[1];
+        SB_CUDA(cudaMemcpyAsync(shiftBuf, ctx->hpin, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+        SB_CUDA(cudaStreamSynchronize(ctx->st));  // hpin is reused by the next reduction
     }
-    SB_CUDA(cudaMemcpyAsync(ctx->hpin, redOut, 2 * nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
-    ctx->sync();
-    double sv[2] = {0.0, 0.0};
-    for (int b = 0; b < nl; ++b) { sv[0] += ctx->hpin[2 * b]; sv[1] += ctx->hpin[2 * b + 1]; }
-    ctx->allreduceSum(sv, 2);
-    ctx->hpin[0] = sv[0]; ctx->hpin[1] = sv[1];
-    SB_CUDA(cudaMemcpyAsync(redOut, ctx->hpin, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
-    k::add_scalar_valid(st(), lay, phi, redOut);
-    ctx->sync();  // hpin is reused by the next reduction
+    if (defer) return true;
+    k::add_scalar_valid(st(), lay, phi, shiftBuf);
+    return false;
 }
 
 // StateOps::norm (LDFABOps.cpp:134-164) with FArrayBox::norm (FArrayBox.cpp:56-150)
@@ -798,7 +852,7 @@ void Op::MGRestrict(Op& crse, double* crseRes, const double* fineRes)
 }
 
 // PoissonOp::MGProlong (PoissonOp.cpp:1032-1152)
-void Op::MGProlong(Op& crse, double* finePhi, double* crseCor, int order)
+bool Op::MGProlong(Op& crse, double* finePhi, double* crseCor, int order, bool deferKernel)
 {
     int ref[3];
     for (int d = 0; d < 3; ++d) ref[d] = domain.size(d) / crse.domain.size(d);
@@ -819,7 +873,7 @@ void Op::MGProlong(Op& crse, double* finePhi, double* crseCor, int order)
             k::prolong_quad2(st(), lay, crse.lay, ref, finePhi, crseCor, dim);
         }
     }
-    removeKernel(finePhi);
+    return removeKernel(finePhi, deferKernel);
 }
 
 // PoissonOp::levelDivergence (PoissonOp.cpp:1568-1610)
