@@ -189,7 +189,9 @@ void pack_faces_split(cudaStream_t st, const SLay& S, double* s0, double* s1, do
 void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const double* tab, double* own, const double* oth,
                          const double* rhs, int pass, int region = 0, int nbMask = 0);
 bool vertline_split_fits(int nz);
-int  vertline_split_chunk(int nz);  // levels per warp chunk (the P/Q tables depend on it)
+int  vertline_split_chunk(int nz);  // levels per warp chunk (the tables depend on it)
+int  vertline_split_nw();           // chunks per column
+bool vertline_split_fused();        // which of the two kernels (and table layouts) is in use
 void j_deviation(cudaStream_t st, const Lay& L, const double* J, const double* jcol, double* out);
 
 void restrict_avg(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* crse, const double* fine);

@@ -222,37 +222,179 @@ void pack_faces_split(cudaStream_t st, const SLay& S, double* s0, double* s1, do
 }
 
 // ------------------------------------------------------------------------------------------
-// The relaxation pass.  tab = [6][N]: s (unused here: folded into the split right-hand side),
-// a_k = -MzL_k / d'_{k-1}, P_k = prod_{m = chunk start..k} a_m, g_k = 1 / d'_k,
-// c_k = -MzR_k g_k, Q_k = prod_{m = k..chunk end} c_m.   own / oth: the colour being updated and
-// the other one; rhs: this colour's right-hand side, already multiplied by s_k.
+// The relaxation pass.  own / oth: the colour being updated and the other one; rhs: this colour's
+// right-hand side, already multiplied by s_k = 1 / (beta J_k).  Two kernels:
+//
+//  * vertline_fused_k (default).  In terms of z_k = g_k y_k the Thomas sweeps are
+//        z_k = g_k b_k + a'_k z_{k-1},   x_k = z_k + c_k x_{k+1},   a'_k = -MzL_k g_k, c_k = -MzR_k g_k, g_k = 1 / d'_k.
+//    A warp runs the forward recurrence over its chunk from zero (zl) and, in the same loop,
+//    accumulates acc = sum_k R_k zl_k with R_k = prod_{m = chunk start}^{k-1} c_m: the local part of
+//    the chunk's first unknown.  The true values are z_k = zl_k + P'_k Z and
+//    x_first = acc + Z T + Rend X, where Z / X are the carries entering the chunk from below /
+//    above and P'_k = prod a', T = sum_k R_k P'_k, Rend = prod c are tables.  So after ONE barrier
+//    every warp resolves both carry chains from the NW chunk summaries and its backward sweep
+//    produces final values that go straight to HBM: two passes over shared memory per level
+//    instead of three, two barriers instead of three.
+//    tab = {a', g}[N] | {P', c}[N] | R[N] | Pend[NW] | T[NW] | Rend[NW].
+//  * vertline_split_k (SB_LINE_VARIANT=1): the earlier three-phase form (local forward, local
+//    backward, correction), tab = [6][N]: s, a, P, g, c, Q.
 // ------------------------------------------------------------------------------------------
-// Launch shape (development knob SB_LINE_VARIANT, read once): warps per CTA = chunks per column
-// (the P/Q tables are built for it), loads in flight per thread, CTAs per SM, tables in shared
-// memory or read through L1.
-struct LineVariant { int nw, u, minb, tg; };
+// Launch shape (development knob SB_LINE_VARIANT, read once).
+struct LineVariant { int nw, u, minb, fused; };
 static LineVariant line_variant()
 {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SB_LINE_VARIANT"); v = e ? atoi(e) : 0; }
     switch (v) {
-        case 1: return {8, 2, 2, 0};
-        case 2: return {8, 8, 1, 0};
-        case 3: return {8, 2, 3, 1};
-        case 4: return {16, 2, 2, 0};
-        case 5: return {16, 1, 2, 0};
-        case 6: return {8, 4, 3, 1};
-        case 7: return {16, 2, 2, 1};
-        default: return {8, 4, 2, 0};
+        case 1: return {8, 4, 2, 0};
+        case 2: return {8, 4, 2, 1};
+        case 3: return {8, 8, 1, 1};
+        case 4: return {16, 4, 1, 1};
+        case 5: return {8, 4, 1, 1};
+        default: return {8, 2, 2, 1};  // measured best on B200 (profiles/r1_v4_summary.md)
     }
 }
-int vertline_split_chunk(int nz) { const int nw = line_variant().nw; return (nz + nw - 1) / nw; }
+int  vertline_split_chunk(int nz) { const int nw = line_variant().nw; return (nz + nw - 1) / nw; }
+int  vertline_split_nw() { return line_variant().nw; }
+bool vertline_split_fused() { return line_variant().fused != 0; }
 size_t vertline_split_smem(int nz)
 {
     const LineVariant v = line_variant();
-    return ((size_t)nz * 32 + (v.tg ? 0 : 5 * (size_t)nz) + 2 * (size_t)v.nw * 32) * sizeof(double);
+    return ((size_t)nz * 32 + 5 * (size_t)nz + 2 * (size_t)v.nw * 32 + 3 * (size_t)v.nw) * sizeof(double);
 }
 bool vertline_split_fits(int nz) { return vertline_split_smem(nz) <= 110 * 1024; }
+
+// ALIGNED: nz = NW * CL and CL a multiple of 2 U (true for the power-of-two depths of the bench
+// grid): no clamps or per-level predicates, 32-bit element offsets (one IMAD.WIDE per load).
+template <int NW, int U, int MINB, bool ALIGNED>
+__global__ void __launch_bounds__(NW * 32, MINB)
+    vertline_fused_k(SLay S, const double* __restrict__ mx, const double* __restrict__ my, const double* __restrict__ tab,
+                     double* __restrict__ own, const double* __restrict__ oth, const double* __restrict__ rhs, int pass, int CL,
+                     int region, int nbMask)
+{
+    // region 1 / 2: only the CTAs that do / do not own cells of a face layer that is sent to a
+    // neighbouring tile (nbMask bits: x-lo, x-hi, y-lo, y-hi), so that the exchange of those layers
+    // can overlap the rest of the pass (Op::relaxLineSplit).
+    if (region != 0) {
+        const bool edge = ((nbMask & 1) && blockIdx.x == 0) || ((nbMask & 2) && blockIdx.x == gridDim.x - 1) ||
+                          ((nbMask & 4) && blockIdx.y == 0) || ((nbMask & 8) && blockIdx.y == gridDim.y - 1);
+        if (edge != (region == 1)) return;
+    }
+    extern __shared__ double sm[];
+    const int      N  = S.nz;
+    double* const  sy = sm;                         // [N][32] local forward sweep
+    double* const  cz = sm + (size_t)N * 32;        // [NW][32] its value at the chunk end
+    double* const  ca = cz + NW * 32;               // [NW][32] acc of the chunk
+    double* const  ts = ca + NW * 32;               // tables
+    const double2* const T1 = reinterpret_cast<const double2*>(ts);          // {a', g}
+    const double2* const T2 = reinterpret_cast<const double2*>(ts + 2 * N);  // {P', c}
+    const double*  const tR = ts + 4 * N;
+    const double*  const tPend = ts + 5 * N;
+    const double*  const tT    = tPend + NW;
+    const double*  const tRend = tT + NW;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int j    = blockIdx.y;
+    const int i0   = (pass + S.par + j) & 1;   // own cells of this row: i = 2 m + i0
+    const int m    = blockIdx.x * 32 + lane;
+    const bool act = 2 * m + i0 < S.nx;
+    const int  mm  = act ? m : 0;              // idle lanes shadow column 0 and never store
+    const int  ii  = 2 * mm + i0;
+    const double mxl = mx[ii], mxr = mx[S.nx + ii], myl = my[j], myr = my[S.ny + j];
+    for (int k = threadIdx.x; k < 5 * N + 3 * NW; k += NW * 32) ts[k] = tab[k];
+    const long long base = (long long)(SOX + mm) + S.sy * (long long)(1 + j);
+    const double*   pw = oth + base + (i0 - 1);  // west neighbour (east = pw[1])
+    const double*   ps = oth + base - S.sy;      // south
+    const double*   pn = oth + base + S.sy;      // north
+    const double*   pr = rhs + base;
+    const int       szi = (int)S.sz;             // one colour array has fewer than 2^31 elements (checked by the launcher)
+
+    const int k0 = w * CL, k1 = ALIGNED ? k0 + CL : min(N, k0 + CL);
+    double    a0[U][5], a1[U][5];
+    // running pointers of the four load streams (levels are issued in ascending order)
+    const long long szl = S.sz;
+    const double *qw = pw + (long long)k0 * szl, *qs = ps + (long long)k0 * szl, *qn = pn + (long long)k0 * szl,
+                 *qr = pr + (long long)k0 * szl;
+    auto issue = [&](double(&a)[U][5], int kk) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ALIGNED) {
+                a[u][0] = qw[0]; a[u][1] = qw[1]; a[u][2] = qs[0]; a[u][3] = qn[0]; a[u][4] = qr[0];
+                qw += szl; qs += szl; qn += szl; qr += szl;
+            } else {
+                const int o = min(kk + u, N - 1) * szi;
+                a[u][0] = pw[o]; a[u][1] = pw[o + 1]; a[u][2] = ps[o]; a[u][3] = pn[o]; a[u][4] = pr[o];
+            }
+        }
+    };
+    if (k0 < k1) issue(a0, k0);
+    __syncthreads();  // tables visible
+
+    // P1: right-hand sides, local forward sweep in z, and the chunk's contribution to its first unknown.
+    double zl = 0.0, acc = 0.0;
+    auto consume = [&](double(&a)[U][5], int kk) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = kk + u;
+            if (ALIGNED || k < k1) {
+                const double  lphi = fma(myr, a[u][3], fma(myl, a[u][2], fma(mxr, a[u][1], mxl * a[u][0])));
+                const double  b    = a[u][4] - lphi;
+                const double2 t    = T1[k];
+                zl                 = fma(t.x, zl, t.y * b);
+                acc                = fma(tR[k], zl, acc);
+                sy[k * 32 + lane]  = zl;
+            }
+        }
+    };
+    if (ALIGNED) {
+        for (int kk = k0; kk < k1; kk += 2 * U) {
+            issue(a1, kk + U);
+            consume(a0, kk);
+            if (kk + 2 * U < k1) issue(a0, kk + 2 * U);
+            consume(a1, kk + U);
+        }
+    } else {
+        for (int kk = k0; kk < k1;) {
+            if (kk + U < k1) issue(a1, kk + U);
+            consume(a0, kk);
+            kk += U;
+            if (kk >= k1) break;
+            if (kk + U < k1) issue(a0, kk + U);
+            consume(a1, kk);
+            kk += U;
+        }
+    }
+    cz[w * 32 + lane] = zl;
+    ca[w * 32 + lane] = acc;
+    __syncthreads();
+    if (k0 >= k1) return;
+
+    // Carries.  Zs[v]: true z just below chunk v; X: true x just above this warp's chunk.
+    const int nch = ALIGNED ? NW : (N + CL - 1) / CL;
+    double    Zs[NW];
+    double    Z = 0.0, Zm = 0.0;
+#pragma unroll
+    for (int v = 0; v < NW; ++v) {
+        Zs[v] = Z;
+        if (v == w) Zm = Z;
+        if (v < nch) Z = fma(tPend[v], Z, cz[v * 32 + lane]);
+    }
+    double X = 0.0;
+#pragma unroll
+    for (int v = NW - 1; v >= 1; --v)
+        if (v < nch && v > w) X = fma(tRend[v], X, fma(Zs[v], tT[v], ca[v * 32 + lane]));
+
+    // P2: true backward sweep of this chunk, straight to HBM.
+    double* po = own + base + (long long)(k1 - 1) * szl;
+    double  xl = X;
+    if (!act) return;
+#pragma unroll 4
+    for (int k = k1 - 1; k >= k0; --k) {
+        const double2 t = T2[k];
+        xl              = fma(t.y, xl, fma(t.x, Zm, sy[k * 32 + lane]));
+        *po             = xl;
+        po -= szl;
+    }
+}
 
 template <int NW, int U, int MINB, bool TG>
 __global__ void __launch_bounds__(NW * 32, MINB)
@@ -368,23 +510,27 @@ void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const do
     const int    CL = vertline_split_chunk(S.nz);
     const dim3   g(((S.nx + 1) / 2 + 31) / 32, S.ny);
     const LineVariant v = line_variant();
-#define SB_LAUNCH(NWv, U, MB, TGv)                                                                                    \
-    {                                                                                                                 \
-        static size_t configured = 0;                                                                                 \
-        if (sh > configured) {                                                                                        \
-            cudaFuncSetAttribute(vertline_split_k<NWv, U, MB, TGv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); \
-            configured = sh;                                                                                          \
-        }                                                                                                             \
-        vertline_split_k<NWv, U, MB, TGv><<<g, NWv * 32, sh, st>>>(S, c.mxl, c.myl, tab, own, oth, rhs, pass, CL, region, nbMask); \
+#define SB_LAUNCH(KERNEL)                                                                                    \
+    {                                                                                                        \
+        static size_t configured = 0;                                                                        \
+        if (sh > configured) {                                                                               \
+            cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);              \
+            configured = sh;                                                                                 \
+        }                                                                                                    \
+        KERNEL<<<g, v.nw * 32, sh, st>>>(S, c.mxl, c.myl, tab, own, oth, rhs, pass, CL, region, nbMask);     \
     }
-    if (v.nw == 8 && v.u == 2 && v.minb == 2) SB_LAUNCH(8, 2, 2, false)
-    else if (v.nw == 8 && v.u == 8) SB_LAUNCH(8, 8, 1, false)
-    else if (v.nw == 8 && v.u == 2 && v.minb == 3) SB_LAUNCH(8, 2, 3, true)
-    else if (v.nw == 8 && v.u == 4 && v.minb == 3) SB_LAUNCH(8, 4, 3, true)
-    else if (v.nw == 16 && v.u == 2 && !v.tg) SB_LAUNCH(16, 2, 2, false)
-    else if (v.nw == 16 && v.u == 2 && v.tg) SB_LAUNCH(16, 2, 2, true)
-    else if (v.nw == 16 && v.u == 1) SB_LAUNCH(16, 1, 2, false)
-    else SB_LAUNCH(8, 4, 2, false)
+    if ((long long)S.sz * S.nz >= (1LL << 31)) SB_FAIL("colour-split field too large for 32-bit element offsets");
+    const bool al = S.nz == v.nw * CL && CL % (2 * v.u) == 0;
+    if (!v.fused) SB_LAUNCH((vertline_split_k<8, 4, 2, false>))
+    else if (v.nw == 8 && v.u == 2 && al) SB_LAUNCH((vertline_fused_k<8, 2, 2, true>))
+    else if (v.nw == 8 && v.u == 2) SB_LAUNCH((vertline_fused_k<8, 2, 2, false>))
+    else if (v.nw == 8 && v.u == 8 && al) SB_LAUNCH((vertline_fused_k<8, 8, 1, true>))
+    else if (v.nw == 16 && v.u == 4 && al) SB_LAUNCH((vertline_fused_k<16, 4, 1, true>))
+    else if (v.nw == 16 && v.u == 4) SB_LAUNCH((vertline_fused_k<16, 4, 1, false>))
+    else if (v.nw == 8 && v.u == 4 && v.minb == 1 && al) SB_LAUNCH((vertline_fused_k<8, 4, 1, true>))
+    else if (al && v.nw == 8) SB_LAUNCH((vertline_fused_k<8, 4, 2, true>))
+    else if (v.nw == 8) SB_LAUNCH((vertline_fused_k<8, 4, 2, false>))
+    else SB_FAIL("SB_LINE_VARIANT: no kernel instance for this shape");
 #undef SB_LAUNCH
     note_launch();
 }

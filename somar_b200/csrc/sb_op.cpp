@@ -530,21 +530,47 @@ void Op::buildLineTables(double sLo, double sHi)
     if (force && std::string(force) == "smem") return;
     if (!k::vertline_split_fits(N)) return;
     const int           CL = k::vertline_split_chunk(N);
-    std::vector<double> u(6 * (size_t)N);
-    for (int k = 0; k < N; ++k) {
-        u[k]         = t[k];
-        u[N + k]     = k > 0 ? t[N + (k - 1)] : 0.0;
-        u[3 * N + k] = t[2 * N + k];
-        u[4 * N + k] = k < N - 1 ? t[3 * N + k] : 0.0;
+    std::vector<double> u;
+    if (!k::vertline_split_fused()) {
+        u.assign(6 * (size_t)N, 0.0);
+        for (int k = 0; k < N; ++k) {
+            u[k]         = t[k];
+            u[N + k]     = k > 0 ? t[N + (k - 1)] : 0.0;
+            u[3 * N + k] = t[2 * N + k];
+            u[4 * N + k] = k < N - 1 ? t[3 * N + k] : 0.0;
+        }
+        for (int k0 = 0; k0 < N; k0 += CL) {
+            const int k1 = std::min(N, k0 + CL);
+            double    p  = 1.0;
+            for (int k = k0; k < k1; ++k) { p *= u[N + k]; u[2 * N + k] = p; }
+            p = 1.0;
+            for (int k = k1 - 1; k >= k0; --k) { p *= u[4 * N + k]; u[5 * N + k] = p; }
+        }
+    } else {
+        // vertline_fused_k: {a', g}[N] | {P', c}[N] | R[N] | Pend[NW] | T[NW] | Rend[NW]  (sb_line.cu)
+        const int NW = k::vertline_split_nw();
+        u.assign(5 * (size_t)N + 3 * (size_t)NW, 0.0);
+        for (int k = 0; k < N; ++k) {
+            const double g = t[2 * N + k];                          // 1 / d'_k
+            u[2 * k]     = k > 0 ? -(mzl[k] * g) : 0.0;             // a'_k
+            u[2 * k + 1] = g;
+            u[2 * N + 2 * k + 1] = k < N - 1 ? t[3 * N + k] : 0.0;  // c_k = -MzR_k g_k
+        }
+        for (int v = 0; v < NW; ++v) {
+            const int k0 = v * CL, k1 = std::min(N, k0 + CL);
+            double    P = 1.0, R = 1.0, T = 0.0;
+            for (int k = k0; k < k1; ++k) {
+                P *= u[2 * k];
+                u[2 * N + 2 * k] = P;   // P'_k
+                u[4 * N + k]     = R;   // R_k = prod_{m = k0}^{k-1} c_m
+                T += R * P;
+                R *= u[2 * N + 2 * k + 1];
+            }
+            if (k0 < k1) { u[5 * N + v] = P; u[5 * N + NW + v] = T; u[5 * N + 2 * NW + v] = R; }
+        }
     }
-    for (int k0 = 0; k0 < N; k0 += CL) {
-        const int k1 = std::min(N, k0 + CL);
-        double    p  = 1.0;
-        for (int k = k0; k < k1; ++k) { p *= u[N + k]; u[2 * N + k] = p; }
-        p = 1.0;
-        for (int k = k1 - 1; k >= k0; --k) { p *= u[4 * N + k]; u[5 * N + k] = p; }
-    }
-    if (!lineTabS) SB_CUDA(cudaMalloc((void**)&lineTabS, u.size() * sizeof(double)));
+    if (lineTabS) SB_CUDA(cudaFree(lineTabS));
+    SB_CUDA(cudaMalloc((void**)&lineTabS, u.size() * sizeof(double)));
     SB_CUDA(cudaMemcpy(lineTabS, u.data(), u.size() * sizeof(double), cudaMemcpyHostToDevice));
     slay      = makeSLay(lay);
     lineSplit = true;
@@ -656,11 +682,11 @@ void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUncha
     cudaEvent_t e0;
     ctx->profBegin("linesplit_convert", depth, &e0);
     if (pre == RELAX_PRE_PRECOND) {
-        k::split_precond(st(), lay, slay, res, Dinv, lineTabS, sp[0], sp[1], sp[2], sp[3]);
+        k::split_precond(st(), lay, slay, res, Dinv, lineTab, sp[0], sp[1], sp[2], sp[3]);
         splitResSrc = res;
     } else {
         if (!(resUnchanged && splitResSrc == res)) {
-            k::split_field(st(), lay, slay, res, sp[2], sp[3], lineTabS);  // rhs_k / (beta J_k)
+            k::split_field(st(), lay, slay, res, sp[2], sp[3], lineTab);  // rhs_k * s_k, s_k = 1 / (beta J_k) = lineTab[0..nz)
             splitResSrc = res;
         }
         k::split_field(st(), lay, slay, cor, sp[0], sp[1], nullptr, pre == RELAX_PRE_SHIFT ? shiftBuf : nullptr);
