@@ -158,6 +158,7 @@ void fill_ghosts(cudaStream_t st, const Lay& L, double* phi, const SideBC bc[3][
 // faces, then edges (needed only by the quadratic prolongation's mixed differences)
 void fill_ghosts_with_edges(cudaStream_t st, const Lay& L, double* phi, const SideBC bc[3][2], int dim);
 long long launch_count();
+void note_launches(long long n);  // kernels replayed by a CUDA graph launch
 // pack / unpack of one side's face layer for neighbour exchange
 void fill_ghosts_dir(cudaStream_t st, const Lay& L, double* phi, int dir, const SideBC& lo, const SideBC& hi, int ext0, int ext1);
 void extrap_domain_edges(cudaStream_t st, const Lay& L, double* phi, const SideBC bc[3][2], int dim);

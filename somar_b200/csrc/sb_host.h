@@ -31,6 +31,7 @@ struct Context {
     void profBegin(const char* key, int depth, cudaEvent_t* e0);
     void profEnd(const char* key, int depth, cudaEvent_t e0);
     void profResolve();
+    bool isProfiling() const { return parent ? parent->profiling : profiling; }
 
     Context(int dev, int rank, int nranks);
     explicit Context(Context& parent);  // single-rank view on the parent's device and stream
@@ -111,6 +112,12 @@ struct Op {
     bool    lineSplit = false;
     double* sp[4] = {nullptr, nullptr, nullptr, nullptr};
     const double* splitResSrc = nullptr;  // natural-layout field whose split copy sp[2], sp[3] hold
+    // The pass loop of a line relaxation on a small depth is launch-latency bound (two tiny kernels
+    // per colour pass): captured once per iteration count into a CUDA graph and replayed.
+    struct RelaxGraph { cudaGraphExec_t exec = nullptr; long long kernels = 0; };
+    std::map<int, RelaxGraph> relaxGraphs;
+    int                       relaxCallsSeen = 0;
+    void linePasses(int iters);  // the (ghost fill, colour pass) x 2 x iters loop on sp[]
     std::vector<double> hM[3];  // host copies of the 1-D tables over the whole domain (2*N_d)
     double* xbuf[3][2][2] = {};  // exchange buffers [dir][side][send/recv]
 

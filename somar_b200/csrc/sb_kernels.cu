@@ -15,6 +15,7 @@ static long long g_launches = 0;
 long long launch_count() { return g_launches; }
 #define LAUNCHED() (++g_launches)
 void note_launch() { ++g_launches; }
+void note_launches(long long n) { g_launches += n; }
 
 static inline dim3 grid3(int nx, int ny, int nz, dim3 b)
 {

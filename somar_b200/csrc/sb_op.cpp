@@ -283,6 +283,7 @@ Op::~Op()
     for (int i = 0; i < 3; ++i) cudaFree(Jgup[i]);
     cudaFree(lineTab); cudaFree(lineTabS);
     for (double* q : sp) cudaFree(q);
+    for (auto& kv : relaxGraphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     cudaFree(mtab); cudaFree(loBC); cudaFree(hiBC); cudaFree(boxLoHi); cudaFree(redPartial); cudaFree(redOut); cudaFree(shiftBuf); cudaFree(pivotFlag);
     for (int d = 0; d < 3; ++d)
         for (int s = 0; s < 2; ++s)
@@ -725,17 +726,50 @@ void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUncha
             }
             ctx->profEnd("vertline", depth, e0);
         }
-    } else
-    for (int it = 0; it < iters; ++it)
-        for (int pass = 0; pass < 2; ++pass) {
-            k::fill_ghosts_split(st(), slay, sp[0], sp[1], side, dim, pass == 0);
-            ctx->profBegin("vertline", depth, &e0);
-            k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass);
-            ctx->profEnd("vertline", depth, e0);
+    } else {
+        // Small depths: replay the pass loop as a CUDA graph (captured on the second call with this
+        // iteration count, once every kernel has been configured by a plain run).
+        static const long long graphCells = [] { const char* e = getenv("SB_GRAPH_CELLS"); return e ? atoll(e) : (1LL << 23); }();
+        const bool small = (long long)lay.nx * lay.ny * lay.nz <= graphCells;
+        if (small && !ctx->isProfiling()) {
+            RelaxGraph& g = relaxGraphs[iters];
+            if (!g.exec && ++relaxCallsSeen >= 2) {
+                cudaGraph_t     graph = nullptr;
+                const long long l0    = k::launch_count();
+                SB_CUDA(cudaStreamBeginCapture(st(), cudaStreamCaptureModeThreadLocal));
+                linePasses(iters);
+                SB_CUDA(cudaStreamEndCapture(st(), &graph));
+                g.kernels = k::launch_count() - l0;
+                k::note_launches(-g.kernels);  // captured, not launched
+                SB_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+                SB_CUDA(cudaGraphDestroy(graph));
+            }
+            if (g.exec) {
+                SB_CUDA(cudaGraphLaunch(g.exec, st()));
+                k::note_launches(g.kernels);
+            } else linePasses(iters);
+        } else {
+            for (int it = 0; it < iters; ++it)
+                for (int pass = 0; pass < 2; ++pass) {
+                    k::fill_ghosts_split(st(), slay, sp[0], sp[1], side, dim, pass == 0);
+                    ctx->profBegin("vertline", depth, &e0);
+                    k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass);
+                    ctx->profEnd("vertline", depth, e0);
+                }
         }
+    }
     ctx->profBegin("linesplit_convert", depth, &e0);
     k::unsplit_field(st(), lay, slay, cor, sp[0], sp[1]);
     ctx->profEnd("linesplit_convert", depth, e0);
+}
+
+void Op::linePasses(int iters)
+{
+    for (int it = 0; it < iters; ++it)
+        for (int pass = 0; pass < 2; ++pass) {
+            k::fill_ghosts_split(st(), slay, sp[0], sp[1], side, dim, pass == 0);
+            k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass);
+        }
 }
 
 void Op::relax(double* cor, const double* res, int iters, bool resUnchanged, int pre)
