@@ -247,11 +247,11 @@ static LineVariant line_variant()
     if (v < 0) { const char* e = getenv("SB_LINE_VARIANT"); v = e ? atoi(e) : 0; }
     switch (v) {
         case 1: return {8, 4, 2, 0};
-        case 2: return {8, 4, 2, 1};
+        case 2: return {8, 2, 2, 1};
         case 3: return {8, 8, 1, 1};
         case 4: return {16, 4, 1, 1};
         case 5: return {8, 4, 1, 1};
-        default: return {8, 2, 2, 1};  // measured best on B200 (profiles/r1_v4_summary.md)
+        default: return {8, 4, 2, 1};  // measured best on B200 (profiles/r1_v4_summary.md)
     }
 }
 int  vertline_split_chunk(int nz) { const int nw = line_variant().nw; return (nz + nw - 1) / nw; }
@@ -346,11 +346,28 @@ __global__ void __launch_bounds__(NW * 32, MINB)
         }
     };
     if (ALIGNED) {
+        // rolling prefetch: 2 U levels stay in flight; a slot is reloaded as soon as it is consumed
+        auto roll = [&](double(&a)[U][5], int kk, bool more) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int     k    = kk + u;
+                const double  lphi = fma(myr, a[u][3], fma(myl, a[u][2], fma(mxr, a[u][1], mxl * a[u][0])));
+                const double  b    = a[u][4] - lphi;
+                const double2 t    = T1[k];
+                zl                 = fma(t.x, zl, t.y * b);
+                acc                = fma(tR[k], zl, acc);
+                sy[k * 32 + lane]  = zl;
+                if (more) {
+                    a[u][0] = qw[0]; a[u][1] = qw[1]; a[u][2] = qs[0]; a[u][3] = qn[0]; a[u][4] = qr[0];
+                    qw += szl; qs += szl; qn += szl; qr += szl;
+                }
+            }
+        };
+        issue(a1, k0 + U);
         for (int kk = k0; kk < k1; kk += 2 * U) {
-            issue(a1, kk + U);
-            consume(a0, kk);
-            if (kk + 2 * U < k1) issue(a0, kk + 2 * U);
-            consume(a1, kk + U);
+            const bool more = kk + 2 * U < k1;
+            roll(a0, kk, more);
+            roll(a1, kk + U, more);
         }
     } else {
         for (int kk = k0; kk < k1;) {
