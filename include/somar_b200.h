@@ -35,6 +35,8 @@ enum { SB_STATUS_UNDEFINED = -1, SB_STATUS_DIVERGED = 0, SB_STATUS_CONVERGED = 1
 enum { SB_MAP_CARTESIAN = 0, SB_MAP_STRETCHED = 1, SB_MAP_CALLBACK = 2 };
 /* field centering */
 enum { SB_CELL = -1, SB_FACE_X = 0, SB_FACE_Y = 1, SB_FACE_Z = 2 };
+/* streams of a context: the compute stream every operator call runs on, and two copy streams */
+enum { SB_STREAM_COMPUTE = 0, SB_STREAM_H2D = 1, SB_STREAM_D2H = 2 };
 /* LevelHybridSolver::SolveMode (LevelHybridSolver.H) */
 enum { SB_MODE_MG = 1, SB_MODE_LEPTIC = 2, SB_MODE_LEPTIC_MG = 3 };
 
@@ -102,6 +104,11 @@ int sb_version(void);
 int sb_context_create(sb_context** ctx, int device, int rank, int nranks);
 int sb_context_destroy(sb_context* ctx);
 int sb_context_sync(sb_context* ctx);
+/* Stream ordering for callers that pipeline independent solves (SB_STREAM_*): work enqueued on
+ * `waiter` after this call starts only when everything enqueued on `signaller` so far has
+ * finished; sb_context_stream_sync blocks the host on one stream. */
+int sb_context_stream_wait(sb_context* ctx, int waiter, int signaller);
+int sb_context_stream_sync(sb_context* ctx, int which);
 /* Number of kernels this library launched on the context's stream since creation. */
 long long sb_context_launch_count(sb_context* ctx);
 /* CUDA-event stopwatch on the context's stream (what bench.py times with), and optional
@@ -151,6 +158,10 @@ int sb_field_destroy(sb_field* f);
  * into / out of the device field; only the part inside this rank's valid+ghost region moves. */
 int sb_field_upload(sb_field* f, const double* host, const int lo[3], const int hi[3]);
 int sb_field_download(sb_field* f, double* host, const int lo[3], const int hi[3]);
+/* The same copies, asynchronous on the context's H2D / D2H stream (host memory must be pinned);
+ * order them against the compute stream with sb_context_stream_wait. */
+int sb_field_upload_async(sb_field* f, const double* pinned_host, const int lo[3], const int hi[3]);
+int sb_field_download_async(sb_field* f, double* pinned_host, const int lo[3], const int hi[3]);
 
 /* ---- LevelOperator / StateOps / MGOperator methods ------------------------------------------ */
 int sb_op_apply_bcs(sb_op* op, sb_field* phi, int homog);                         /* PoissonOp.cpp:726-763 */

@@ -170,6 +170,13 @@ class Context:
     def sync(self):
         capi.check(self.lib.sb_context_sync(self.h))
 
+    def stream_wait(self, waiter, signaller):
+        """Work enqueued later on stream `waiter` starts after everything enqueued so far on `signaller`."""
+        capi.check(self.lib.sb_context_stream_wait(self.h, waiter, signaller))
+
+    def stream_sync(self, which):
+        capi.check(self.lib.sb_context_stream_sync(self.h, which))
+
     def timer_start(self):
         capi.check(self.lib.sb_context_timer_start(self.h))
 
@@ -221,6 +228,18 @@ class Field:
         if lo is None:
             lo, hi = self.box()
         capi.check(self.lib.sb_field_download(self.h, C.cast(ptr, capi.DP), _i3(lo), _i3(hi)))
+
+    def upload_ptr_async(self, ptr, lo=None, hi=None):
+        """Asynchronous upload from pinned host memory on the context's H2D stream."""
+        if lo is None:
+            lo, hi = self.box()
+        capi.check(self.lib.sb_field_upload_async(self.h, C.cast(ptr, capi.DP), _i3(lo), _i3(hi)))
+
+    def download_ptr_async(self, ptr, lo=None, hi=None):
+        """Asynchronous download into pinned host memory on the context's D2H stream."""
+        if lo is None:
+            lo, hi = self.box()
+        capi.check(self.lib.sb_field_download_async(self.h, C.cast(ptr, capi.DP), _i3(lo), _i3(hi)))
 
     def upload(self, arr, lo=None, hi=None):
         if lo is None:
@@ -398,6 +417,9 @@ class PoissonOp:
         if self.h:
             self.lib.sb_op_destroy(self.h)
             self.h = C.c_void_p()
+
+
+STREAM_COMPUTE, STREAM_H2D, STREAM_D2H = 0, 1, 2  # include/somar_b200.h SB_STREAM_*
 
 
 class _SolverBase:

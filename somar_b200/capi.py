@@ -142,6 +142,10 @@ PROTOTYPES = {
     "sb_solver_solve": (C.c_int, [P, P, P, C.c_int, C.c_int, C.c_double, C.POINTER(SolverStatus)]),
     "sb_solver_vcycle": (C.c_int, [P, P, P]),
     "sb_solver_precond_vcycle": (C.c_int, [P, P, P]),
+    "sb_context_stream_wait": (C.c_int, [P, C.c_int, C.c_int]),
+    "sb_context_stream_sync": (C.c_int, [P, C.c_int]),
+    "sb_field_upload_async": (C.c_int, [P, DP, IP, IP]),
+    "sb_field_download_async": (C.c_int, [P, DP, IP, IP]),
     "sb_project_host": (C.c_int, [P, DP * 3, DP, DP, C.c_double, DP, DP, C.POINTER(SolverStatus)]),
 }
 

@@ -134,8 +134,10 @@ int sb_op_destroy(sb_op* op)
     SB_END
 }
 
-static void copy3d(Op& o, int centering, double* dev, double* host, const int lo[3], const int hi[3], bool toDevice)
+static void copy3d(Op& o, int centering, double* dev, double* host, const int lo[3], const int hi[3], bool toDevice,
+                   cudaStream_t stream = nullptr)
 {
+    if (!stream) stream = o.ctx->st;
     // allowed region of the device array in global indices
     int alo[3], ahi[3];
     for (int d = 0; d < 3; ++d) {
@@ -161,7 +163,7 @@ static void copy3d(Op& o, int centering, double* dev, double* host, const int lo
                                (size_t)(chi[2] - clo[2] + 1));
     if (toDevice) { p.srcPtr = hp; p.srcPos = hpos; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
     else { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
-    SB_CUDA(cudaMemcpy3DAsync(&p, o.ctx->st));
+    SB_CUDA(cudaMemcpy3DAsync(&p, stream));
 }
 
 int sb_op_set_metric(sb_op* op, int centering, int box_id, const double* host, const int lo[3], const int hi[3])
@@ -261,6 +263,35 @@ int sb_field_download(sb_field* f, double* host, const int lo[3], const int hi[3
     copy3d(*f->f.op, f->f.centering, f->f.d, host, lo, hi, false);
     f->f.op->ctx->sync();
     SB_END
+}
+
+int sb_field_upload_async(sb_field* f, const double* host, const int lo[3], const int hi[3])
+{
+    SB_TRY REQ(f); REQ(host);
+    Op& o = *f->f.op;
+    copy3d(o, f->f.centering, f->f.d, const_cast<double*>(host), lo, hi, true, o.ctx->stream(SB_STREAM_H2D));
+    SB_END
+}
+int sb_field_download_async(sb_field* f, double* host, const int lo[3], const int hi[3])
+{
+    SB_TRY REQ(f); REQ(host);
+    Op& o = *f->f.op;
+    copy3d(o, f->f.centering, f->f.d, host, lo, hi, false, o.ctx->stream(SB_STREAM_D2H));
+    SB_END
+}
+int sb_context_stream_wait(sb_context* ctx, int waiter, int signaller)
+{
+    SB_TRY REQ(ctx);
+    cudaEvent_t e;
+    SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    SB_CUDA(cudaEventRecord(e, ctx->c.stream(signaller)));
+    SB_CUDA(cudaStreamWaitEvent(ctx->c.stream(waiter), e, 0));
+    SB_CUDA(cudaEventDestroy(e));  // released once the recorded work completes
+    SB_END
+}
+int sb_context_stream_sync(sb_context* ctx, int which)
+{
+    SB_TRY REQ(ctx); SB_CUDA(cudaStreamSynchronize(ctx->c.stream(which))); SB_END
 }
 
 // ---- operator methods ------------------------------------------------------------------------

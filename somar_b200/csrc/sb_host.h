@@ -16,6 +16,8 @@ struct Context {
     cudaStream_t st     = nullptr;
     cudaStream_t commSt = nullptr;          // halo exchanges that overlap interior work (multi-rank line relaxation)
     cudaEvent_t  evEdge = nullptr, evHalo = nullptr;
+    cudaStream_t copySt[2] = {nullptr, nullptr};  // SB_STREAM_H2D, SB_STREAM_D2H (asynchronous uploads / downloads)
+    cudaStream_t stream(int which);               // SB_STREAM_*; the copy streams are created on first use
     double*      hpin   = nullptr;  // pinned host scratch (scalars coming back from reductions)
     size_t       hpinLen = 0;
     void*        scratch = nullptr;  // device scratch shared by all depths (line-relax workspace)

@@ -37,7 +37,16 @@ Context::~Context()
     if (evEdge) cudaEventDestroy(evEdge);
     if (evHalo) cudaEventDestroy(evHalo);
     if (commSt) cudaStreamDestroy(commSt);
+    for (cudaStream_t q : copySt) if (q) cudaStreamDestroy(q);
     if (st && !parent) cudaStreamDestroy(st);
+}
+cudaStream_t Context::stream(int which)
+{
+    if (which == SB_STREAM_COMPUTE) return st;
+    if (which != SB_STREAM_H2D && which != SB_STREAM_D2H) SB_FAIL("bad stream id");
+    cudaStream_t& q = copySt[which - 1];
+    if (!q) SB_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    return q;
 }
 void Context::profBegin(const char* key, int depth, cudaEvent_t* e0)
 {

@@ -46,7 +46,7 @@ class RefResult:
 
 
 def run_ref(mode, nx, L, inp=None, max_box=(0, 0, 0), block_factor=None, offset=None, periodic=(0, 0, 0), relax=6,
-            mapname="cartesian", ampl=(0, 0, 0), extra=None, timeout=600, dim=3):
+            mapname="cartesian", ampl=(0, 0, 0), extra=None, timeout=600, dim=3, split_dirs=None):
     """Run the reference driver.  nx, L, offset: 3-vectors (2-D: dim=2 and 2-vectors)."""
     nx = list(nx)
     D = len(nx)
@@ -60,7 +60,7 @@ def run_ref(mode, nx, L, inp=None, max_box=(0, 0, 0), block_factor=None, offset=
         while block_factor > 1 and any(n % block_factor for n in nx[:D - 1]):
             block_factor //= 2
         block_factor = max(1, min(block_factor, 16))
-    split = [1] * (D - 1) + [0]
+    split = list(split_dirs) if split_dirs is not None else [1] * (D - 1) + [0]
     vec = lambda v: " ".join(str(x) for x in v)
     with tempfile.TemporaryDirectory() as td:
         args = [ref_binary(dim), DECK,

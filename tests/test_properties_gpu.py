@@ -152,3 +152,30 @@ def test_fused_precond_vcycle_is_bitwise_the_two_calls(ctx, relax, periodic):
     assert np.array_equal(a.download(), b.download())
     solver.free()
     op.free()
+
+
+def test_async_copies_are_ordered_by_stream_wait(ctx):
+    """sb_field_upload_async / sb_field_download_async on the copy streams, ordered against the compute
+    stream with sb_context_stream_wait, give the same bytes as the synchronous calls."""
+    import torch
+    nx = (64, 32, 16)
+    op = _op(ctx, nx, L=(4.0, 2.0, 1.0), box=(32, 16, 0), bf=8)
+    n = int(np.prod(nx))
+    src = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    dst = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    src.numpy()[:] = np.random.default_rng(9).standard_normal(n)
+    a, b, ref = op.field(), op.field(), op.field()
+    ref.upload_ptr(src.data_ptr())
+    op.preCond(b, ref, 0)
+    want = b.download()
+    C_, H, D = sb.STREAM_COMPUTE, sb.STREAM_H2D, sb.STREAM_D2H
+    for _ in range(3):
+        ctx.stream_wait(H, C_)
+        a.upload_ptr_async(src.data_ptr())
+        ctx.stream_wait(C_, H)
+        op.preCond(b, a, 0)
+        ctx.stream_wait(D, C_)
+        b.download_ptr_async(dst.data_ptr())
+        ctx.stream_sync(D)
+        assert np.array_equal(dst.numpy().reshape(nx, order="F"), want)
+    op.free()
