@@ -691,9 +691,8 @@ __global__ void prolong_c_k(Lay Lf, Lay Lc, int r1, int r2, double* __restrict__
 {
     const int ic = blockIdx.x * blockDim.x + threadIdx.x;
     const int jc = blockIdx.y * blockDim.y + threadIdx.y;
-    const int k  = blockIdx.z;
+    const int kc = blockIdx.z;
     if (ic >= Lc.nx || jc >= Lc.ny) return;
-    const int       kc = r2 == 2 ? (k >> 1) : k;
     const long long qc = Lc.idx(ic, jc, kc);
     const double    c  = crse[qc];
     double          m0 = 0.0, m1 = 0.0, m2 = 0.0;
@@ -709,42 +708,44 @@ __global__ void prolong_c_k(Lay Lf, Lay Lc, int r1, int r2, double* __restrict__
         m1 = 0.25 * (crse[qc + Lc.sy] + mid + crse[qc - Lc.sy]);
         m2 = 0.25 * (crse[qc + Lc.sz] + mid + crse[qc - Lc.sz]);
     }
-    const int    kk   = k - kc * r2;
-    const double dxf2 = order == 2 ? -0.5 + ((kk + 0.5) / r2) : -0.5 + ((kk + 0.5) * sc2);
-    for (int jj = 0; jj < r1; ++jj) {
-        const double    dxf1 = order == 2 ? -0.5 + ((jj + 0.5) / r1) : -0.5 + ((jj + 0.5) * sc1);
-        const long long qf   = Lf.idx(ic * R0, jc * r1 + jj, k);
-        double          f[R0];
-        if (R0 == 2) { const double2 v = *reinterpret_cast<const double2*>(fine + qf); f[0] = v.x; f[R0 - 1] = v.y; }
-        else f[0] = fine[qf];
+    for (int kk = 0; kk < r2; ++kk) {
+        const int    k    = kc * r2 + kk;
+        const double dxf2 = order == 2 ? -0.5 + ((kk + 0.5) / r2) : -0.5 + ((kk + 0.5) * sc2);
+        for (int jj = 0; jj < r1; ++jj) {
+            const double    dxf1 = order == 2 ? -0.5 + ((jj + 0.5) / r1) : -0.5 + ((jj + 0.5) * sc1);
+            const long long qf   = Lf.idx(ic * R0, jc * r1 + jj, k);
+            double          f[R0];
+            if (R0 == 2) { const double2 v = *reinterpret_cast<const double2*>(fine + qf); f[0] = v.x; f[R0 - 1] = v.y; }
+            else f[0] = fine[qf];
 #pragma unroll
-        for (int ii = 0; ii < R0; ++ii) {
-            double g = f[ii];
-            if (order == 0 || order == 1) g = g + c;
-            if (order == 1) {
-                const double dxf0 = -0.5 + ((ii + 0.5) * sc0);
-                g                 = g + dxf0 * m0 + dxf1 * m1 + dxf2 * m2;
+            for (int ii = 0; ii < R0; ++ii) {
+                double g = f[ii];
+                if (order == 0 || order == 1) g = g + c;
+                if (order == 1) {
+                    const double dxf0 = -0.5 + ((ii + 0.5) * sc0);
+                    g                 = g + dxf0 * m0 + dxf1 * m1 + dxf2 * m2;
+                }
+                if (order == 2) {
+                    const double dxf0 = -0.5 + ((ii + 0.5) / R0);
+                    g                 = g + dxf0 * dxf0 * m0 + dxf1 * dxf1 * m1 + dxf2 * dxf2 * m2;
+                }
+                f[ii] = g;
             }
-            if (order == 2) {
-                const double dxf0 = -0.5 + ((ii + 0.5) / R0);
-                g                 = g + dxf0 * dxf0 * m0 + dxf1 * dxf1 * m1 + dxf2 * dxf2 * m2;
-            }
-            f[ii] = g;
+            if (R0 == 2) *reinterpret_cast<double2*>(fine + qf) = make_double2(f[0], f[R0 - 1]);
+            else fine[qf] = f[0];
         }
-        if (R0 == 2) *reinterpret_cast<double2*>(fine + qf) = make_double2(f[0], f[R0 - 1]);
-        else fine[qf] = f[0];
     }
 }
 static void launch_prolong(cudaStream_t st, const Lay& Lf, const Lay& Lc, const int ref[3], double* fine, const double* crse, int order)
 {
     const bool fast = (ref[0] == 1 || ref[0] == 2) && (ref[1] == 1 || ref[1] == 2) && (ref[2] == 1 || ref[2] == 2) &&
-                      Lc.nx * ref[0] == Lf.nx && Lc.ny * ref[1] == Lf.ny;
+                      Lc.nx * ref[0] == Lf.nx && Lc.ny * ref[1] == Lf.ny && Lc.nz * ref[2] == Lf.nz;
     if (!fast) {
         prolong_k<<<grid3(Lf.nx, Lf.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[0], ref[1], ref[2], fine, crse, order);
     } else if (ref[0] == 2) {
-        prolong_c_k<2><<<grid3(Lc.nx, Lc.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[1], ref[2], fine, crse, order);
+        prolong_c_k<2><<<grid3(Lc.nx, Lc.ny, Lc.nz, B3), B3, 0, st>>>(Lf, Lc, ref[1], ref[2], fine, crse, order);
     } else {
-        prolong_c_k<1><<<grid3(Lc.nx, Lc.ny, Lf.nz, B3), B3, 0, st>>>(Lf, Lc, ref[1], ref[2], fine, crse, order);
+        prolong_c_k<1><<<grid3(Lc.nx, Lc.ny, Lc.nz, B3), B3, 0, st>>>(Lf, Lc, ref[1], ref[2], fine, crse, order);
     }
     LAUNCHED();
 }
