@@ -183,6 +183,14 @@ int sb_op_mg_prolong(sb_op* fine, sb_op* crse, sb_field* fine_phi, sb_field* crs
  * D directions of a LevelData<FluxBox>. */
 int sb_op_level_divergence(sb_op* op, sb_field* div, sb_field* const vel[3]);
 int sb_op_level_gradient(sb_op* op, sb_field* const grad[3], sb_field* phi, int homog);
+/* AMRNSLevel::sendToAdvectingVelocity / sendToCartesianVelocity (AMRNSLevelFill.cpp:194-280), in place on
+ * device-resident face fields: vel[d] *= (or /=) dx^mu/dXi^mu for the other directions mu = (d+1)%D, (d+2)%D
+ * in that order.  ghost = ghost width of the caller's LevelData<FluxBox> (the reference builds its 1-D
+ * tables from the grown FAB's small end, which shows in the last bits for stretched maps).  With these the
+ * velocity can stay on the device across toAdvecting -> levelDivergence -> solve -> levelGradient ->
+ * flux_incr -> toCartesian. */
+int sb_op_send_to_advecting_velocity(sb_op* op, sb_field* const vel[3], int ghost);
+int sb_op_send_to_cartesian_velocity(sb_op* op, sb_field* const vel[3], int ghost);
 /* vel[d] -= scale * grad[d]  (AMRNSLevelProject.cpp:331-336 with scale 1; :155-160 with projDt). */
 int sb_op_flux_incr(sb_op* op, sb_field* const vel[3], sb_field* const grad[3], double scale);
 

@@ -13,7 +13,7 @@
 // precision (the reference only prints 7 digits), and (d) reads / writes flat binary files.
 //
 // Usage: somar_ref <deck> [key=value ...]
-//   drv.mode  = solve | project | applyop | relax
+//   drv.mode  = solve | project | applyop | relax | transform | vcycle
 //   drv.map   = cartesian | stretched        drv.ampl = ax ay az (StretchedMap amplitudes)
 //   drv.in    = <file>    raw little-endian doubles, global Fortran order over the domain box:
 //                  solve:   rhs[nx*ny*nz]
@@ -326,6 +326,60 @@ main(int argc, char* argv[])
         g_norms.clear();
         out.kv("norm2", opPtr->norm(lhs, 2));
         out.kv("norm0", opPtr->norm(lhs, 0));
+        return 0;
+    }
+
+    if (mode == "transform") {
+        // AMRNSLevel::sendToAdvectingVelocity / sendToCartesianVelocity (Grade5_SOMAR/AMRNSLevelFill.cpp:
+        // 194-280) -- Grade5 is not part of this build, so the two loops are restated here around the
+        // reference's own GeoSourceInterface::fill_dxdXi and FArrayBox::mult / divide, statement for
+        // statement.  drv.velGhost = ghost width of the FluxBox (AMRNSLevel's velocity carries 1).
+        int velGhost = 1;
+        drv.query("velGhost", velGhost);
+        LevelData<FluxBox> vel(grids, 1, velGhost * IntVect::Unit);
+        size_t off = 0;
+        for (int d = 0; d < SpaceDim; ++d) {
+            const Box fcDom = surroundingNodes(domBox, d);
+            for (DataIterator dit(grids); dit.ok(); ++dit) {
+                vel[dit][d].setVal(0.0);
+                scatterFAB(vel[dit][d], grids[dit], in.data() + off, fcDom);
+            }
+            off += fcDom.numPts();
+        }
+        const GeoSourceInterface& geoSrc = levGeo.getGeoSource();
+        const RealVect&           dXi    = levGeo.getDXi();
+        auto dump = [&](const char* tag) {
+            for (int d = 0; d < SpaceDim; ++d) {
+                const Box           fcDom = surroundingNodes(domBox, d);
+                std::vector<double> v(fcDom.numPts(), 0.0);
+                for (DataIterator dit(grids); dit.ok(); ++dit) gatherFAB(v, vel[dit][d], grids[dit], fcDom);
+                out.put(std::string(tag) + char('0' + d), v);
+            }
+        };
+        for (DataIterator dit(grids); dit.ok(); ++dit) {
+            for (int fcDir = 0; fcDir < SpaceDim; ++fcDir) {
+                FArrayBox& velFAB = vel[dit][fcDir];
+                FArrayBox  dxdXiFAB(velFAB.box(), 1);
+                for (int offset = 1; offset < SpaceDim; ++offset) {
+                    const int mu = (fcDir + offset) % SpaceDim;
+                    geoSrc.fill_dxdXi(dxdXiFAB, 0, mu, dXi);
+                    velFAB.mult(dxdXiFAB, 0, 0, 1);
+                }
+            }
+        }
+        dump("adv");
+        for (DataIterator dit(grids); dit.ok(); ++dit) {
+            for (int fcDir = 0; fcDir < SpaceDim; ++fcDir) {
+                FArrayBox& velFAB = vel[dit][fcDir];
+                FArrayBox  dxdXiFAB(velFAB.box(), 1);
+                for (int offset = 1; offset < SpaceDim; ++offset) {
+                    const int mu = (fcDir + offset) % SpaceDim;
+                    geoSrc.fill_dxdXi(dxdXiFAB, 0, mu, dXi);
+                    velFAB.divide(dxdXiFAB, 0, 0, 1);
+                }
+            }
+        }
+        dump("cart");
         return 0;
     }
 

@@ -410,6 +410,14 @@ class PoissonOp:
     def levelGradient(self, grad, phi, homog=True):
         capi.check(self.lib.sb_op_level_gradient(self.h, self._f3(grad), phi.h, int(homog)))
 
+    def sendToAdvectingVelocity(self, vel, ghost=1):
+        """AMRNSLevel::sendToAdvectingVelocity (AMRNSLevelFill.cpp:194-232), in place on device face fields."""
+        capi.check(self.lib.sb_op_send_to_advecting_velocity(self.h, self._f3(vel), ghost))
+
+    def sendToCartesianVelocity(self, vel, ghost=1):
+        """AMRNSLevel::sendToCartesianVelocity (AMRNSLevelFill.cpp:238-280)."""
+        capi.check(self.lib.sb_op_send_to_cartesian_velocity(self.h, self._f3(vel), ghost))
+
     def fluxIncr(self, vel, grad, scale=1.0):
         capi.check(self.lib.sb_op_flux_incr(self.h, self._f3(vel), self._f3(grad), scale))
 

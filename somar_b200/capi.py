@@ -132,6 +132,8 @@ PROTOTYPES = {
     "sb_op_level_divergence": (C.c_int, [P, P, F3]),
     "sb_op_level_gradient": (C.c_int, [P, F3, P, C.c_int]),
     "sb_op_flux_incr": (C.c_int, [P, F3, F3, C.c_double]),
+    "sb_op_send_to_advecting_velocity": (C.c_int, [P, F3, C.c_int]),
+    "sb_op_send_to_cartesian_velocity": (C.c_int, [P, F3, C.c_int]),
     "sb_mg_default_options": (None, [C.POINTER(MGOptions)]),
     "sb_mg_quick_and_dirty_options": (None, [C.POINTER(MGOptions)]),
     "sb_mgsolver_create": (C.c_int, [P, C.POINTER(MGOptions), IP, C.c_int, PP]),

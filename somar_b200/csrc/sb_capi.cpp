@@ -373,6 +373,20 @@ int sb_op_level_gradient(sb_op* op, sb_field* const grad[3], sb_field* phi, int 
     OPF(op).levelGradient(g, D(phi), homog);
     SB_END
 }
+int sb_op_send_to_advecting_velocity(sb_op* op, sb_field* const vel[3], int ghost)
+{
+    SB_TRY sameOp(op, {});
+    double* v[3]; fluxPtrs(op, vel, v);
+    OPF(op).scaleVelocity(v, ghost, true);
+    SB_END
+}
+int sb_op_send_to_cartesian_velocity(sb_op* op, sb_field* const vel[3], int ghost)
+{
+    SB_TRY sameOp(op, {});
+    double* v[3]; fluxPtrs(op, vel, v);
+    OPF(op).scaleVelocity(v, ghost, false);
+    SB_END
+}
 int sb_op_flux_incr(sb_op* op, sb_field* const vel[3], sb_field* const grad[3], double scale)
 {
     SB_TRY sameOp(op, {});

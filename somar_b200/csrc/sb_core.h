@@ -214,6 +214,9 @@ void divergence(cudaStream_t st, const Lay& L, double* div, const double* u0, co
 void gradient(cudaStream_t st, const Lay& L, double* g, const double* phi, const double* Jgup, int dir, double oneOnDx,
               double beta, int scaleBeta);
 
+void scale_faces_box(cudaStream_t st, const Lay& L, const int blo[3], const int n[3], int mu1, int mu2, const double* t1,
+                     const double* t2, double* vel, bool divide);
+
 // Leptic solver leaves.  F is the layout of the flattened (one-layer) fields.
 // excess = hiBC - sum_k rhs*dz, k ascending (LevelLepticSolver.cpp:725-770, SubspaceF.ChF:33-58)
 void vert_excess(cudaStream_t st, const Lay& L, const Lay& F, double* excess, const double* hiBC, const double* rhs, double dzScale);

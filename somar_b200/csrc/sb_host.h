@@ -167,6 +167,8 @@ struct Op {
     bool   MGProlong(Op& crse, double* finePhi, double* crseCor, int order, bool deferKernel = false);  // returns removeKernel's
     void   levelDivergence(double* div, double* const vel[3]);
     void   levelGradient(double* const grad[3], double* phi, bool homog);
+    // AMRNSLevel::sendToAdvectingVelocity (toAdvecting) / sendToCartesianVelocity, AMRNSLevelFill.cpp:194-280
+    void   scaleVelocity(double* const vel[3], int ghost, bool toAdvecting);
     void   checkPivot();
     double* alloc() const;
 };

@@ -833,6 +833,35 @@ void fill_metric_box(cudaStream_t st, const Lay& L, const int blo[3], const int 
 }
 
 // ------------------------------------------------------------------------------------------
+// AMRNSLevel::sendToAdvectingVelocity / sendToCartesianVelocity (Grade5_SOMAR/AMRNSLevelFill.cpp:
+// 194-280): the faces of one box in direction `dir` are multiplied (divided) by dx/dXi of the other
+// directions, first mu = (dir + 1) % D, then (dir + 2) % D -- two FArrayBox::mult / divide calls in
+// the reference, two roundings here.  t1 / t2: cell-centred 1-D tables over the box in those two
+// directions (t2 null in 2-D).  n[]: faces handled in each direction (box-local, from blo).
+// ------------------------------------------------------------------------------------------
+__global__ void scale_faces_box_k(Lay L, int b0, int b1, int b2, int n0, int n1, int n2, int mu1, int mu2,
+                                  const double* __restrict__ t1, const double* __restrict__ t2, double* __restrict__ vel, int divide)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= n0 || j >= n1 || k >= n2) return;
+    const int       idx[3] = {i, j, k};
+    const long long q      = L.idx(b0 + i, b1 + j, b2 + k);
+    double          v      = vel[q];
+    if (divide) { v = v / t1[idx[mu1]]; if (t2) v = v / t2[idx[mu2]]; }
+    else { v = v * t1[idx[mu1]]; if (t2) v = v * t2[idx[mu2]]; }
+    vel[q] = v;
+}
+void scale_faces_box(cudaStream_t st, const Lay& L, const int blo[3], const int n[3], int mu1, int mu2, const double* t1,
+                     const double* t2, double* vel, bool divide)
+{
+    scale_faces_box_k<<<grid3(n[0], n[1], n[2], B3), B3, 0, st>>>(L, blo[0], blo[1], blo[2], n[0], n[1], n[2], mu1, mu2, t1, t2, vel,
+                                                                 divide ? 1 : 0);
+    LAUNCHED();
+}
+
+// ------------------------------------------------------------------------------------------
 // Leaves of the leptic solver (Elliptic/LevelLepticSolver.cpp).  One thread per column; the
 // vertical loops keep the reference's order, so the results agree operation for operation.
 // ------------------------------------------------------------------------------------------

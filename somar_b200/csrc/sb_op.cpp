@@ -952,6 +952,41 @@ void Op::levelDivergence(double* div, double* const vel[3])
     k::divergence(st(), lay, div, vel[0], vel[1], vel[2], m[0], m[1], m[2], dim);
 }
 
+// AMRNSLevel::sendToAdvectingVelocity / sendToCartesianVelocity (AMRNSLevelFill.cpp:194-280).  The
+// reference fills dx/dXi per FAB over velFAB.box() -- the box's faces grown by the FluxBox's ghost
+// width -- with xi accumulated from that small end (GeoSourceInterface.cpp:166-199), hence `ghost`.
+// A face shared by two boxes is scaled once, with the tables of the box it is the low face of.
+void Op::scaleVelocity(double* const vel[3], int ghost, bool toAdvecting)
+{
+    if (ghost < 0) SB_FAIL("ghost width must be >= 0");
+    for (int lb = 0; lb < nlocal(); ++lb) {
+        const Box3& b = boxes[local[lb]];
+        for (int d = 0; d < 3; ++d) {
+            if (dim == 2 && d == 1) continue;
+            // the other directions in the reference's order (fcDir + offset) % SpaceDim, mapped to slots
+            int mus[2], nmu = 0;
+            if (dim == 3) { mus[0] = (d + 1) % 3; mus[1] = (d + 2) % 3; nmu = 2; }
+            else { mus[0] = d == 0 ? 2 : 0; nmu = 1; }
+            std::vector<double> tab;
+            size_t              off[2] = {0, 0};
+            for (int m = 0; m < nmu; ++m) {
+                const int           mu = mus[m], n = b.size(mu);
+                std::vector<double> t  = map.dxdXi(mu, dXi[mu], b.lo[mu] - ghost, n + 2 * ghost, 0);
+                off[m] = tab.size();
+                tab.insert(tab.end(), t.begin() + ghost, t.begin() + ghost + n);
+            }
+            double* dt = (double*)ctx->getScratch(tab.size() * sizeof(double));
+            SB_CUDA(cudaMemcpyAsync(dt, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+            int blo[3], n[3];
+            for (int i = 0; i < 3; ++i) { blo[i] = b.lo[i] - tile.lo[i]; n[i] = b.size(i); }
+            if (b.hi[d] == tile.hi[d]) n[d] += 1;  // the tile's last face belongs to this box
+            k::scale_faces_box(st(), lay, blo, n, mus[0], nmu == 2 ? mus[1] : 0, dt + off[0], nmu == 2 ? dt + off[1] : nullptr, vel[d],
+                               !toAdvecting);
+            ctx->sync();  // scratch and tab are reused
+        }
+    }
+}
+
 // PoissonOp::levelGradient (PoissonOp.cpp:1486-1545)
 void Op::levelGradient(double* const grad[3], double* phi, bool homog)
 {

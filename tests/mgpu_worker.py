@@ -27,22 +27,36 @@ def main():
     dist.broadcast(idt, 0)
     ctx.init_comm(idt.cpu().numpy().tobytes())
 
-    if name in CASES:
-        c = CASES[name]
+    import test_parity2d_gpu as t2
+    from test_leptic_gpu import DJL_OPTS, LEPTIC2D, LEPTIC3D
+    two_d = name in t2.CASES2D or name in LEPTIC2D
+    if two_d:
+        # 2-D build of the reference: directions (x, z) in slots 0 and 2, ranks split x only
+        c = t2.CASES2D[name] if name in t2.CASES2D else LEPTIC2D[name][0]
+        nx, L, dXi, lo, hi = t2.geometry(c)
+        blo, bhi = sb.make_base_grids(lo, hi, (c["max_box"][0], 0, 0), (1, 0, 0), c["bf"])
+        ranks = sb.assign_boxes_to_ranks(blo, bhi, world)
+        xmin = lo * dXi
+        kind = sb.MAP_CARTESIAN if c["map"] == "cartesian" else sb.MAP_STRETCHED
+        op = sb.PoissonOp(ctx, lo, hi, dXi, blo, bhi, box_rank=ranks, periodic=(c["periodic"][0], 0, c["periodic"][1]), dim=2,
+                          map_kind=kind, map_xmin=xmin, map_xmax=xmin + L, map_ampl=(c["ampl"][0], 0.0, c["ampl"][1]),
+                          relax_method=c["relax"])
+        rhs0 = t2.up(t2.rand_field(c, 4, zero_mean=True))
     else:
-        from test_leptic_gpu import LEPTIC3D  # leptic / leptic-MG modes of the hybrid solver
-        c = LEPTIC3D[name][0]
-    nx, L, dXi, lo, hi = geometry(c)
-    blo, bhi = sb.make_base_grids(lo, hi, c["max_box"], (1, 1, 0), c["bf"])
-    ranks = sb.assign_boxes_to_ranks(blo, bhi, world)
-    xmin = lo * dXi
-    kind = sb.MAP_CARTESIAN if c["map"] == "cartesian" else sb.MAP_STRETCHED
-    op = sb.PoissonOp(ctx, lo, hi, dXi, blo, bhi, box_rank=ranks, periodic=c["periodic"], map_kind=kind, map_xmin=xmin,
-                      map_xmax=xmin + L, map_ampl=c["ampl"], relax_method=c["relax"])
+        c = CASES[name] if name in CASES else LEPTIC3D[name][0]
+        nx, L, dXi, lo, hi = geometry(c)
+        blo, bhi = sb.make_base_grids(lo, hi, c["max_box"], (1, 1, 0), c["bf"])
+        ranks = sb.assign_boxes_to_ranks(blo, bhi, world)
+        xmin = lo * dXi
+        kind = sb.MAP_CARTESIAN if c["map"] == "cartesian" else sb.MAP_STRETCHED
+        op = sb.PoissonOp(ctx, lo, hi, dXi, blo, bhi, box_rank=ranks, periodic=c["periodic"], map_kind=kind, map_xmin=xmin,
+                          map_xmax=xmin + L, map_ampl=c["ampl"], relax_method=c["relax"])
+        rhs0 = rand_field(c, 4, zero_mean=True)       # every rank builds the global field, uploads its part
     over = {} if optset == "defaults" else dict(numCycles=1, numSmoothDown=2, numSmoothUp=2, numSmoothBottom=2, prolongOrder=1,
                                                 maxIters=20, relTol=1e-10)
+    if name.startswith("c2_"):
+        over = dict(DJL_OPTS)
     solver = sb.LevelHybridSolver(op, sb.default_options(**over))
-    rhs0 = rand_field(c, 4, zero_mean=True)           # every rank builds the global field, uploads its part
     phi, rhs = op.field(), op.field()
     rhs.upload(rhs0)                                  # upload clips to this rank's tile (+ghosts)
     st = solver.solve(phi, rhs)

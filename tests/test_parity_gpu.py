@@ -119,3 +119,55 @@ def test_project(ctx, name):
     assert abs(n1 - ref.kv["finalDivNorm"]) <= 1e-6 * max(ref.kv["finalDivNorm"], 1e-30) + 1e-12 * n0
     solver.free()
     op.free()
+
+
+@pytest.mark.parametrize("name", ["line_stretch", "line_aniso", "gsrb_stretch", "line_cart"])
+@pytest.mark.parametrize("ghost", [0, 1])
+def test_velocity_transforms(ctx, name, ghost):
+    """AMRNSLevel::sendToAdvectingVelocity / sendToCartesianVelocity (AMRNSLevelFill.cpp:194-280) on
+    device-resident face fields, against the reference's GeoSourceInterface::fill_dxdXi +
+    FArrayBox::mult / divide (oracle driver, mode transform): same tables, same two roundings per
+    face, so the match is exact."""
+    c = CASES[name]
+    op = make_op(ctx, c)
+    vel0 = rand_velocity(c, 6)
+    ref = run_ref("transform", inp=vel0, extra={"drv.velGhost": ghost}, **ref_kwargs(c))
+    vel = [op.field(centering=d, data=vel0[d]) for d in range(3)]
+    op.sendToAdvectingVelocity(vel, ghost)
+    for d in range(3):
+        assert rel_err(vel[d].download(), ref[f"adv{d}"]) == 0.0
+    op.sendToCartesianVelocity(vel, ghost)
+    for d in range(3):
+        assert rel_err(vel[d].download(), ref[f"cart{d}"]) == 0.0
+    op.free()
+
+
+def test_device_resident_projection_chain(ctx):
+    """toAdvecting -> levelDivergence -> solve -> levelGradient -> vel -= grad -> toCartesian with every
+    field on the device gives bit for bit what sb_project_host computes from the
+    advecting velocity, followed by the back-transform."""
+    c = CASES["line_stretch"]
+    op = make_op(ctx, c)
+    cart0 = rand_velocity(c, 8)
+    solver = sb.LevelHybridSolver(op, sb.default_options())
+    vel = [op.field(centering=d, data=cart0[d]) for d in range(3)]
+    grad = [op.field(centering=d) for d in range(3)]
+    div, phi = op.field(), op.field()
+    op.sendToAdvectingVelocity(vel, 1)
+    adv0 = [v.download() for v in vel]
+    op.levelDivergence(div, vel)
+    solver.solve(phi, div)
+    op.levelGradient(grad, phi)
+    op.fluxIncr(vel, grad, 1.0)
+    adv1 = [v.download() for v in vel]
+    op.sendToCartesianVelocity(vel, 1)
+    velh, phih, n0, n1, st = solver.project_host(adv0)
+    for d in range(3):
+        assert np.array_equal(adv1[d], velh[d])
+    assert np.array_equal(phi.download(), phih)
+    chk = [op.field(centering=d, data=velh[d]) for d in range(3)]
+    op.sendToCartesianVelocity(chk, 1)
+    for d in range(3):
+        assert np.array_equal(vel[d].download(), chk[d].download())
+    solver.free()
+    op.free()
