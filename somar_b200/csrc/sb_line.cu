@@ -240,18 +240,20 @@ void pack_faces_split(cudaStream_t st, const SLay& S, double* s0, double* s1, do
 //    backward, correction), tab = [6][N]: s, a, P, g, c, Q.
 // ------------------------------------------------------------------------------------------
 // Launch shape (development knob SB_LINE_VARIANT, read once).
-struct LineVariant { int nw, u, minb, fused; };
+struct LineVariant { int nw, u, minb, fused, pers; };
 static LineVariant line_variant()
 {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SB_LINE_VARIANT"); v = e ? atoi(e) : 0; }
     switch (v) {
-        case 1: return {8, 4, 2, 0};
-        case 2: return {8, 2, 2, 1};
-        case 3: return {8, 8, 1, 1};
-        case 4: return {16, 4, 1, 1};
-        case 5: return {8, 4, 1, 1};
-        default: return {8, 4, 2, 1};  // measured best on B200 (profiles/r1_v4_summary.md)
+        case 1: return {8, 4, 2, 0, 0};
+        case 2: return {8, 2, 2, 1, 0};
+        case 3: return {8, 8, 1, 1, 0};
+        case 4: return {16, 4, 1, 1, 0};
+        case 5: return {8, 4, 1, 1, 0};
+        case 7: return {8, 4, 2, 2, 0};
+        case 8: return {8, 4, 2, 1, 1};   // persistent CTAs with cross-tile prefetch: measured slower (0.776 ms, see header of vertline_pers_k)
+        default: return {8, 4, 2, 1, 0};  // measured best on B200 (profiles/r1_v4_summary.md)
     }
 }
 int  vertline_split_chunk(int nz) { const int nw = line_variant().nw; return (nz + nw - 1) / nw; }
@@ -262,7 +264,7 @@ size_t vertline_split_smem(int nz)
     const LineVariant v = line_variant();
     return ((size_t)nz * 32 + 5 * (size_t)nz + 2 * (size_t)v.nw * 32 + 3 * (size_t)v.nw) * sizeof(double);
 }
-bool vertline_split_fits(int nz) { return vertline_split_smem(nz) <= 110 * 1024; }
+bool vertline_split_fits(int nz) { return vertline_split_smem(nz) <= 108 * 1024; }
 
 // ALIGNED: nz = NW * CL and CL a multiple of 2 U (true for the power-of-two depths of the bench
 // grid): no clamps or per-level predicates, 32-bit element offsets (one IMAD.WIDE per load).
@@ -413,6 +415,190 @@ __global__ void __launch_bounds__(NW * 32, MINB)
     }
 }
 
+// Persistent form of vertline_fused_k for aligned shapes (nz = NW * CL, CL a multiple of 2 U): a
+// CTA walks over tiles (32 columns of one row) with stride gridDim.x.  The tables are staged once per
+// CTA instead of once per tile, and the first 2 U levels of the NEXT tile are requested before the
+// barrier of the current one, so HBM requests stay in flight while the carries are resolved and the
+// backward sweep streams its results out (the load registers are idle in that phase anyway).  The
+// chunk summaries are double-buffered: the one barrier per tile bounds the skew between warps to
+// less than a tile.  Per-cell arithmetic is that of vertline_fused_k.
+// Measured on S5 (B200): 0.776 ms per pass against 0.709 ms for one CTA per tile, although the pure
+// access pattern (vertline_probe_k) runs in 0.557 ms (0.620 ms at the same residency of 2 CTAs per
+// SM): the persistent CTAs advance in lock-step, so the whole GPU alternates between a read phase
+// and a write phase, whereas CTAs that start and finish at scattered times mix the two.  Kept as
+// SB_LINE_VARIANT=8 for the next round (staggered start, or a read / write warp split).
+template <int NW, int U>
+__global__ void __launch_bounds__(NW * 32, 2)
+    vertline_pers_k(SLay S, const double* __restrict__ mx, const double* __restrict__ my, const double* __restrict__ tab,
+                    double* __restrict__ own, const double* __restrict__ oth, const double* __restrict__ rhs, int pass, int CL,
+                    int region, int nbMask, int nbx, int ntiles)
+{
+    extern __shared__ double sm[];
+    const int      N  = S.nz;
+    double* const  sy = sm;                         // [N][32] local forward sweep
+    double* const  cs = sm + (size_t)N * 32;        // [2 sets][cz, ca][NW][32]
+    double* const  ts = cs + 4 * NW * 32;           // tables
+    const double2* const T1 = reinterpret_cast<const double2*>(ts);          // {a', g}
+    const double2* const T2 = reinterpret_cast<const double2*>(ts + 2 * N);  // {P', c}
+    const double*  const tR = ts + 4 * N;
+    const double*  const tPend = ts + 5 * N;
+    const double*  const tT    = tPend + NW;
+    const double*  const tRend = tT + NW;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nby  = S.ny;
+    auto in_region = [&](int t) -> bool {
+        if (region == 0) return true;
+        const int  bx = t % nbx, j = t / nbx;
+        const bool edge = ((nbMask & 1) && bx == 0) || ((nbMask & 2) && bx == nbx - 1) || ((nbMask & 4) && j == 0) ||
+                          ((nbMask & 8) && j == nby - 1);
+        return edge == (region == 1);
+    };
+    int t = blockIdx.x;
+    while (t < ntiles && !in_region(t)) t += gridDim.x;
+    if (t >= ntiles) return;
+    for (int k = threadIdx.x; k < 5 * N + 3 * NW; k += NW * 32) ts[k] = tab[k];
+
+    const long long szl = S.sz;
+    const int       k0 = w * CL, k1 = k0 + CL;
+    // state of the tile whose loads are being issued
+    double        mxl, mxr, myl, myr;
+    bool          act;
+    long long     base;
+    const double *qw, *qs, *qn, *qr;
+    auto setup = [&](int tile) {
+        const int bx = tile % nbx, j = tile / nbx;
+        const int i0 = (pass + S.par + j) & 1;   // own cells of this row: i = 2 m + i0
+        const int m  = bx * 32 + lane;
+        act          = 2 * m + i0 < S.nx;
+        const int mm = act ? m : 0;              // idle lanes shadow column 0 and never store
+        const int ii = 2 * mm + i0;
+        mxl = mx[ii]; mxr = mx[S.nx + ii]; myl = my[j]; myr = my[S.ny + j];
+        base = (long long)(SOX + mm) + S.sy * (long long)(1 + j);
+        const long long o = base + (long long)k0 * szl;
+        qw = oth + o + (i0 - 1);  // west neighbour (east = qw[1])
+        qs = oth + o - S.sy;      // south
+        qn = oth + o + S.sy;      // north
+        qr = rhs + o;
+    };
+    double a0[U][5], a1[U][5];
+    auto issue = [&](double(&a)[U][5]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            a[u][0] = qw[0]; a[u][1] = qw[1]; a[u][2] = qs[0]; a[u][3] = qn[0]; a[u][4] = qr[0];
+            qw += szl; qs += szl; qn += szl; qr += szl;
+        }
+    };
+    setup(t);
+    issue(a0);
+    issue(a1);
+    __syncthreads();  // tables visible
+
+    int set = 0;
+    while (true) {
+        double* const cz = cs + set * (2 * NW * 32);
+        double* const ca = cz + NW * 32;
+        // P1: right-hand sides, local forward sweep in z, the chunk's contribution to its first unknown.
+        double zl = 0.0, acc = 0.0;
+        auto roll = [&](double(&a)[U][5], int kk, bool more) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int     k    = kk + u;
+                const double  lphi = fma(myr, a[u][3], fma(myl, a[u][2], fma(mxr, a[u][1], mxl * a[u][0])));
+                const double  b    = a[u][4] - lphi;
+                const double2 tt   = T1[k];
+                zl                 = fma(tt.x, zl, tt.y * b);
+                acc                = fma(tR[k], zl, acc);
+                sy[k * 32 + lane]  = zl;
+                if (more) {
+                    a[u][0] = qw[0]; a[u][1] = qw[1]; a[u][2] = qs[0]; a[u][3] = qn[0]; a[u][4] = qr[0];
+                    qw += szl; qs += szl; qn += szl; qr += szl;
+                }
+            }
+        };
+        for (int kk = k0; kk < k1; kk += 2 * U) {
+            const bool more = kk + 2 * U < k1;
+            roll(a0, kk, more);
+            roll(a1, kk + U, more);
+        }
+        cz[w * 32 + lane] = zl;
+        ca[w * 32 + lane] = acc;
+        // what the backward sweep of THIS tile needs
+        double*    po     = own + base + (long long)(k1 - 1) * szl;
+        const bool actCur = act;
+        // request the head of the next tile before waiting for the other warps
+        int tn = t + gridDim.x;
+        while (tn < ntiles && !in_region(tn)) tn += gridDim.x;
+        const bool hasNext = tn < ntiles;
+        if (hasNext) {
+            setup(tn);
+            issue(a0);
+            issue(a1);
+        }
+        __syncthreads();
+
+        // Carries.  Zs[v]: true z just below chunk v; X: true x just above this warp's chunk.
+        double Zs[NW];
+        double Z = 0.0, Zm = 0.0;
+#pragma unroll
+        for (int v = 0; v < NW; ++v) {
+            Zs[v] = Z;
+            if (v == w) Zm = Z;
+            Z = fma(tPend[v], Z, cz[v * 32 + lane]);
+        }
+        double X = 0.0;
+#pragma unroll
+        for (int v = NW - 1; v >= 1; --v)
+            if (v > w) X = fma(tRend[v], X, fma(Zs[v], tT[v], ca[v * 32 + lane]));
+
+        // P2: true backward sweep of this chunk, straight to HBM.
+        double xl = X;
+#pragma unroll 4
+        for (int k = k1 - 1; k >= k0; --k) {
+            const double2 tt = T2[k];
+            xl               = fma(tt.y, xl, fma(tt.x, Zm, sy[k * 32 + lane]));
+            if (actCur) *po = xl;
+            po -= szl;
+        }
+        if (!hasNext) break;
+        t = tn;
+        set ^= 1;
+    }
+}
+
+// Diagnostic only (SB_LINE_VARIANT=7, never used by the solver): the memory access pattern of
+// vertline_fused_k -- same five load streams per level, same chunking, same store -- without the
+// recurrences, shared memory or barriers.  Its time is the floor the access pattern allows.
+template <int NW, int U>
+__global__ void __launch_bounds__(NW * 32, 2)
+    vertline_probe_k(SLay S, double* __restrict__ own, const double* __restrict__ oth, const double* __restrict__ rhs, int pass, int CL)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int j    = blockIdx.y;
+    const int i0   = (pass + S.par + j) & 1;
+    const int m    = blockIdx.x * 32 + lane;
+    const bool act = 2 * m + i0 < S.nx;
+    const int  mm  = act ? m : 0;
+    const long long base = (long long)(SOX + mm) + S.sy * (long long)(1 + j);
+    const long long szl  = S.sz;
+    const int k0 = w * CL, k1 = min(S.nz, k0 + CL);
+    const double *qw = oth + base + (i0 - 1) + (long long)k0 * szl, *qs = oth + base - S.sy + (long long)k0 * szl,
+                 *qn = oth + base + S.sy + (long long)k0 * szl, *qr = rhs + base + (long long)k0 * szl;
+    double* po = own + base + (long long)k0 * szl;
+    for (int kk = k0; kk < k1; kk += U) {
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            v[u] = qw[0] + qw[1] + qs[0] + qn[0] + qr[0];
+            qw += szl; qs += szl; qn += szl; qr += szl;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (act) *po = v[u];
+            po += szl;
+        }
+    }
+}
+
 template <int NW, int U, int MINB, bool TG>
 __global__ void __launch_bounds__(NW * 32, MINB)
     vertline_split_k(SLay S, const double* __restrict__ mx, const double* __restrict__ my, const double* __restrict__ tab,
@@ -538,7 +724,25 @@ void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const do
     }
     if ((long long)S.sz * S.nz >= (1LL << 31)) SB_FAIL("colour-split field too large for 32-bit element offsets");
     const bool al = S.nz == v.nw * CL && CL % (2 * v.u) == 0;
-    if (!v.fused) SB_LAUNCH((vertline_split_k<8, 4, 2, false>))
+    if (v.fused == 1 && v.pers && al && v.nw == 8 && v.u == 4) {
+        static int    nsm = 0;
+        static size_t configured = 0;
+        if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+        const size_t shp = sh + 2 * (size_t)v.nw * 32 * sizeof(double);  // second set of chunk summaries
+        if (shp > configured) {
+            cudaFuncSetAttribute(vertline_pers_k<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shp);
+            configured = shp;
+        }
+        const int nbx = (int)g.x, ntiles = (int)(g.x * g.y);
+        const int grid = ntiles < 2 * nsm ? ntiles : 2 * nsm;
+        vertline_pers_k<8, 4><<<grid, 256, shp, st>>>(S, c.mxl, c.myl, tab, own, oth, rhs, pass, CL, region, nbMask, nbx, ntiles);
+    } else if (v.fused == 2) {  // access-pattern probe (diagnostic)
+        if (S.nz % (8 * 8) != 0) SB_FAIL("probe kernel needs nz to be a multiple of 64");
+        static const int psm = [] { const char* e = getenv("SB_PROBE_SMEM"); return e ? atoi(e) : 0; }();  // limits residency
+        static bool      set = false;
+        if (psm > 48 * 1024 && !set) { cudaFuncSetAttribute(vertline_probe_k<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm); set = true; }
+        vertline_probe_k<8, 8><<<g, 256, psm, st>>>(S, own, oth, rhs, pass, CL);
+    } else if (!v.fused) SB_LAUNCH((vertline_split_k<8, 4, 2, false>))
     else if (v.nw == 8 && v.u == 2 && al) SB_LAUNCH((vertline_fused_k<8, 2, 2, true>))
     else if (v.nw == 8 && v.u == 2) SB_LAUNCH((vertline_fused_k<8, 2, 2, false>))
     else if (v.nw == 8 && v.u == 8 && al) SB_LAUNCH((vertline_fused_k<8, 8, 1, true>))
