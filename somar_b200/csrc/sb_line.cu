@@ -424,9 +424,8 @@ __global__ void __launch_bounds__(NW * 32, MINB)
 // less than a tile.  Per-cell arithmetic is that of vertline_fused_k.
 // Measured on S5 (B200): 0.776 ms per pass against 0.709 ms for one CTA per tile, although the pure
 // access pattern (vertline_probe_k) runs in 0.557 ms (0.620 ms at the same residency of 2 CTAs per
-// SM): the persistent CTAs advance in lock-step, so the whole GPU alternates between a read phase
-// and a write phase, whereas CTAs that start and finish at scattered times mix the two.  Kept as
-// SB_LINE_VARIANT=8 for the next round (staggered start, or a read / write warp split).
+// SM).  Why it loses is not established: starting half of the CTAs 3-9 us late changes nothing, so
+// it is not lock-step between CTAs.  Kept as SB_LINE_VARIANT=8 for the next round.
 template <int NW, int U>
 __global__ void __launch_bounds__(NW * 32, 2)
     vertline_pers_k(SLay S, const double* __restrict__ mx, const double* __restrict__ my, const double* __restrict__ tab,
