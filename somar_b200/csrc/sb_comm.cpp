@@ -112,9 +112,10 @@ void Comm::exchangeFaces(Op& op, double* phi)
             if (op.side[d][s].kind == SIDE_NEIGHBOR) k::unpack_face(ctx->st, op.lay, phi, d, s, op.xbuf[d][s][1]);
 }
 
-void Comm::exchangeFacesSplit(Op& op, double* s0, double* s1, cudaStream_t st)
+void Comm::exchangeFacesSplit(Op& op, double* s0, double* s1, cudaStream_t st, const SLay* Sp)
 {
     if (!st) st = ctx->st;
+    const SLay& S = Sp ? *Sp : op.slay;
     double* snd[2][2];
     double* rcv[2][2];
     bool    any = false;
@@ -126,7 +127,7 @@ void Comm::exchangeFacesSplit(Op& op, double* s0, double* s1, cudaStream_t st)
             any = any || nb;
         }
     if (!any) return;
-    k::pack_faces_split(st, op.slay, s0, s1, snd, false);
+    k::pack_faces_split(st, S, s0, s1, snd, false);
     SB_NCCL(api().GroupStart());
     for (int d = 0; d < 2; ++d) {
         const size_t n = (size_t)(d == 0 ? op.lay.ny : op.lay.nx) * op.lay.nz;
@@ -136,7 +137,7 @@ void Comm::exchangeFacesSplit(Op& op, double* s0, double* s1, cudaStream_t st)
             if (rcv[d][s]) SB_NCCL(api().Recv(rcv[d][s], n, kNcclFloat64, op.side[d][s].neighbor, comm, st));
     }
     SB_NCCL(api().GroupEnd());
-    k::pack_faces_split(st, op.slay, s0, s1, rcv, true);
+    k::pack_faces_split(st, S, s0, s1, rcv, true);
 }
 
 // One direction only, optionally extended over the ghosts of the other directions.

@@ -17,7 +17,7 @@ struct Comm {
     void allreduceHost(double* v, int n, bool isMax);
     void exchangeFaces(Op& op, double* phi);
     void exchangeDir(Op& op, double* phi, int dir, int ext0, int ext1);
-    void exchangeFacesSplit(Op& op, double* s0, double* s1, cudaStream_t st = nullptr);  // same, on colour-split storage (x and y sides); st: default ctx->st
+    void exchangeFacesSplit(Op& op, double* s0, double* s1, cudaStream_t st = nullptr, const SLay* S = nullptr);  // same, on colour-split storage (x and y sides); st: default ctx->st; S: default op.slay
     // Agglomeration: the tiles of `dist` (every rank) <-> one array over the whole domain on rank 0
     // (layout `full`, meaningful on rank 0 only).  buf: staging, sum over ranks of tile sizes on
     // rank 0, one tile elsewhere.  centering: SB_CELL or the face direction.

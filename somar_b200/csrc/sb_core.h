@@ -91,25 +91,29 @@ constexpr int SOX = 4;
 struct SLay {
     int nx, ny, nz;
     int par;           // (lo0 + lo1) & 1
+    int lo2p;          // lo2 & 1 (point red-black colours also count k)
+    int zg;            // ghost layers in z: 0 for the line relaxation, 1 for point GSRB
     int px, py;        // allocated extents of one colour array
     long long sy, sz;  // strides (elements)
     long long n;       // elements of one colour array
     __host__ __device__ long long idx(int i, int j, int k) const
     {
-        return (long long)(SOX + (i >> 1)) + sy * (long long)(1 + j) + sz * (long long)k;
+        return (long long)(SOX + (i >> 1)) + sy * (long long)(1 + j) + sz * (long long)(k + zg);
     }
     __host__ __device__ int colour(int i, int j) const { return (par + i + j) & 1; }
 };
-inline SLay makeSLay(const Lay& L)
+inline SLay makeSLay(const Lay& L, int zg = 0)
 {
     SLay S;
     S.nx = L.nx; S.ny = L.ny; S.nz = L.nz;
     S.par = (L.lo0 + L.lo1) & 1;
+    S.lo2p = L.lo2 & 1;
+    S.zg = zg;
     S.px = ((SOX + (L.nx + 1) / 2 + 2 + 3) / 4) * 4;
     S.py = L.ny + 2;
     S.sy = S.px;
     S.sz = (long long)S.px * S.py;
-    S.n  = S.sz * L.nz;
+    S.n  = S.sz * (L.nz + 2 * zg);
     return S;
 }
 
@@ -186,6 +190,12 @@ void split_precond(cudaStream_t st, const Lay& L, const SLay& S, const double* r
                    double* c0, double* c1, double* r0, double* r1);
 void unsplit_field(cudaStream_t st, const Lay& L, const SLay& S, double* nat, const double* s0, const double* s1);
 void fill_ghosts_split(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC bc[3][2], int dim, bool physToo);
+// vertical sides of a split field with z ghosts (S.zg = 1): Robin / periodic, as fill_ghosts_dir_k
+void fill_ghosts_split_z(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC& lo, const SideBC& hi, bool physToo);
+// one colour of point red-black Gauss-Seidel on split storage (PoissonOpF.ChF:420-474); p / r / J / Dinv: the two
+// colour arrays of phi, rhs, J and Dinv
+void gsrb_split_pass(cudaStream_t st, const SLay& S, const Coef& c, double* const p[2], const double* const r[2],
+                     const double* const J[2], const double* const Di[2], int pass);
 void pack_faces_split(cudaStream_t st, const SLay& S, double* s0, double* s1, double* const bufs[2][2], bool unpack);
 void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const double* tab, double* own, const double* oth,
                          const double* rhs, int pass, int region = 0, int nbMask = 0);

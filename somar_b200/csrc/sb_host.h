@@ -114,6 +114,12 @@ struct Op {
     bool    lineSplit = false;
     double* sp[4] = {nullptr, nullptr, nullptr, nullptr};
     const double* splitResSrc = nullptr;  // natural-layout field whose split copy sp[2], sp[3] hold
+    // point GSRB on colour-split storage with z ghosts (sb_line.cu: gsrb_split_k): cor, rhs, J, Dinv x 2 colours
+    SLay    slayG;
+    double* sg[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool    gsrbCoefSplit = false;            // sg[4..7] hold the current J / Dinv
+    const double* splitResSrcG = nullptr;
+    void   relaxGsrbSplit(double* cor, const double* res, int iters, bool resUnchanged, bool shift);
     // The pass loop of a line relaxation on a small depth is launch-latency bound (two tiny kernels
     // per colour pass): captured once per iteration count into a CUDA graph and replayed.
     struct RelaxGraph { cudaGraphExec_t exec = nullptr; long long kernels = 0; };

@@ -190,6 +190,99 @@ void fill_ghosts_split(cudaStream_t st, const SLay& S, double* s0, double* s1, c
     note_launch();
 }
 
+// Vertical sides (split storage with z ghosts): same formulas as fill_ghosts_dir_k.
+__global__ void fill_ghosts_split_z_k(SLay S, double* s0, double* s1, SideBC lo, SideBC hi, int physToo)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= S.nx || j >= S.ny) return;
+    double* a = S.colour(i, j) ? s1 : s0;
+    for (int side = 0; side < 2; ++side) {
+        const SideBC& bc = side ? hi : lo;
+        const int g = side ? S.nz : -1, p0 = side ? S.nz - 1 : 0, p1 = side ? S.nz - 2 : 1, wv = side ? 0 : S.nz - 1;
+        if (bc.kind == SIDE_PHYS) {
+            if (!physToo) continue;
+            double v;
+            if (bc.twoCells) {
+                const double cg = 3.0 * bc.a + bc.bb;
+                const double c0 = 6.0 * bc.a - bc.bb;
+                const double c1 = -1.0 * bc.a;
+                v = -(c0 * a[S.idx(i, j, p0)] + c1 * a[S.idx(i, j, p1)]) / cg;
+            } else {
+                const double cg = bc.a + bc.bb;
+                const double c0 = bc.a - bc.bb;
+                v = -(c0 * a[S.idx(i, j, p0)]) / cg;
+            }
+            a[S.idx(i, j, g)] = v;
+        } else if (bc.kind == SIDE_PERIODIC_SELF) {
+            a[S.idx(i, j, g)] = a[S.idx(i, j, wv)];
+        }
+    }
+}
+void fill_ghosts_split_z(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC& lo, const SideBC& hi, bool physToo)
+{
+    auto idle = [&](const SideBC& b) { return b.kind == SIDE_NEIGHBOR || b.kind < 0 || (b.kind == SIDE_PHYS && !physToo); };
+    if (S.zg == 0 || (idle(lo) && idle(hi))) return;
+    const dim3 b(64, 4, 1);
+    fill_ghosts_split_z_k<<<dim3((S.nx + 63) / 64, (S.ny + 3) / 4), b, 0, st>>>(S, s0, s1, lo, hi, physToo ? 1 : 0);
+    note_launch();
+}
+
+// Point red-black Gauss-Seidel on split storage.  The cells of one pass, (i + j + k + pass) even in
+// global indices, lie at level k in the colour array a = (pass + k + lo2) & 1; their horizontal
+// neighbours are in the other array at the same level, their vertical neighbours in the same array at
+// k -+ 1.  Every access is unit-stride, and only what the pass needs moves: 20 B per grid cell per
+// pass against 40 B in the natural layout (where every sector brings the other colour along).
+// Same expression as gsrb_k / stencil7, so the result is bit-identical.
+// Two adjacent cells of the pass per thread (16-byte accesses; the east neighbour of the first is the
+// west neighbour of the second); the arrays of the level are picked once per CTA.
+__global__ void gsrb_split_k(SLay S, Coef c, double* __restrict__ p0, double* __restrict__ p1, const double* __restrict__ r0,
+                             const double* __restrict__ r1, const double* __restrict__ J0, const double* __restrict__ J1,
+                             const double* __restrict__ D0, const double* __restrict__ D1, int pass)
+{
+    const int m = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    const int a  = (pass + k + S.lo2p) & 1;             // array of the cells being updated at this level
+    const int i0 = (a + S.par + j) & 1;                 // colour(i, j) == a  <=>  i = 2 m + i0
+    const int i  = 2 * m + i0;
+    if (i >= S.nx || j >= S.ny) return;
+    double* const       own = a ? p1 : p0;
+    const double* const oth = a ? p0 : p1;
+    const double* const rr  = a ? r1 : r0;
+    const double* const JJ  = a ? J1 : J0;
+    const double* const DD  = a ? D1 : D0;
+    const long long q  = S.idx(i, j, k);                // element SOX + m of the row: 16-byte aligned
+    const bool      two = i + 2 < S.nx;
+    const double mzl = c.mzl[k], mzr = c.mzr[k], myl = c.myl[j], myr = c.myr[j], beta = c.beta;
+    const double2 dn = *reinterpret_cast<const double2*>(own + q - S.sz), up = *reinterpret_cast<const double2*>(own + q + S.sz);
+    const double2 so = *reinterpret_cast<const double2*>(oth + q - S.sy), no = *reinterpret_cast<const double2*>(oth + q + S.sy);
+    const double2 rv = *reinterpret_cast<const double2*>(rr + q), Jv = *reinterpret_cast<const double2*>(JJ + q),
+                  Dv = *reinterpret_cast<const double2*>(DD + q);
+    // horizontal neighbours in the other array: elements m + i0 - 1, m + i0, m + i0 + 1
+    double w0, e0, e1;
+    if (i0) { const double2 t = *reinterpret_cast<const double2*>(oth + q); w0 = t.x; e0 = t.y; e1 = oth[q + 2]; }
+    else { const double2 t = *reinterpret_cast<const double2*>(oth + q); w0 = oth[q - 1]; e0 = t.x; e1 = t.y; }
+    double s = c.mxl[i] * w0 + c.mxr[i] * e0 + myl * so.x + myr * no.x;
+    s        = s + mzl * dn.x + mzr * up.x;
+    const double x0 = (rv.x - beta * Jv.x * s) * Dv.x;
+    if (two) {
+        double s2 = c.mxl[i + 2] * e0 + c.mxr[i + 2] * e1 + myl * so.y + myr * no.y;
+        s2        = s2 + mzl * dn.y + mzr * up.y;
+        const double x1 = (rv.y - beta * Jv.y * s2) * Dv.y;
+        *reinterpret_cast<double2*>(own + q) = make_double2(x0, x1);
+    } else own[q] = x0;
+}
+void gsrb_split_pass(cudaStream_t st, const SLay& S, const Coef& c, double* const p[2], const double* const r[2],
+                     const double* const J[2], const double* const Di[2], int pass)
+{
+    const dim3 b(64, 4, 1);
+    const int  pairs = ((S.nx + 1) / 2 + 1) / 2;
+    gsrb_split_k<<<dim3((pairs + 63) / 64, (S.ny + 3) / 4, S.nz), b, 0, st>>>(S, c, p[0], p[1], r[0], r[1], J[0], J[1], Di[0], Di[1],
+                                                                            pass);
+    note_launch();
+}
+
 // Face layer pack / unpack for the neighbour exchange on split storage; buffer order as
 // pack_face_k: (tangential index, k), tangential = j for dir 0, i for dir 1.
 struct FaceBufs { double* b[2][2]; };  // [dir][side], null = side not exchanged

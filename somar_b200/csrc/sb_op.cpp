@@ -292,6 +292,7 @@ Op::~Op()
     for (int i = 0; i < 3; ++i) cudaFree(Jgup[i]);
     cudaFree(lineTab); cudaFree(lineTabS);
     for (double* q : sp) cudaFree(q);
+    for (double* q : sg) cudaFree(q);
     for (auto& kv : relaxGraphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     cudaFree(mtab); cudaFree(loBC); cudaFree(hiBC); cudaFree(boxLoHi); cudaFree(redPartial); cudaFree(redOut); cudaFree(shiftBuf); cudaFree(pivotFlag);
     for (int d = 0; d < 3; ++d)
@@ -430,6 +431,7 @@ void Op::cacheMatrixElements()
 
     if (!Dinv) Dinv = alloc();
     k::compute_dinv(st(), lay, coef(), alpha, Dinv, dim);
+    gsrbCoefSplit = false;
 
     // Physical-boundary ghost-fill constants (BCTools.cpp:466-508: dx = dx/dXi * dXi at the
     // boundary face; BCToolsF.ChF:222-337).
@@ -772,6 +774,48 @@ void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUncha
     ctx->profEnd("linesplit_convert", depth, e0);
 }
 
+// Point GSRB on colour-split storage (gsrb_split_k): convert once, iterate, convert back.  Call
+// order of PoissonOp::gsrb_relax (PoissonOp.cpp:1833-1870): applyBCs (physical + exchange ghosts)
+// before the first colour, exchange only before the second.
+void Op::relaxGsrbSplit(double* cor, const double* res, int iters, bool resUnchanged, bool shift)
+{
+    if (!sg[0]) {
+        slayG = makeSLay(lay, 1);
+        for (double*& q : sg) {
+            SB_CUDA(cudaMalloc((void**)&q, slayG.n * sizeof(double)));
+            SB_CUDA(cudaMemsetAsync(q, 0, slayG.n * sizeof(double), ctx->st));
+        }
+        splitResSrcG  = nullptr;
+        gsrbCoefSplit = false;
+    }
+    if (!gsrbCoefSplit) {
+        k::split_field(st(), lay, slayG, J, sg[4], sg[5], nullptr);
+        k::split_field(st(), lay, slayG, Dinv, sg[6], sg[7], nullptr);
+        gsrbCoefSplit = true;
+    }
+    if (!(resUnchanged && splitResSrcG == res)) {
+        k::split_field(st(), lay, slayG, res, sg[2], sg[3], nullptr);
+        splitResSrcG = res;
+    }
+    k::split_field(st(), lay, slayG, cor, sg[0], sg[1], nullptr, shift ? shiftBuf : nullptr);
+    double* const       p[2] = {sg[0], sg[1]};
+    const double* const r[2] = {sg[2], sg[3]};
+    const double* const Jc[2] = {sg[4], sg[5]};
+    const double* const Dc[2] = {sg[6], sg[7]};
+    cudaEvent_t e0;
+    for (int it = 0; it < iters; ++it)
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool physToo = pass == 0;
+            k::fill_ghosts_split(st(), slayG, sg[0], sg[1], side, dim, physToo);
+            k::fill_ghosts_split_z(st(), slayG, sg[0], sg[1], side[2][0], side[2][1], physToo);
+            if (ctx->nranks > 1) ctx->comm->exchangeFacesSplit(*this, sg[0], sg[1], nullptr, &slayG);
+            ctx->profBegin("gsrb", depth, &e0);
+            k::gsrb_split_pass(st(), slayG, coef(), p, r, Jc, Dc, pass);
+            ctx->profEnd("gsrb", depth, e0);
+        }
+    k::unsplit_field(st(), lay, slayG, cor, sg[0], sg[1]);
+}
+
 void Op::linePasses(int iters)
 {
     for (int it = 0; it < iters; ++it)
@@ -783,11 +827,15 @@ void Op::linePasses(int iters)
 
 void Op::relax(double* cor, const double* res, int iters, bool resUnchanged, int pre)
 {
+    const char* const gk          = getenv("SB_GSRB_KERNEL");  // "natural" keeps point GSRB on the natural layout (tests)
+    const bool        gsrbNatural = gk && std::string(gk) == "natural";
+    const bool gsrbSplit = relaxMethod == SB_RELAX_GSRB && iters >= 2 && !gsrbNatural;
     if (pre != RELAX_PRE_NONE) {
         if (relaxMethod == SB_RELAX_VERTLINE && lineSplit && iters >= 2) { relaxLineSplit(cor, res, iters, resUnchanged, pre); return; }
         if (pre == RELAX_PRE_PRECOND) k::mult_valid(st(), lay, cor, res, Dinv);
-        else k::add_scalar_valid(st(), lay, cor, shiftBuf);
+        else if (!gsrbSplit) k::add_scalar_valid(st(), lay, cor, shiftBuf);
     }
+    if (gsrbSplit) { relaxGsrbSplit(cor, res, iters, resUnchanged, pre == RELAX_PRE_SHIFT); return; }
     switch (relaxMethod) {
         case SB_RELAX_NONE: break;
         case SB_RELAX_GSRB:  // PoissonOp.cpp:1833-1870
