@@ -38,6 +38,7 @@
 #include "FluxBox.H"
 #include "LevelData.H"
 #include "LevelGeometry.H"
+#include "AMRHybridSolver.H"
 #include "LevelHybridSolver.H"
 #include "MGSolver.H"
 #include "ParmParse.H"
@@ -270,6 +271,7 @@ main(int argc, char* argv[])
     OutFile out(outPrefix);
     out.kv("spacedim", SpaceDim);
     out.kv("numBoxes", boxes.size());
+
     {
         LayoutIterator lit = grids.layoutIterator();
         int            n   = 0;
@@ -316,6 +318,126 @@ main(int argc, char* argv[])
         fclose(f);
     }
     const size_t N = domBox.numPts();
+
+    if (mode == "amr") {
+        // Two-level composite solve: AMRHybridSolver over the base level and one
+        // refined patch, set up the way AMRNSLevel::validateOpsAndSolvers does
+        // (Grade5_SOMAR/AMRNSLevelInit.cpp:617-676).
+        //   drv.refRatio   = r0 r1 [r2]          refinement ratio of level 1
+        //   drv.fineRegion = lo... hi...          coarse-index box that level 1 covers
+        //   drv.fineMaxBox = n                     level-1 boxes are cut to at most n cells per direction (0: one box)
+        //   drv.in: rhs on level 0 over the domain box, then rhs on level 1 over refine(fineRegion)
+        Vector<int> vr(SpaceDim, 2), vreg;
+        drv.queryarr("refRatio", vr, 0, SpaceDim);
+        drv.getarr("fineRegion", vreg, 0, 2 * SpaceDim);
+        int fineMaxBox = 0;
+        drv.query("fineMaxBox", fineMaxBox);
+        const IntVect ref(D_DECL(vr[0], vr[1], vr[2]));
+        const Box     crseRegion(IntVect(D_DECL(vreg[0], vreg[1], vreg[2])),
+                                 IntVect(D_DECL(vreg[SpaceDim], vreg[SpaceDim + 1], vreg[SpaceDim + 2])));
+        if (!domBox.contains(crseRegion)) MayDay::Error("drv.fineRegion must lie inside the domain");
+        ProblemDomain fineDomain = domain;
+        fineDomain.refine(ref);
+        const Box   fineRegion = refine(crseRegion, ref);
+        Vector<Box> fineBoxes;
+        {
+            IntVect nb, sz;
+            for (int d = 0; d < SpaceDim; ++d) {
+                const int n = fineRegion.size(d);
+                nb[d]       = (fineMaxBox > 0) ? (n + fineMaxBox - 1) / fineMaxBox : 1;
+                if (n % nb[d]) MayDay::Error("drv.fineMaxBox must divide the refined region evenly");
+                sz[d] = n / nb[d];
+            }
+            for (BoxIterator bit(Box(IntVect::Zero, nb - IntVect::Unit)); bit.ok(); ++bit) {
+                const IntVect lo = fineRegion.smallEnd() + bit() * sz;
+                fineBoxes.push_back(Box(lo, lo + sz - IntVect::Unit));
+            }
+        }
+        DisjointBoxLayout fineGrids;
+        fineGrids.defineAndLoadBalance(fineBoxes, nullptr, fineDomain);
+
+        LevelGeometry fineLevGeo(fineDomain, L, &levGeo, geoPtr);
+        fineLevGeo.createMetricCache(fineGrids);
+
+        using OpType = Elliptic::AMRMGOperator<LDFAB>;
+        Vector<std::shared_ptr<const OpType>> vOps(2);
+        vOps[0].reset(new PoissonOp(levGeo, fineGrids, DisjointBoxLayout(), 1, bcPtr));
+        vOps[1].reset(new PoissonOp(fineLevGeo, DisjointBoxLayout(), grids, 1, bcPtr));
+
+        int cfOnly = 0;
+        drv.query("cfInterpOnly", cfOnly);
+        if (cfOnly) {
+            // Known-answer hook for the coarse-fine ghost interpolation (PoissonOp::applyBCs with a coarse
+            // level -> CFInterp::interpAtCFI -> MappedQuadCFInterp): drv.in = phi on level 0 over the domain,
+            // then phi on level 1 over refine(fineRegion); output = level-1 phi with its ghost layer.
+            LDFAB c(grids, 1, IntVect::Unit), f(fineGrids, 1, IntVect::Unit);
+            const size_t n0 = domBox.numPts(), n1 = fineRegion.numPts();
+            if (in.size() < n0 + n1) MayDay::Error("drv.in too short");
+            for (DataIterator dit(grids); dit.ok(); ++dit) c[dit].setVal(0.0);
+            for (DataIterator dit(fineGrids); dit.ok(); ++dit) f[dit].setVal(0.0);
+            scatter(c, in.data(), domBox);
+            scatter(f, in.data() + n0, fineRegion);
+            vOps[1]->applyBCs(f, &c, 0.0, true, false);
+            Box gb = fineRegion;
+            gb.grow(1);
+            std::vector<double> v(gb.numPts(), 0.0);
+            // face ghosts only (edge and corner ghosts are not filled by the CF interpolation)
+            for (DataIterator dit(fineGrids); dit.ok(); ++dit)
+                for (int d = 0; d < SpaceDim; ++d) {
+                    Box b = fineGrids[dit];
+                    b.grow(d, 1);
+                    gatherFAB(v, f[dit], b, gb);
+                }
+            // valid data last, so that a ghost of one box never hides the valid value of its neighbour
+            for (DataIterator dit(fineGrids); dit.ok(); ++dit) gatherFAB(v, f[dit], fineGrids[dit], gb);
+            out.put("fineWithGhosts", v);
+            return 0;
+        }
+        Elliptic::AMRHybridSolver amr;
+        amr.define(vOps, 0, 1, Elliptic::AMRHybridSolver::getDefaultOptions());
+
+        LDFAB phi0(grids, 1, IntVect::Unit), rhs0(grids, 1), phi1(fineGrids, 1, IntVect::Unit), rhs1(fineGrids, 1);
+        const size_t N0 = domBox.numPts(), N1 = fineRegion.numPts();
+        if (in.size() < N0 + N1) MayDay::Error("drv.in too short for the two-level right-hand side");
+        scatter(rhs0, in.data(), domBox);
+        scatter(rhs1, in.data() + N0, fineRegion);
+        for (DataIterator dit(grids); dit.ok(); ++dit) phi0[dit].setVal(0.0);
+        for (DataIterator dit(fineGrids); dit.ok(); ++dit) phi1[dit].setVal(0.0);
+        Vector<LDFAB*>       vphi(2);
+        Vector<const LDFAB*> vrhs(2);
+        vphi[0] = &phi0; vphi[1] = &phi1; vrhs[0] = &rhs0; vrhs[1] = &rhs1;
+        const auto t0 = std::chrono::high_resolution_clock::now();
+        Elliptic::SolverStatus st = amr.solve(vphi, vrhs, 0.0, true, true);
+        const auto t1 = std::chrono::high_resolution_clock::now();
+        out.put("phi0", gather(phi0, domBox));
+        out.put("phi1", gather(phi1, fineRegion));
+        // Composite residual through the operators' public AMR interface (AMRMGOperator.H:137-175), before
+        // (phi = 0) and after the solve, and its composite norm (AMRNormLevel, PoissonOp.cpp:1215-1260):
+        // an evaluation that does not go through AMRHybridSolver's own bookkeeping.
+        {
+            LDFAB res0(grids, 1), res1(fineGrids, 1), z0(grids, 1, IntVect::Unit), z1(fineGrids, 1, IntVect::Unit);
+            for (DataIterator dit(grids); dit.ok(); ++dit) z0[dit].setVal(0.0);
+            for (DataIterator dit(fineGrids); dit.ok(); ++dit) z1[dit].setVal(0.0);
+            auto compNorm = [&](LDFAB& f1, LDFAB& f0, const char* tag) {
+                vOps[1]->AMRResidualNF(res1, f1, f0, rhs1, ref, 0.0, true);
+                vOps[0]->AMRResidualNC(res0, f1, f0, rhs0, ref, 0.0, true, *vOps[1]);
+                const Real n1 = vOps[1]->AMRNormLevel(res1, nullptr, IntVect::Unit, ctx->proj.normType);
+                const Real n0 = vOps[0]->AMRNormLevel(res0, &res1, ref, ctx->proj.normType);
+                out.kv(std::string(tag) + "Norm0", n0);
+                out.kv(std::string(tag) + "Norm1", n1);
+                out.put(std::string(tag) + "0", gather(res0, domBox));
+                out.put(std::string(tag) + "1", gather(res1, fineRegion));
+            };
+            compNorm(z1, z0, "res_init");
+            compNorm(phi1, phi0, "res_final");
+        }
+        out.kv("status", st.getSolverStatus());
+        out.kv("initResNorm", st.getInitResNorm());
+        out.kv("finalResNorm", st.getFinalResNorm());
+        out.kv("solveTime", std::chrono::duration<double>(t1 - t0).count());
+        out.kv("numFineBoxes", fineBoxes.size());
+        return 0;
+    }
 
     if (mode == "applyop") {
         LDFAB phi(grids, 1, IntVect::Unit), lhs(grids, 1);
