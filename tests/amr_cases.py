@@ -16,12 +16,31 @@ AMR_CASES = {
 }
 
 
+DJL_L = 724.07734393502466498646462679537
+AMR_CASES.update({
+    # 2-D build (CH_SPACEDIM = 2; directions x, z).  The DJL deck's base level with a vertically spanning patch at
+    # the deck's two refinement ratios: the level solves inside AMRHybridSolver run in the leptic modes.
+    "amr2d_djl_r22": dict(nx=(128, 32), L=(DJL_L, 1.0), offset=(0, -32), max_box=(32, 0), bf=16, periodic=(0, 0), relax=6,
+                          ref=(2, 2), region=(32, -32, 95, -1), fine_max_box=128, split=(1, 0)),
+    "amr2d_djl_r41": dict(nx=(128, 32), L=(DJL_L, 1.0), offset=(0, -32), max_box=(32, 0), bf=16, periodic=(0, 0), relax=6,
+                          ref=(4, 1), region=(32, -32, 95, -1), fine_max_box=128, split=(1, 0)),
+    "amr2d_r2_centre": dict(nx=(64, 32), L=(4.0, 1.0), offset=(0, -32), max_box=(32, 0), bf=8, periodic=(0, 0), relax=5,
+                            ref=(2, 2), region=(16, -24, 47, -9), fine_max_box=32, split=(1, 1)),
+})
+
+
+def ndim(c):
+    return len(c["nx"])
+
+
 def fine_shape(c):
-    return tuple((c["region"][3 + d] - c["region"][d] + 1) * c["ref"][d] for d in range(3))
+    D = ndim(c)
+    return tuple((c["region"][D + d] - c["region"][d] + 1) * c["ref"][d] for d in range(D))
 
 
 def region_slices(c):
-    return tuple(slice(c["region"][d] - c["offset"][d], c["region"][3 + d] - c["offset"][d] + 1) for d in range(3))
+    D = ndim(c)
+    return tuple(slice(c["region"][d] - c["offset"][d], c["region"][D + d] - c["offset"][d] + 1) for d in range(D))
 
 
 def composite_rhs(c, seed):
@@ -34,7 +53,8 @@ def composite_rhs(c, seed):
     nf = fine_shape(c)
     r1 = rng.standard_normal(nf)
     sl = region_slices(c)
-    r0[sl] = r1.reshape(nf[0] // ref[0], ref[0], nf[1] // ref[1], ref[1], nf[2] // ref[2], ref[2]).mean(axis=(1, 3, 5))
+    shape = [v for d in range(ndim(c)) for v in (nf[d] // ref[d], ref[d])]
+    r0[sl] = r1.reshape(shape).mean(axis=tuple(range(1, 2 * ndim(c), 2)))
     mask = np.ones(nx, bool)
     mask[sl] = False
     total = r0[mask].sum() + r1.sum() / np.prod(ref)   # in units of the coarse cell volume
@@ -44,7 +64,7 @@ def composite_rhs(c, seed):
 
 def ref_kwargs_amr(c, **extra):
     kw = dict(nx=c["nx"], L=c["L"], max_box=c["max_box"], block_factor=c["bf"], offset=c["offset"], periodic=c["periodic"],
-              relax=c["relax"], split_dirs=(1, 1, 1),
+              relax=c["relax"], split_dirs=c.get("split", (1, 1, 1)), dim=ndim(c),
               extra={"drv.refRatio": " ".join(map(str, c["ref"])), "drv.fineRegion": " ".join(map(str, c["region"])),
                      "drv.fineMaxBox": c["fine_max_box"]})
     kw["extra"].update(extra)
