@@ -110,35 +110,37 @@ class ClockSampler:
 
 def synthetic_residual(lo, hi, dXi, seed):
     """RHS-B of SURVEY.md 8(d) on one tile: divergence of a sheared, noisy, stratified face velocity
-    (u = tanh shear + noise, v = noise, w = noise under a Gaussian pycnocline envelope; no flow
-    through the domain walls).  Cartesian map: the advecting velocity equals the Cartesian one."""
+    (u = tanh shear + noise, v = noise, w = noise under a Gaussian pycnocline envelope).  The field is
+    built reference box by reference box (BOX cells in x and y) with a generator seeded by the box's
+    global position and no flow through box faces, so it is the same global field for every
+    decomposition into tiles, and its integral vanishes (a solvable all-Neumann problem).
+    Cartesian map: the advecting velocity equals the Cartesian one."""
     import numpy as np
-    rng = np.random.default_rng(seed)
     n = [int(h - l + 1) for l, h in zip(lo, hi)]
+    bx = [BOX[0] or NX[0], BOX[1] or NX[1]]
     z_c = (np.arange(lo[2], hi[2] + 1) + 0.5) * dXi[2]
     z_f = np.arange(lo[2], hi[2] + 2) * dXi[2]
     res = np.zeros(n, order="F")
-    # d/dx of u
-    u = 0.05 * (2.0 * rng.random((n[0] + 1, n[1], n[2]), dtype=np.float64) - 1.0)
-    u += np.tanh((z_c + 0.2) / 0.1)[None, None, :]
-    if lo[0] == 0:
-        u[0] = 0.0
-    if hi[0] == NX[0] - 1:
-        u[-1] = 0.0
-    res += (u[1:] - u[:-1]) * (1.0 / dXi[0])
-    del u
-    v = 0.05 * (2.0 * rng.random((n[0], n[1] + 1, n[2]), dtype=np.float64) - 1.0)
-    if lo[1] == 0:
-        v[:, 0] = 0.0
-    if hi[1] == NX[1] - 1:
-        v[:, -1] = 0.0
-    res += (v[:, 1:] - v[:, :-1]) * (1.0 / dXi[1])
-    del v
-    w = 0.05 * (2.0 * rng.random((n[0], n[1], n[2] + 1), dtype=np.float64) - 1.0)
-    w *= np.exp(-((z_f + 0.2) / 0.1) ** 2)[None, None, :]
-    w[:, :, 0] = 0.0
-    w[:, :, -1] = 0.0
-    res += (w[:, :, 1:] - w[:, :, :-1]) * (1.0 / dXi[2])
+    for j0 in range(int(lo[1]), int(hi[1]) + 1, bx[1]):
+        for i0 in range(int(lo[0]), int(hi[0]) + 1, bx[0]):
+            m = [min(bx[0], int(hi[0]) + 1 - i0), min(bx[1], int(hi[1]) + 1 - j0), n[2]]
+            rng = np.random.default_rng([seed, i0 // bx[0], j0 // bx[1]])
+            blk = np.zeros(m)
+            u = 0.05 * (2.0 * rng.random((m[0] + 1, m[1], m[2]), dtype=np.float64) - 1.0)
+            u += np.tanh((z_c + 0.2) / 0.1)[None, None, :]
+            u[0] = 0.0
+            u[-1] = 0.0
+            blk += (u[1:] - u[:-1]) * (1.0 / dXi[0])
+            v = 0.05 * (2.0 * rng.random((m[0], m[1] + 1, m[2]), dtype=np.float64) - 1.0)
+            v[:, 0] = 0.0
+            v[:, -1] = 0.0
+            blk += (v[:, 1:] - v[:, :-1]) * (1.0 / dXi[1])
+            w = 0.05 * (2.0 * rng.random((m[0], m[1], m[2] + 1), dtype=np.float64) - 1.0)
+            w *= np.exp(-((z_f + 0.2) / 0.1) ** 2)[None, None, :]
+            w[:, :, 0] = 0.0
+            w[:, :, -1] = 0.0
+            blk += (w[:, :, 1:] - w[:, :, :-1]) * (1.0 / dXi[2])
+            res[i0 - int(lo[0]):i0 - int(lo[0]) + m[0], j0 - int(lo[1]):j0 - int(lo[1]) + m[1], :] = blk
     return res
 
 
@@ -184,7 +186,7 @@ def run_ours(args):
     res_h = torch.empty(ncell_tile, dtype=torch.float64, pin_memory=True)
     cor_h = torch.empty(ncell_tile, dtype=torch.float64, pin_memory=True)
     res_np = res_h.numpy().reshape(tuple(int(v) for v in thi - tlo + 1), order="F")
-    res_np[...] = synthetic_residual(tlo, thi, dXi, 20250829 + rank)
+    res_np[...] = synthetic_residual(tlo, thi, dXi, 20250829)
 
     res, cor = op.field(), op.field()
     res.upload_ptr(res_h.data_ptr(), tlo, thi)
