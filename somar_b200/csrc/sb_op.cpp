@@ -474,7 +474,11 @@ void Op::cacheMatrixElements()
 // factorisation of that matrix once (the dgtsv no-interchange recurrence, PoissonOpF.ChF:905-1002).
 void Op::buildLineTables(double sLo, double sHi)
 {
-    lineFast = false;
+    // captured pass loops hold pointers to the tables rebuilt below
+    for (auto& kv : relaxGraphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    relaxGraphs.clear();
+    lineFast  = false;
+    lineSplit = false;
     const char* force = getenv("SB_LINE_KERNEL");  // "general" disables the fast path (tests)
     if (force && std::string(force) == "general") return;
     const int N = lay.nz;
