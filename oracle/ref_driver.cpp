@@ -266,7 +266,12 @@ main(int argc, char* argv[])
 
     // Operator + solver, as AMRNSLevel::validateOpsAndSolvers does.
     std::shared_ptr<BCTools::BCFunction> bcPtr(new BCTools::HomogNeumBC);
-    std::shared_ptr<TapOp> opPtr(new TapOp(levGeo, DisjointBoxLayout(), DisjointBoxLayout(), 1, bcPtr, 0.0, 1.0, nullptr));
+    // drv.alpha / drv.beta: L = J (alpha + beta Lap) (PoissonOp::setAlphaAndBeta, PoissonOp.cpp:707-718); the projector uses 0, 1,
+    // the implicit viscous / diffusive solves a Helmholtz form of the same operator
+    Real opAlpha = 0.0, opBeta = 1.0;
+    drv.query("alpha", opAlpha);
+    drv.query("beta", opBeta);
+    std::shared_ptr<TapOp> opPtr(new TapOp(levGeo, DisjointBoxLayout(), DisjointBoxLayout(), 1, bcPtr, opAlpha, opBeta, nullptr));
 
     OutFile out(outPrefix);
     out.kv("spacedim", SpaceDim);
