@@ -881,13 +881,14 @@ void Op::relax(double* cor, const double* res, int iters, bool resUnchanged, int
             }
             break;
         }
-        case SB_RELAX_JACOBIRB: {  // PoissonOp.cpp:1741-1775
+        case SB_RELAX_JACOBIRB: {  // PoissonOp.cpp:1741-1775: ONE residual per iteration, then both colours from it
             double* r = (double*)ctx->getScratch(lay.n * sizeof(double));
-            for (int it = 0; it < iters; ++it)
-                for (int pass = 0; pass < 2; ++pass) {
-                    residual(r, cor, res, true);
-                    k::jacobi(st(), lay, coef(), cor, r, pass);
-                }
+            for (int it = 0; it < iters; ++it) {
+                residual(r, cor, res, true);
+                k::jacobi(st(), lay, coef(), cor, r, 0);
+                exchange(cor);
+                k::jacobi(st(), lay, coef(), cor, r, 1);
+            }
             break;
         }
         default: SB_FAIL("relaxation method " + std::to_string(relaxMethod) + " is not available on the B200 path (sequential GS cannot be parallelised bit-faithfully)");
