@@ -206,7 +206,7 @@ def test_solve_vcycle_prolong_orders(ctx, name, order):
     ref_norms = ref["norms"][1:]
     if st.status == 0:
         # DIVERGED: the solver withdraws the last correction and drops its norm from the history
-        # (MGSolverI.H:395-405); the oracle's tap still saw that norm() call
+        # (MGSolverI.H:383-392); the oracle's tap still saw that norm() call
         ref_norms = ref_norms[:-1]
     assert_norms(st.norms, ref_norms)
     assert rel_err(phi.download(), ref["phi"]) <= 1e-9
