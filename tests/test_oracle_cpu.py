@@ -55,3 +55,44 @@ def test_null_space_and_projection_invariants():
     assert int(r.kv["hasNullSpace"]) == 1
     z = np.load(os.path.join(HERE, "golden", "g_line_cart.npz"))
     assert float(z["proj_finalDivNorm"]) <= 1e-5 * float(z["proj_initDivNorm"])
+
+
+def _truncation_error(n, ampl):
+    """max |L_h[u] - J Lap u| / max |J Lap u| for a smooth u with homogeneous Neumann walls on an n^3
+    grid of the stretched map x = xi + A sin(2 pi (xi - xmin) / L) (maps/StretchedMap.cpp:9-38)."""
+    nx, L = (n, n, n), (2.0, 1.0, 1.5)
+    c = dict(nx=nx, L=L, max_box=(n // 2, n // 2, 0), bf=4, periodic=(0, 0, 0), relax=5, map="stretched", ampl=ampl)
+    lo = np.array([0.0, 0.0, -L[2]])           # offset (0, 0, -n) cells: z in [-Lz, 0]
+    xs, dxs = [], []
+    for d in range(3):
+        xi = lo[d] + (np.arange(nx[d]) + 0.5) * L[d] / nx[d]
+        k = 2 * np.pi / L[d]
+        xs.append(xi + ampl[d] * np.sin(k * (xi - lo[d])))
+        dxs.append(1.0 + ampl[d] * k * np.cos(k * (xi - lo[d])))
+    m = (2, 1, 3)                                # wall-compatible cosine modes per direction
+    w = [m[d] * np.pi / L[d] for d in range(3)]
+    cosx = [np.cos(w[d] * (xs[d] - lo[d])) for d in range(3)]
+    u = cosx[0][:, None, None] * cosx[1][None, :, None] * cosx[2][None, None, :]
+    lap = -(w[0] ** 2 + w[1] ** 2 + w[2] ** 2) * u
+    r = run_ref("applyop", inp=[np.asfortranarray(u)], **ref_kwargs(c))
+    J = r["J"].reshape(nx, order="F")
+    Jexact = dxs[0][:, None, None] * dxs[1][None, :, None] * dxs[2][None, None, :]
+    lhs = r["lhs"].reshape(nx, order="F")
+    return (np.max(np.abs(lhs - J * lap)) / np.max(np.abs(J * lap)), np.max(np.abs(J - Jexact)) / np.max(Jexact))
+
+
+@pytest.mark.parametrize("ampl", [(0.0, 0.0, 0.0), (0.08, 0.04, -0.1)])
+def test_operator_is_second_order_accurate_on_the_mapped_grid(ampl):
+    """An independent pin of the restated coefficient / stencil / boundary leaves (COMPUTEMATRIXELEMENTS,
+    COMPUTEDINV, APPLYOP, FILLGHOSTCELLS, the metric fills): against the CONTINUOUS operator J Lap u the
+    discrete one must converge at second order, walls included.  A wrong coefficient, index shift or
+    ghost formula in any of them shows as O(1) or first-order error."""
+    e16, j16 = _truncation_error(16, ampl)
+    e32, j32 = _truncation_error(32, ampl)
+    e64, j64 = _truncation_error(64, ampl)
+    assert e16 < 0.2 and e64 < 0.02
+    assert 3.3 <= e16 / e32 <= 4.8 and 3.5 <= e32 / e64 <= 4.5
+    if any(ampl):
+        assert 3.3 <= j16 / j32 <= 4.8 and 3.5 <= j32 / j64 <= 4.5     # the metric is a centred difference of the map
+    else:
+        assert j16 == 0.0 and j64 == 0.0
