@@ -13,7 +13,7 @@
 // precision (the reference only prints 7 digits), and (d) reads / writes flat binary files.
 //
 // Usage: somar_ref <deck> [key=value ...]
-//   drv.mode  = solve | project | applyop | relax | transform | vcycle
+//   drv.mode  = solve | project | applyop | relax | transform | divgrad | vcycle
 //   drv.map   = cartesian | stretched        drv.ampl = ax ay az (StretchedMap amplitudes)
 //   drv.in    = <file>    raw little-endian doubles, global Fortran order over the domain box:
 //                  solve:   rhs[nx*ny*nz]
@@ -507,6 +507,32 @@ main(int argc, char* argv[])
             }
         }
         dump("cart");
+        return 0;
+    }
+
+    if (mode == "divgrad") {
+        // Known-answer hooks for the face-centred operators: drv.in = phi over the domain box, then the D
+        // face fields of an advecting velocity; out = levelGradient(phi) and levelDivergence(vel)
+        // (PoissonOp.cpp:1486-1545, 1568-1610).
+        LDFAB phi(grids, 1, IntVect::Unit), div(grids, 1);
+        for (DataIterator dit(grids); dit.ok(); ++dit) phi[dit].setVal(0.0);
+        scatter(phi, in.data(), domBox);
+        LevelData<FluxBox> vel(grids, 1), grad(grids, 1);
+        size_t off = N;
+        for (int d = 0; d < SpaceDim; ++d) {
+            const Box fcDom = surroundingNodes(domBox, d);
+            for (DataIterator dit(grids); dit.ok(); ++dit) scatterFAB(vel[dit][d], grids[dit], in.data() + off, fcDom);
+            off += fcDom.numPts();
+        }
+        opPtr->levelGradient(grad, phi, nullptr, 0.0, true, true);
+        opPtr->levelDivergence(div, vel);
+        out.put("div", gather(div, domBox));
+        for (int d = 0; d < SpaceDim; ++d) {
+            const Box           fcDom = surroundingNodes(domBox, d);
+            std::vector<double> g(fcDom.numPts(), 0.0);
+            for (DataIterator dit(grids); dit.ok(); ++dit) gatherFAB(g, grad[dit][d], grids[dit], fcDom);
+            out.put(std::string("grad") + char('0' + d), g);
+        }
         return 0;
     }
 

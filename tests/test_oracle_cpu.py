@@ -96,3 +96,63 @@ def test_operator_is_second_order_accurate_on_the_mapped_grid(ampl):
         assert 3.3 <= j16 / j32 <= 4.8 and 3.5 <= j32 / j64 <= 4.5     # the metric is a centred difference of the map
     else:
         assert j16 == 0.0 and j64 == 0.0
+
+
+def _divgrad_errors(n, ampl):
+    """Relative max errors of levelDivergence and levelGradient against the continuous J div(u) and
+    J (dxi/dx) dphi/dx on an n^3 grid of the stretched map."""
+    nx, L = (n, n, n), (2.0, 1.0, 1.5)
+    c = dict(nx=nx, L=L, max_box=(n // 2, n // 2, 0), bf=4, periodic=(0, 0, 0), relax=5, map="stretched", ampl=ampl)
+    lo = np.array([0.0, 0.0, -L[2]])
+    k = [2 * np.pi / L[d] for d in range(3)]
+    xi_c = [lo[d] + (np.arange(nx[d]) + 0.5) * L[d] / nx[d] for d in range(3)]
+    xi_f = [lo[d] + np.arange(nx[d] + 1) * L[d] / nx[d] for d in range(3)]
+    mp = lambda d, xi: xi + ampl[d] * np.sin(k[d] * (xi - lo[d]))                 # x(xi)
+    dm = lambda d, xi: 1.0 + ampl[d] * k[d] * np.cos(k[d] * (xi - lo[d]))         # dx/dxi
+    w = [2 * np.pi / L[0], np.pi / L[1], 3 * np.pi / L[2]]
+
+    def grid(cent):   # coordinates, dx/dxi on the centring cent (tuple of 0 cell / 1 face per direction)
+        xi = [xi_f[d] if cent[d] else xi_c[d] for d in range(3)]
+        X = np.meshgrid(*[mp(d, xi[d]) for d in range(3)], indexing="ij")
+        D = np.meshgrid(*[dm(d, xi[d]) for d in range(3)], indexing="ij")
+        return X, D
+
+    # phi = prod cos(w_d (x_d - lo_d)) (Neumann walls); u_d = sin(w_d (x_d - lo_d)) * cos * cos (no flow through walls)
+    def phi_of(X):
+        return np.cos(w[0] * (X[0] - lo[0])) * np.cos(w[1] * (X[1] - lo[1])) * np.cos(w[2] * (X[2] - lo[2]))
+
+    Xc, Dc = grid((0, 0, 0))
+    Jc = Dc[0] * Dc[1] * Dc[2]
+    vel, div_exact = [], np.zeros(nx)
+    for d in range(3):
+        cent = tuple(1 if e == d else 0 for e in range(3))
+        Xf, Df = grid(cent)
+        f = [np.cos(w[e] * (Xf[e] - lo[e])) for e in range(3)]
+        f[d] = np.sin(w[d] * (Xf[d] - lo[d]))
+        Jf = Df[0] * Df[1] * Df[2]
+        vel.append(np.asfortranarray(Jf / Df[d] * f[0] * f[1] * f[2]))            # advecting velocity J (dxi/dx) u
+        g = [np.cos(w[e] * (Xc[e] - lo[e])) for e in range(3)]
+        g[d] = w[d] * np.cos(w[d] * (Xc[d] - lo[d]))
+        div_exact += g[0] * g[1] * g[2]
+    r = run_ref("divgrad", inp=[np.asfortranarray(phi_of(Xc))] + vel, **ref_kwargs(c))
+    e_div = np.max(np.abs(r["div"].reshape(nx, order="F") - Jc * div_exact)) / np.max(np.abs(Jc * div_exact))
+    e_grad = 0.0
+    for d in range(3):
+        cent = tuple(1 if e == d else 0 for e in range(3))
+        Xf, Df = grid(cent)
+        f = [np.cos(w[e] * (Xf[e] - lo[e])) for e in range(3)]
+        f[d] = -w[d] * np.sin(w[d] * (Xf[d] - lo[d]))
+        want = Df[0] * Df[1] * Df[2] / Df[d] * f[0] * f[1] * f[2]                 # Jg^{dd} dphi/dxi = J (dxi/dx) dphi/dx
+        got = r[f"grad{d}"].reshape(want.shape, order="F")
+        e_grad = max(e_grad, np.max(np.abs(got - want)) / np.max(np.abs(want)))
+    return e_div, e_grad
+
+
+@pytest.mark.parametrize("ampl", [(0.0, 0.0, 0.0), (0.08, 0.04, -0.1)])
+def test_div_and_grad_are_second_order_accurate(ampl):
+    """Same kind of pin for the face-centred leaves (FINITEDIFF_DIV3D, FINITEDIFF_PARTIALD_CC2NC, the Jgup
+    fill, the wall ghost fill used by levelGradient)."""
+    e = [_divgrad_errors(n, ampl) for n in (16, 32, 64)]
+    for q in (0, 1):
+        assert e[2][q] < 0.01
+        assert 3.3 <= e[0][q] / e[1][q] <= 4.8 and 3.5 <= e[1][q] / e[2][q] <= 4.5
