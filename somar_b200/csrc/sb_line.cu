@@ -1,7 +1,10 @@
-// sb_line.cu -- vertical line relaxation on colour-split storage (sm_100a, fp64).
+// sb_line.cu -- relaxation on colour-split storage (sm_100a, fp64): vertical line relaxation
+// (vertline_fused_k and its predecessors / diagnostics) and point red-black Gauss-Seidel
+// (gsrb_split_k), plus the layout conversions, ghost fills and face packing that go with it.
 //
 // Reference: PoissonOp::vertLineGSRB_relax (Grade3_Calculus/Elliptic/PoissonOp.cpp:1927-2010),
-// FORT_POISSONOP_VERTLINEGSRB_3D (Elliptic/PoissonOpF.ChF:851-1019) + LAPACK dgtsv.
+// FORT_POISSONOP_VERTLINEGSRB_3D (Elliptic/PoissonOpF.ChF:851-1019) + LAPACK dgtsv;
+// PoissonOp::gsrb_relax (:1833-1921) + FORT_POISSONOP_GSRB (PoissonOpF.ChF:420-474).
 //
 // Why a second layout.  A colour pass reads only cells of the other colour and writes only its
 // own.  In the natural layout (x contiguous) that is stride-2 access: every 32-byte sector that
