@@ -101,3 +101,41 @@ def test_amr_oracle_reproduces_golden(path):
     assert int(r.kv["status"]) == int(z["status"])
     assert np.array_equal(r["phi0"], z["phi0"].ravel(order="F"))
     assert np.array_equal(r["phi1"], z["phi1"].ravel(order="F"))
+
+
+# Patches that stress the one-sided / order-dropping branches of the coarse derivative stencils
+# (used for the interpolation spec only, not solved).
+SPEC_CASES = dict({n: AMR_CASES[n] for n in CASES3D}, **{
+    "corner": dict(nx=(16, 16, 16), L=(2.0, 1.0, 1.0), offset=(0, 0, -16), max_box=(8, 8, 0), bf=4, periodic=(0, 0, 0), relax=5,
+                   ref=(2, 2, 2), region=(0, 0, -16, 7, 5, -9), fine_max_box=16),
+    "thin": dict(nx=(16, 16, 16), L=(1.0, 1.0, 1.0), offset=(0, 0, 0), max_box=(8, 8, 0), bf=4, periodic=(0, 0, 0), relax=5,
+                 ref=(2, 2, 2), region=(4, 6, 4, 11, 7, 11), fine_max_box=8),
+    "near_wall": dict(nx=(16, 16, 16), L=(1.0, 1.0, 1.0), offset=(0, 0, 0), max_box=(8, 8, 0), bf=4, periodic=(0, 0, 0), relax=5,
+                      ref=(4, 2, 2), region=(1, 1, 1, 8, 14, 10), fine_max_box=16),
+})
+
+
+@pytest.mark.parametrize("name", sorted(SPEC_CASES))
+def test_cf_interpolation_numpy_spec_matches_the_reference(name):
+    """tests/amr_cfinterp_spec.py restates the reference's coarse-fine ghost interpolation (which coarse cells
+    get centred, one-sided or dropped derivative stencils, phistar, the normal quadratic) in numpy -- the
+    blueprint of next round's CUDA kernel.  On random data it must give the reference's ghost values bit for bit."""
+    from amr_cfinterp_spec import CFInterpSpec
+    c = SPEC_CASES[name]
+    nx, ref, reg, off = c["nx"], c["ref"], c["region"], np.array(c["offset"])
+    rng = np.random.default_rng(5)
+    nf = fine_shape(c)
+    p0, p1 = rng.standard_normal(nx), rng.standard_normal(nf)
+    r = run_ref("amr", inp=[np.asfortranarray(p0), np.asfortranarray(p1)], **ref_kwargs_amr(c, **{"drv.cfInterpOnly": 1}))
+    g = r["fineWithGhosts"].reshape(tuple(n + 2 for n in nf), order="F")
+    flo = np.array([reg[d] * ref[d] for d in range(3)])
+    fmb = c["fine_max_box"]                       # fine boxes as oracle/ref_driver.cpp cuts them
+    nb = [(nf[d] + fmb - 1) // fmb for d in range(3)]
+    sz = np.array([nf[d] // nb[d] for d in range(3)])
+    boxes = [(flo + np.array(i) * sz, flo + np.array(i) * sz + sz - 1) for i in np.ndindex(*nb)]
+    dxf = np.array(c["L"]) / np.array(nx) / np.array(ref)
+    spec = CFInterpSpec(off, off + np.array(nx) - 1, c["periodic"], ref, boxes, dxf)
+    out = spec.ghosts(lambda cc: p0[tuple(np.array(cc) - off)], lambda ff: p1[tuple(np.array(ff) - flo)])
+    assert len(out) > 0
+    bad = [(f, g[tuple(np.array(f) - flo + 1)], v) for f, v in out.items() if g[tuple(np.array(f) - flo + 1)] != v]
+    assert not bad, (len(bad), bad[:3])
