@@ -411,6 +411,26 @@ main(int argc, char* argv[])
         Vector<LDFAB*>       vphi(2);
         Vector<const LDFAB*> vrhs(2);
         vphi[0] = &phi0; vphi[1] = &phi1; vrhs[0] = &rhs0; vrhs[1] = &rhs1;
+        int applyOnly = 0;
+        drv.query("applyOnly", applyOnly);
+        if (applyOnly) {
+            // Known-answer hook for the composite operator: drv.in holds phi on both levels (not a right-hand
+            // side); out = -L[phi] on each level through AMRResidualNF / AMRResidualNC with a zero right-hand
+            // side, i.e. the level operator with inhomogeneous coarse-fine ghosts on level 1 and the refluxed
+            // operator on level 0 (PoissonOp.cpp:1156-1200, 1296-1440).
+            scatter(phi0, in.data(), domBox);
+            scatter(phi1, in.data() + N0, fineRegion);
+            for (DataIterator dit(grids); dit.ok(); ++dit) rhs0[dit].setVal(0.0);
+            for (DataIterator dit(fineGrids); dit.ok(); ++dit) rhs1[dit].setVal(0.0);
+            LDFAB res0(grids, 1), res1(fineGrids, 1);
+            vOps[1]->AMRResidualNF(res1, phi1, phi0, rhs1, ref, 0.0, true);
+            vOps[0]->AMRResidualNC(res0, phi1, phi0, rhs0, ref, 0.0, true, *vOps[1]);
+            out.put("minusL0", gather(res0, domBox));
+            out.put("minusL1", gather(res1, fineRegion));
+            out.kv("normComposite", vOps[0]->AMRNormLevel(res0, &res1, ref, ctx->proj.normType));
+            out.kv("normFine", vOps[1]->AMRNormLevel(res1, nullptr, IntVect::Unit, ctx->proj.normType));
+            return 0;
+        }
         const auto t0 = std::chrono::high_resolution_clock::now();
         Elliptic::SolverStatus st = amr.solve(vphi, vrhs, 0.0, true, true);
         const auto t1 = std::chrono::high_resolution_clock::now();
