@@ -132,6 +132,17 @@ int sb_plan_tile(const sb_level_desc* desc, int rank, int nranks, int tile_lo[3]
  * HorizCoarseningStrategy(doVertCoarsening) when relax_method is VERTLINE, else Semicoarsening. */
 int sb_plan_schedule(const sb_level_desc* desc, int max_depth, int* schedule, int capacity, int* num_sched);
 
+/* Stencil records of the quadratic coarse-fine ghost interpolation (MappedQuadCFStencil::define / buildStencils,
+ * Grade2_AnisotropicChombo/QuadCFInterp/MappedCFStencil.cpp:833-1237) for side (dir, side: 0 low, 1 high) of fine box
+ * `box` of a refined patch: the coarse cells under the fine ghost layer (cells[3 n]) and, per cell, weights of the
+ * tangential first / second derivative stencils (w_first / w_second: [2 tangential directions, ascending][offsets -2..2],
+ * to be divided by dx and dx^2) and of the mixed derivative (w_mixed: [o1 + 1][o0 + 1], offsets -1..1, to be divided by
+ * dx_t0 dx_t1).  Centred, one-sided, order-dropped and out-of-buffer cases are resolved into the weights.  Call with
+ * NULL arrays to get num_cells.  Host-only groundwork for the two-level AMR solve. */
+int sb_plan_cf_stencils(const int dom_lo[3], const int dom_hi[3], const int periodic[3], const int ref[3], int num_fine_boxes,
+                        const int* fine_lo, const int* fine_hi, int box, int dir, int side, int capacity, int* num_cells, int* cells,
+                        double* w_first, double* w_second, double* w_mixed);
+
 /* ---- PoissonOp --------------------------------------------------------------------------- */
 /* PoissonOp::PoissonOp(levGeo, fineGrids, crseGrids, 1, bcFunc, alpha, beta) PoissonOp.cpp:33.
  * The metric (J, Jgup) is built the way LevelGeometry::createMetricCache does

@@ -125,6 +125,24 @@ def plan_tile(domain_lo, domain_hi, box_lo, box_hi, box_rank, rank, nranks, peri
     return list(lo), list(hi), list(kind), list(nb), n.value
 
 
+def plan_cf_stencils(dom_lo, dom_hi, periodic, ref, fine_lo, fine_hi, box, direction, side):
+    """Host-only: stencil records of the quadratic coarse-fine ghost interpolation for one side of one fine box
+    (include/somar_b200.h: sb_plan_cf_stencils).  Returns (cells[n,3], w_first[n,2,5], w_second[n,2,5], w_mixed[n,3,3])."""
+    fl = np.ascontiguousarray(fine_lo, dtype=np.int32)
+    fh = np.ascontiguousarray(fine_hi, dtype=np.int32)
+    lib = capi.load()
+    n = C.c_int()
+    args = (_i3(dom_lo), _i3(dom_hi), _i3(periodic), _i3(ref), len(fl), fl.ctypes.data_as(capi.IP), fh.ctypes.data_as(capi.IP), box,
+            direction, side)
+    capi.check(lib.sb_plan_cf_stencils(*args, 0, C.byref(n), None, None, None, None))
+    cells = np.zeros((n.value, 3), dtype=np.int32)
+    w1, w2, wm = np.zeros((n.value, 2, 5)), np.zeros((n.value, 2, 5)), np.zeros((n.value, 3, 3))
+    if n.value:
+        capi.check(lib.sb_plan_cf_stencils(*args, n.value, C.byref(n), cells.ctypes.data_as(capi.IP), w1.ctypes.data_as(capi.DP),
+                                           w2.ctypes.data_as(capi.DP), wm.ctypes.data_as(capi.DP)))
+    return cells, w1, w2, wm
+
+
 def plan_schedule(domain_lo, domain_hi, dXi, box_lo, box_hi, relax_method=RELAX_VERTLINE, max_depth=-1, dim=3):
     """Host-only: the MG refinement schedule MGSolver::define would build (MGCoarseningStrategy.cpp)."""
     d = _level_desc(domain_lo, domain_hi, dXi, box_lo, box_hi, None, (0, 0, 0), dim, relax_method)

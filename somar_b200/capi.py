@@ -102,6 +102,7 @@ PROTOTYPES = {
     "sb_comm_init": (C.c_int, [P, C.c_void_p]),
     "sb_plan_tile": (C.c_int, [C.POINTER(LevelDesc), C.c_int, C.c_int, IP, IP, IP, IP, IP]),
     "sb_plan_schedule": (C.c_int, [C.POINTER(LevelDesc), C.c_int, IP, C.c_int, IP]),
+    "sb_plan_cf_stencils": (C.c_int, [IP, IP, IP, IP, C.c_int, IP, IP, C.c_int, C.c_int, C.c_int, C.c_int, IP, IP, DP, DP, DP]),
     "sb_op_create": (C.c_int, [P, C.POINTER(LevelDesc), PP]),
     "sb_op_set_metric": (C.c_int, [P, C.c_int, C.c_int, DP, IP, IP]),
     "sb_op_finalize": (C.c_int, [P]),

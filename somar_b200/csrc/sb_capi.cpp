@@ -102,6 +102,29 @@ int sb_plan_tile(const sb_level_desc* d, int rank, int nranks, int tile_lo[3], i
     if (num_local_boxes) *num_local_boxes = (int)local.size();
     SB_END
 }
+int sb_plan_cf_stencils(const int dom_lo[3], const int dom_hi[3], const int periodic[3], const int ref[3], int num_fine_boxes,
+                        const int* fine_lo, const int* fine_hi, int box, int dir, int side, int capacity, int* num_cells, int* cells,
+                        double* w_first, double* w_second, double* w_mixed)
+{
+    SB_TRY REQ(dom_lo); REQ(dom_hi); REQ(periodic); REQ(ref); REQ(fine_lo); REQ(fine_hi); REQ(num_cells);
+    Box3 dom;
+    for (int i = 0; i < 3; ++i) { dom.lo[i] = dom_lo[i]; dom.hi[i] = dom_hi[i]; }
+    std::vector<Box3> fb(num_fine_boxes);
+    for (int b = 0; b < num_fine_boxes; ++b)
+        for (int i = 0; i < 3; ++i) { fb[b].lo[i] = fine_lo[3 * b + i]; fb[b].hi[i] = fine_hi[3 * b + i]; }
+    std::vector<int>    c;
+    std::vector<double> w1, w2, wm;
+    planCFStencils(dom, periodic, ref, fb, box, dir, side, c, w1, w2, wm);
+    *num_cells = (int)(c.size() / 3);
+    if (cells || w_first || w_second || w_mixed) {
+        if (capacity < *num_cells) SB_FAIL("capacity too small");
+        if (cells) std::copy(c.begin(), c.end(), cells);
+        if (w_first) std::copy(w1.begin(), w1.end(), w_first);
+        if (w_second) std::copy(w2.begin(), w2.end(), w_second);
+        if (w_mixed) std::copy(wm.begin(), wm.end(), w_mixed);
+    }
+    SB_END
+}
 int sb_plan_schedule(const sb_level_desc* d, int max_depth, int* schedule, int capacity, int* num_sched)
 {
     SB_TRY REQ(d); REQ(num_sched);

@@ -186,6 +186,11 @@ std::vector<std::array<int, 3>> createMGRefScheduleBoxes(int dim, const Box3& do
                                                          const std::vector<Box3>& boxes, int maxDepth, bool horizStrategy,
                                                          bool doVertCoarsening);
 
+// Stencil records of the quadratic coarse-fine ghost interpolation for one side of one fine box (sb_amr_plan.cpp)
+void planCFStencils(const Box3& dom, const int periodic[3], const int ref[3], const std::vector<Box3>& fineBoxes, int box, int dir,
+                    int side, std::vector<int>& cells, std::vector<double>& wFirst, std::vector<double>& wSecond,
+                    std::vector<double>& wMixed);
+
 // SemicoarseningStrategy / HorizCoarseningStrategy (Elliptic/MGCoarseningStrategy.cpp)
 std::vector<std::array<int, 3>> createMGRefSchedule(const Op& top, int maxDepth, bool horizStrategy, bool doVertCoarsening);
 

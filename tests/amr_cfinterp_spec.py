@@ -49,6 +49,7 @@ class CFInterpSpec:
         """phic(c) -> coarse value, phif(f) -> fine value (callables on index tuples).  Returns
         {fine ghost index: value} for every coarse-fine ghost cell of the patch."""
         out = {}
+        self.derivs = {}     # (box, dir, side) -> {coarse cell: (slope{t}, curv{t}, mixed)}
         for b in range(len(self.fb)):
             for d in range(3):
                 for side in (-1, 1):
@@ -154,6 +155,7 @@ class CFInterpSpec:
                     curv[t] = 0.0 if (drop or t not in seconds) else sten_sum(seconds[t]) / (self.dxc[t] * self.dxc[t])
                 mixed = 0.0 if drop else sten_sum(sten) / (self.dxc[tr[1]] * self.dxc[tr[0]])
             deriv[c] = (slope, curv, mixed)
+        self.derivs[(b, d, side)] = deriv
 
         n_hat = np.eye(3, dtype=int)[d] * side
         h = self.dxf[d]

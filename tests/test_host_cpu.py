@@ -139,3 +139,63 @@ def test_two_rank_plan_over_gloo():
     assert all(ok for _, ok, _ in res)
     tiles = {r: (tuple(pl[0]), tuple(pl[1])) for r, _, pl in res}
     assert tiles[0] != tiles[1]
+
+
+@pytest.mark.parametrize("name", ["amr_r2_centre", "amr_aniso_wall", "amr_r4_periodic", "corner", "thin", "near_wall"])
+def test_cf_stencil_plan(name):
+    """sb_plan_cf_stencils (host-only C++, the table builder of next round's coarse-fine ghost kernel) against the
+    numpy specification tests/amr_cfinterp_spec.py, which itself reproduces the reference bit for bit
+    (tests/test_oracle_amr_cpu.py): same coarse cells per patch side and, on random coarse data, the same first,
+    second and mixed tangential derivatives -- centred, one-sided, order-dropped and out-of-buffer cases included."""
+    import somar_b200 as sb
+    from amr_cases import AMR_CASES, fine_shape
+    from amr_cfinterp_spec import CFInterpSpec
+    extra = {
+        "corner": dict(nx=(16, 16, 16), L=(2.0, 1.0, 1.0), offset=(0, 0, -16), periodic=(0, 0, 0), ref=(2, 2, 2),
+                       region=(0, 0, -16, 7, 5, -9), fine_max_box=16),
+        "thin": dict(nx=(16, 16, 16), L=(1.0, 1.0, 1.0), offset=(0, 0, 0), periodic=(0, 0, 0), ref=(2, 2, 2),
+                     region=(4, 6, 4, 11, 7, 11), fine_max_box=8),
+        "near_wall": dict(nx=(16, 16, 16), L=(1.0, 1.0, 1.0), offset=(0, 0, 0), periodic=(0, 0, 0), ref=(4, 2, 2),
+                          region=(1, 1, 1, 8, 14, 10), fine_max_box=16),
+    }
+    c = AMR_CASES[name] if name in AMR_CASES else extra[name]
+    nx, ref, reg, off = np.array(c["nx"]), np.array(c["ref"]), c["region"], np.array(c["offset"])
+    nf = fine_shape(c)
+    flo = np.array([reg[d] * ref[d] for d in range(3)])
+    fmb = c["fine_max_box"]
+    nb = [(nf[d] + fmb - 1) // fmb for d in range(3)]
+    sz = np.array([nf[d] // nb[d] for d in range(3)])
+    boxes = [(flo + np.array(i) * sz, flo + np.array(i) * sz + sz - 1) for i in np.ndindex(*nb)]
+    dxf = np.array(c["L"]) / nx / ref
+    dxc = dxf * ref
+    p0 = np.random.default_rng(8).standard_normal(tuple(nx))
+    phic = lambda cc: p0[tuple(np.array(cc) - off)]
+    spec = CFInterpSpec(off, off + nx - 1, c["periodic"], ref, boxes, dxf)
+    spec.ghosts(phic, lambda ff: 0.0)
+    dom_hi = off + nx - 1
+    inside = lambda cc: all(c["periodic"][d] or off[d] <= cc[d] <= dom_hi[d] for d in range(3))
+    val = lambda cc: phic(cc) if inside(cc) and all(off[d] <= cc[d] <= dom_hi[d] for d in range(3)) else 0.0
+    checked = 0
+    for b in range(len(boxes)):
+        for d in range(3):
+            tr = [t for t in range(3) if t != d]
+            for side in (0, 1):
+                want = spec.derivs.get((b, d, 1 if side else -1), {})
+                cells, w1, w2, wm = sb.plan_cf_stencils(off, dom_hi, c["periodic"], ref, [bx[0] for bx in boxes], [bx[1] for bx in boxes],
+                                                        b, d, side)
+                assert sorted(map(tuple, cells.tolist())) == sorted(want.keys())
+                for n, cc in enumerate(map(tuple, cells.tolist())):
+                    slope, curv, mixed = want[cc]
+                    ca = np.array(cc)
+                    for q, t in enumerate(tr):
+                        e = np.eye(3, dtype=int)[t]
+                        s1 = sum(w1[n, q, o + 2] * val(tuple(ca + o * e)) for o in range(-2, 3) if w1[n, q, o + 2] != 0.0) / dxc[t]
+                        s2 = sum(w2[n, q, o + 2] * val(tuple(ca + o * e)) for o in range(-2, 3) if w2[n, q, o + 2] != 0.0) / (dxc[t] * dxc[t])
+                        assert abs(s1 - slope[t]) <= 1e-12 * (1.0 + abs(slope[t]))
+                        assert abs(s2 - curv[t]) <= 1e-12 * (1.0 + abs(curv[t]))
+                    e0, e1 = np.eye(3, dtype=int)[tr[0]], np.eye(3, dtype=int)[tr[1]]
+                    sm = sum(wm[n, o1 + 1, o0 + 1] * val(tuple(ca + o0 * e0 + o1 * e1)) for o1 in range(-1, 2) for o0 in range(-1, 2)
+                             if wm[n, o1 + 1, o0 + 1] != 0.0) / (dxc[tr[0]] * dxc[tr[1]])
+                    assert abs(sm - mixed) <= 1e-12 * (1.0 + abs(mixed))
+                    checked += 1
+    assert checked > 0
