@@ -71,7 +71,7 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -264,11 +264,14 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps({"profile_mode": True, "ms_per_step_under_profiler": ms / args.steps, "gpu_launches": launches}))
         return
-    for _ in range(max(args.warmup, 3)):
-        step()
+    # clocks are sampled every 50 ms; the sampler is started one warm-up step early (same load) so that nvidia-smi's own
+    # start-up does not eat the short timed region
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    nwarm = max(args.warmup, 3)
+    for w in range(nwarm):
+        if w == nwarm - 1 and rank == 0:
+            sampler.start()
+        step()
     ms, wall_ms, launches = timed(step, args.steps)
     clocks = sampler.stop() if rank == 0 else {}
 
