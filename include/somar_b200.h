@@ -26,6 +26,7 @@ typedef struct sb_context sb_context;
 typedef struct sb_op      sb_op;     /* Elliptic::PoissonOp at one MG depth            */
 typedef struct sb_field   sb_field;  /* LevelData<FArrayBox> or one FluxBox direction  */
 typedef struct sb_solver  sb_solver; /* Elliptic::MGSolver<T> / LevelHybridSolver      */
+typedef struct sb_amr_solver sb_amr_solver; /* Elliptic::AMRHybridSolver             */
 
 /* ProjectorParameters::RelaxMethod (Grade5_SOMAR/ProjectorParameters.H) */
 enum { SB_RELAX_NONE = 0, SB_RELAX_JACOBI = 2, SB_RELAX_JACOBIRB = 3, SB_RELAX_GS = 4, SB_RELAX_GSRB = 5, SB_RELAX_VERTLINE = 6 };
@@ -66,6 +67,17 @@ typedef struct sb_level_desc {
     double alpha;            /* operator J(alpha + beta*Lap); the projector uses 0, 1             */
     double beta;
     int    relax_method;     /* proj.relaxMethod, read by PoissonOp.cpp:54 and MGSolverI.H:154    */
+    /* AMR: a_crseGrids of PoissonOp's constructor (PoissonOp.cpp:33-43, 83-93, 118-120), the
+     * DisjointBoxLayout of the next coarser AMR level.  num_crse_boxes = 0 on the base level.  A
+     * level with a coarser level is a refined patch: its boxes must form one rectangle, which need
+     * not cover the domain; the refinement ratio is domain size / crse_domain size.  (a_fineGrids
+     * is not needed here: the finer operator is an argument of every call that uses it.) */
+    int    num_crse_boxes;
+    const int* crse_box_lo;  /* [num_crse_boxes][3]                                               */
+    const int* crse_box_hi;
+    const int* crse_box_rank;/* NULL = all rank 0                                                 */
+    int    crse_domain_lo[3];
+    int    crse_domain_hi[3];
 } sb_level_desc;
 
 /* BiCGStabSolver<T>::Options (LevelSolver.H) */
@@ -204,6 +216,46 @@ int sb_op_send_to_advecting_velocity(sb_op* op, sb_field* const vel[3], int ghos
 int sb_op_send_to_cartesian_velocity(sb_op* op, sb_field* const vel[3], int ghost);
 /* vel[d] -= scale * grad[d]  (AMRNSLevelProject.cpp:331-336 with scale 1; :155-160 with projDt). */
 int sb_op_flux_incr(sb_op* op, sb_field* const vel[3], sb_field* const grad[3], double scale);
+
+/* ---- AMRMGOperator (Elliptic/AMRMGOperator.H:43-218) and PoissonOp's AMR extras (PoissonOp.H:350-405) ---------
+ * An operator created with crse_box_* in its sb_level_desc is a refined level.  Coarse data (phi_crse, crse_phi) is a
+ * field of the next coarser level's operator; finer_op / phi_fine belong to the next finer level.  homog_phys is
+ * accepted for interface fidelity (the Robin BCs of this ABI carry no boundary data). */
+/* PoissonOp::applyBCs(phi, crsePhiPtr, time, homogPhys, homogCFI) (PoissonOp.cpp:726-763): coarse-fine ghosts by the
+ * homogeneous formula (CFInterp.cpp:429-515) or, homog_cfi = 0, interpolated from crse_phi (MappedQuadCFInterp). */
+int sb_op_apply_bcs_amr(sb_op* op, sb_field* phi, sb_field* crse_phi, int homog_phys, int homog_cfi);
+/* AMROperator / AMROperatorNF / AMROperatorNC (PoissonOp.cpp:1156-1207) */
+int sb_op_amr_operator(sb_op* op, sb_field* lhs, sb_field* phi_fine, sb_field* phi, sb_field* phi_crse, int homog_phys, sb_op* finer_op);
+int sb_op_amr_operator_nf(sb_op* op, sb_field* lhs, sb_field* phi, sb_field* phi_crse, int homog_phys);
+int sb_op_amr_operator_nc(sb_op* op, sb_field* lhs, sb_field* phi_fine, sb_field* phi, int homog_phys, sb_op* finer_op);
+/* AMRResidual (phi_fine, finer_op and phi_crse given), AMRResidualNF (phi_fine = finer_op = NULL), AMRResidualNC
+ * (phi_crse = NULL) (AMRMGOperator.H:107-175): res = rhs - L[phi]. */
+int sb_op_amr_residual(sb_op* op, sb_field* res, sb_field* phi_fine, sb_field* phi, sb_field* phi_crse, sb_field* rhs, int homog_phys,
+                       sb_op* finer_op);
+/* AMRNormLevel(res, fineResPtr, refRatio, p) (PoissonOp.cpp:1225-1286); finer_op = NULL: plain norm with powScale = prod(dXi). */
+int sb_op_amr_norm_level(sb_op* op, sb_field* res, sb_op* finer_op, int p, double* out);
+/* getFlux (PoissonOp.cpp:1295-1326) on every face of the level: beta Jg^{dd} dphi/dXi_d; phi's ghosts must be filled. */
+int sb_op_get_flux(sb_op* op, sb_field* const flux[3], sb_field* phi);
+/* reflux(res, finePhi, phi, fineRefRatio, finerOp) (PoissonOp.cpp:1333-1418) and reflux(div, flux, fineFlux) (:1425-1477) */
+int sb_op_reflux(sb_op* op, sb_field* res, sb_field* fine_phi, sb_field* phi, sb_op* finer_op);
+int sb_op_reflux_flux(sb_op* op, sb_field* div, sb_field* const flux[3], sb_field* const fine_flux[3], sb_op* finer_op);
+/* compDivergence(div, flux, fineFluxPtr) (PoissonOp.cpp:1618-1631); fine_flux = finer_op = NULL: no finer level */
+int sb_op_comp_divergence(sb_op* op, sb_field* div, sb_field* const flux[3], sb_field* const fine_flux[3], sb_op* finer_op);
+/* levelGradient / compGradient(gradPhi, phi, crsePhiPtr, time, homogPhys, homogCFI) (PoissonOp.cpp:1486-1561) */
+int sb_op_comp_gradient(sb_op* op, sb_field* const grad[3], sb_field* phi, sb_field* crse_phi, int homog_phys, int homog_cfi);
+/* Bounding box of the level's boxes (the refined patch; the domain on a base level) and this rank's tile. */
+int sb_op_get_patch(sb_op* op, int patch_lo[3], int patch_hi[3], int tile_lo[3], int tile_hi[3]);
+
+/* ---- AMRHybridSolver (Elliptic/AMRHybridSolver.H) ---------------------------------------------------------------- */
+/* define(Vector<shared_ptr<const AMRMGOperator>>, lmin, lmax, opts) (AMRHybridSolver.cpp:52-104): ops[0..num_levels),
+ * entries below lbase = max(lmin - 1, 0) may be NULL.  opt stands for the proj.* parameters: the solver's own
+ * tolerances / iteration caps and the options of the per-level LevelHybridSolvers both come from them. */
+int sb_amr_solver_create(sb_op* const* ops, int num_levels, int lmin, int lmax, const sb_mg_options* opt, sb_amr_solver** s);
+int sb_amr_solver_destroy(sb_amr_solver* s);
+/* solve(Vector<T*>& phi, Vector<const T*>& rhs, time, homogBCs, setPhiToZero, convergenceMetric) (AMRHybridSolver.cpp:128-322).
+ * phi[lbase..lmax], rhs[lmin..lmax]; status->res_norms = the composite residual norm before and after every iteration. */
+int sb_amr_solver_solve(sb_amr_solver* s, sb_field* const* phi, sb_field* const* rhs, int homog, int set_phi_to_zero,
+                        double convergence_metric, sb_solver_status* status);
 
 /* ---- solvers ----------------------------------------------------------------------------- */
 void sb_mg_default_options(sb_mg_options* opt);        /* ProjectorParameters.cpp:124-222 defaults */

@@ -90,6 +90,23 @@ public:
 };
 
 
+// Tap on the AMR levels' operators: AMRHybridSolver keeps its residual history private and prints 7 digits, so
+// every AMRNormLevel result is recorded in call order.
+static std::vector<double> g_amrNorms;
+class AmrTapOp : public PoissonOp
+{
+public:
+    using PoissonOp::PoissonOp;
+    Real
+    AMRNormLevel(const LDFAB& a_res, const LDFAB* a_fineResPtr, const IntVect& a_refRatio, const int a_p) const override
+    {
+        const Real v = PoissonOp::AMRNormLevel(a_res, a_fineResPtr, a_refRatio, a_p);
+        g_amrNorms.push_back(v);
+        return v;
+    }
+};
+
+
 static void
 makeBaseGrids(Vector<Box>& a_grids, const ProblemDomain& a_domain, const IntVect& a_maxBGS,
               const IntVect& a_splitDirs, const int a_blockFactor)
@@ -325,31 +342,49 @@ main(int argc, char* argv[])
     const size_t N = domBox.numPts();
 
     if (mode == "amr") {
-        // Two-level composite solve: AMRHybridSolver over the base level and one
-        // refined patch, set up the way AMRNSLevel::validateOpsAndSolvers does
+        // Composite solve over 2 or 3 AMR levels: AMRHybridSolver over the base level and
+        // one refined rectangular patch per finer level, set up the way AMRNSLevel::validateOpsAndSolvers does
         // (Grade5_SOMAR/AMRNSLevelInit.cpp:617-676).
-        //   drv.refRatio   = r0 r1 [r2]          refinement ratio of level 1
-        //   drv.fineRegion = lo... hi...          coarse-index box that level 1 covers
-        //   drv.fineMaxBox = n                     level-1 boxes are cut to at most n cells per direction (0: one box)
-        //   drv.in: rhs on level 0 over the domain box, then rhs on level 1 over refine(fineRegion)
-        Vector<int> vr(SpaceDim, 2), vreg;
-        drv.queryarr("refRatio", vr, 0, SpaceDim);
-        drv.getarr("fineRegion", vreg, 0, 2 * SpaceDim);
-        int fineMaxBox = 0;
-        drv.query("fineMaxBox", fineMaxBox);
-        const IntVect ref(D_DECL(vr[0], vr[1], vr[2]));
-        const Box     crseRegion(IntVect(D_DECL(vreg[0], vreg[1], vreg[2])),
-                                 IntVect(D_DECL(vreg[SpaceDim], vreg[SpaceDim + 1], vreg[SpaceDim + 2])));
-        if (!domBox.contains(crseRegion)) MayDay::Error("drv.fineRegion must lie inside the domain");
-        ProblemDomain fineDomain = domain;
-        fineDomain.refine(ref);
-        const Box   fineRegion = refine(crseRegion, ref);
-        Vector<Box> fineBoxes;
-        {
-            IntVect nb, sz;
+        //   drv.refRatio    = r0 r1 [r2]          refinement ratio of level 1
+        //   drv.fineRegion  = lo... hi...          level-0-index box that level 1 covers
+        //   drv.fineMaxBox  = n                     level-1 boxes are cut to at most n cells per direction (0: one box)
+        //   drv.refRatio2 / drv.fineRegion2 (level-1 indices) / drv.fineMaxBox2: an optional level 2, likewise
+        //   drv.in: rhs on level 0 over the domain box, then rhs on level l over refine(fineRegion_l), l = 1, 2
+        std::vector<IntVect> vref;            // vref[l]: ratio between level l-1 and l
+        std::vector<Box>     vregion;         // in level l index space
+        std::vector<int>     vmaxBox;
+        vref.push_back(IntVect::Unit); vregion.push_back(domBox); vmaxBox.push_back(0);
+        for (int l = 1; l <= 2; ++l) {
+            const std::string sfx = l == 1 ? "" : "2";
+            Vector<int> vr(SpaceDim, 2), vreg;
+            if (l == 2 && !drv.contains("fineRegion2")) break;
+            drv.queryarr(("refRatio" + sfx).c_str(), vr, 0, SpaceDim);
+            drv.getarr(("fineRegion" + sfx).c_str(), vreg, 0, 2 * SpaceDim);
+            int fmb = 0;
+            drv.query(("fineMaxBox" + sfx).c_str(), fmb);
+            const IntVect ref(D_DECL(vr[0], vr[1], vr[2]));
+            const Box     crseRegion(IntVect(D_DECL(vreg[0], vreg[1], vreg[2])),
+                                     IntVect(D_DECL(vreg[SpaceDim], vreg[SpaceDim + 1], vreg[SpaceDim + 2])));
+            if (!vregion.back().contains(crseRegion)) MayDay::Error("drv.fineRegion must lie inside the coarser level");
+            vref.push_back(ref);
+            vregion.push_back(refine(crseRegion, ref));
+            vmaxBox.push_back(fmb);
+        }
+        const int nlev = (int)vref.size();
+        std::vector<ProblemDomain>                  vdom(nlev);
+        std::vector<DisjointBoxLayout>              vgrids(nlev);
+        std::vector<std::shared_ptr<LevelGeometry>> vgeo(nlev);
+        vdom[0] = domain; vgrids[0] = grids;
+        std::vector<size_t> vnumBoxes(nlev, boxes.size());
+        for (int l = 1; l < nlev; ++l) {
+            vdom[l] = vdom[l - 1];
+            vdom[l].refine(vref[l]);
+            const Box&  fineRegion = vregion[l];
+            Vector<Box> fineBoxes;
+            IntVect     nb, sz;
             for (int d = 0; d < SpaceDim; ++d) {
                 const int n = fineRegion.size(d);
-                nb[d]       = (fineMaxBox > 0) ? (n + fineMaxBox - 1) / fineMaxBox : 1;
+                nb[d]       = (vmaxBox[l] > 0) ? (n + vmaxBox[l] - 1) / vmaxBox[l] : 1;
                 if (n % nb[d]) MayDay::Error("drv.fineMaxBox must divide the refined region evenly");
                 sz[d] = n / nb[d];
             }
@@ -357,110 +392,116 @@ main(int argc, char* argv[])
                 const IntVect lo = fineRegion.smallEnd() + bit() * sz;
                 fineBoxes.push_back(Box(lo, lo + sz - IntVect::Unit));
             }
+            vgrids[l].defineAndLoadBalance(fineBoxes, nullptr, vdom[l]);
+            vnumBoxes[l] = fineBoxes.size();
         }
-        DisjointBoxLayout fineGrids;
-        fineGrids.defineAndLoadBalance(fineBoxes, nullptr, fineDomain);
-
-        LevelGeometry fineLevGeo(fineDomain, L, &levGeo, geoPtr);
-        fineLevGeo.createMetricCache(fineGrids);
-
+        for (int l = 1; l < nlev; ++l) {
+            vgeo[l].reset(new LevelGeometry(vdom[l], L, l == 1 ? &levGeo : vgeo[l - 1].get(), geoPtr));
+            vgeo[l]->createMetricCache(vgrids[l]);
+        }
         using OpType = Elliptic::AMRMGOperator<LDFAB>;
-        Vector<std::shared_ptr<const OpType>> vOps(2);
-        vOps[0].reset(new PoissonOp(levGeo, fineGrids, DisjointBoxLayout(), 1, bcPtr));
-        vOps[1].reset(new PoissonOp(fineLevGeo, DisjointBoxLayout(), grids, 1, bcPtr));
+        Vector<std::shared_ptr<const OpType>> vOps(nlev);
+        for (int l = 0; l < nlev; ++l) {
+            const LevelGeometry& lg = l == 0 ? levGeo : *vgeo[l];
+            vOps[l].reset(new AmrTapOp(lg, l + 1 < nlev ? vgrids[l + 1] : DisjointBoxLayout(), l > 0 ? vgrids[l - 1] : DisjointBoxLayout(), 1,
+                                       bcPtr));
+        }
+        // level data
+        std::vector<std::shared_ptr<LDFAB>> phi(nlev), rhs(nlev);
+        std::vector<size_t>                 off(nlev + 1, 0);
+        for (int l = 0; l < nlev; ++l) {
+            phi[l].reset(new LDFAB(vgrids[l], 1, IntVect::Unit));
+            rhs[l].reset(new LDFAB(vgrids[l], 1));
+            for (DataIterator dit(vgrids[l]); dit.ok(); ++dit) { (*phi[l])[dit].setVal(0.0); (*rhs[l])[dit].setVal(0.0); }
+            off[l + 1] = off[l] + vregion[l].numPts();
+        }
+        if (in.size() < off[nlev]) MayDay::Error("drv.in too short for the level data");
+        auto tag = [&](const char* base, int l) { return std::string(base) + char('0' + l); };
 
         int cfOnly = 0;
         drv.query("cfInterpOnly", cfOnly);
         if (cfOnly) {
-            // Known-answer hook for the coarse-fine ghost interpolation (PoissonOp::applyBCs with a coarse
-            // level -> CFInterp::interpAtCFI -> MappedQuadCFInterp): drv.in = phi on level 0 over the domain,
-            // then phi on level 1 over refine(fineRegion); output = level-1 phi with its ghost layer.
-            LDFAB c(grids, 1, IntVect::Unit), f(fineGrids, 1, IntVect::Unit);
-            const size_t n0 = domBox.numPts(), n1 = fineRegion.numPts();
-            if (in.size() < n0 + n1) MayDay::Error("drv.in too short");
-            for (DataIterator dit(grids); dit.ok(); ++dit) c[dit].setVal(0.0);
-            for (DataIterator dit(fineGrids); dit.ok(); ++dit) f[dit].setVal(0.0);
-            scatter(c, in.data(), domBox);
-            scatter(f, in.data() + n0, fineRegion);
-            vOps[1]->applyBCs(f, &c, 0.0, true, false);
-            Box gb = fineRegion;
-            gb.grow(1);
-            std::vector<double> v(gb.numPts(), 0.0);
-            // face ghosts only (edge and corner ghosts are not filled by the CF interpolation)
-            for (DataIterator dit(fineGrids); dit.ok(); ++dit)
-                for (int d = 0; d < SpaceDim; ++d) {
-                    Box b = fineGrids[dit];
-                    b.grow(d, 1);
-                    gatherFAB(v, f[dit], b, gb);
-                }
-            // valid data last, so that a ghost of one box never hides the valid value of its neighbour
-            for (DataIterator dit(fineGrids); dit.ok(); ++dit) gatherFAB(v, f[dit], fineGrids[dit], gb);
-            out.put("fineWithGhosts", v);
+            // Known-answer hook for the coarse-fine ghost interpolation (PoissonOp::applyBCs with a coarse level ->
+            // CFInterp::interpAtCFI -> MappedQuadCFInterp): drv.in = phi on every level; output = the finest level's
+            // phi with its ghost layer ("fineWithGhosts"), and the same for level 1 of 3 ("midWithGhosts").
+            for (int l = 0; l < nlev; ++l) scatter(*phi[l], in.data() + off[l], vregion[l]);
+            for (int l = 1; l < nlev; ++l) {
+                vOps[l]->applyBCs(*phi[l], &*phi[l - 1], 0.0, true, false);
+                Box gb = vregion[l];
+                gb.grow(1);
+                std::vector<double> v(gb.numPts(), 0.0);
+                // face ghosts only (edge and corner ghosts are not filled by the CF interpolation)
+                for (DataIterator dit(vgrids[l]); dit.ok(); ++dit)
+                    for (int d = 0; d < SpaceDim; ++d) {
+                        Box b = vgrids[l][dit];
+                        b.grow(d, 1);
+                        gatherFAB(v, (*phi[l])[dit], b, gb);
+                    }
+                // valid data last, so that a ghost of one box never hides the valid value of its neighbour
+                for (DataIterator dit(vgrids[l]); dit.ok(); ++dit) gatherFAB(v, (*phi[l])[dit], vgrids[l][dit], gb);
+                out.put(l == nlev - 1 ? "fineWithGhosts" : "midWithGhosts", v);
+            }
             return 0;
         }
-        Elliptic::AMRHybridSolver amr;
-        amr.define(vOps, 0, 1, Elliptic::AMRHybridSolver::getDefaultOptions());
 
-        LDFAB phi0(grids, 1, IntVect::Unit), rhs0(grids, 1), phi1(fineGrids, 1, IntVect::Unit), rhs1(fineGrids, 1);
-        const size_t N0 = domBox.numPts(), N1 = fineRegion.numPts();
-        if (in.size() < N0 + N1) MayDay::Error("drv.in too short for the two-level right-hand side");
-        scatter(rhs0, in.data(), domBox);
-        scatter(rhs1, in.data() + N0, fineRegion);
-        for (DataIterator dit(grids); dit.ok(); ++dit) phi0[dit].setVal(0.0);
-        for (DataIterator dit(fineGrids); dit.ok(); ++dit) phi1[dit].setVal(0.0);
-        Vector<LDFAB*>       vphi(2);
-        Vector<const LDFAB*> vrhs(2);
-        vphi[0] = &phi0; vphi[1] = &phi1; vrhs[0] = &rhs0; vrhs[1] = &rhs1;
+        // Composite residual through the operators' public AMR interface (AMRMGOperator.H:107-175) and its norm
+        // (AMRNormLevel, PoissonOp.cpp:1215-1286): an evaluation that does not go through AMRHybridSolver's bookkeeping.
+        auto compResidual = [&](std::vector<std::shared_ptr<LDFAB>>& f, const std::string& name, bool dumpFields) {
+            std::vector<std::shared_ptr<LDFAB>> res(nlev);
+            for (int l = 0; l < nlev; ++l) res[l].reset(new LDFAB(vgrids[l], 1));
+            for (int l = nlev - 1; l >= 0; --l) {
+                if (l == nlev - 1 && l > 0) vOps[l]->AMRResidualNF(*res[l], *f[l], *f[l - 1], *rhs[l], vref[l], 0.0, true);
+                else if (l == 0) vOps[l]->AMRResidualNC(*res[l], *f[l + 1], *f[l], *rhs[l], vref[l + 1], 0.0, true, *vOps[l + 1]);
+                else vOps[l]->AMRResidual(*res[l], *f[l + 1], *f[l], *f[l - 1], *rhs[l], vref[l + 1], vref[l], 0.0, true, *vOps[l + 1]);
+            }
+            for (int l = 0; l < nlev; ++l) {
+                const Real n = l == nlev - 1 ? vOps[l]->AMRNormLevel(*res[l], nullptr, IntVect::Unit, ctx->proj.normType)
+                                             : vOps[l]->AMRNormLevel(*res[l], &*res[l + 1], vref[l + 1], ctx->proj.normType);
+                out.kv(name + "Norm" + char('0' + l), n);
+                if (dumpFields) out.put(name + char('0' + l), gather(*res[l], vregion[l]));
+            }
+        };
+
         int applyOnly = 0;
         drv.query("applyOnly", applyOnly);
         if (applyOnly) {
-            // Known-answer hook for the composite operator: drv.in holds phi on both levels (not a right-hand
-            // side); out = -L[phi] on each level through AMRResidualNF / AMRResidualNC with a zero right-hand
-            // side, i.e. the level operator with inhomogeneous coarse-fine ghosts on level 1 and the refluxed
-            // operator on level 0 (PoissonOp.cpp:1156-1200, 1296-1440).
-            scatter(phi0, in.data(), domBox);
-            scatter(phi1, in.data() + N0, fineRegion);
-            for (DataIterator dit(grids); dit.ok(); ++dit) rhs0[dit].setVal(0.0);
-            for (DataIterator dit(fineGrids); dit.ok(); ++dit) rhs1[dit].setVal(0.0);
-            LDFAB res0(grids, 1), res1(fineGrids, 1);
-            vOps[1]->AMRResidualNF(res1, phi1, phi0, rhs1, ref, 0.0, true);
-            vOps[0]->AMRResidualNC(res0, phi1, phi0, rhs0, ref, 0.0, true, *vOps[1]);
-            out.put("minusL0", gather(res0, domBox));
-            out.put("minusL1", gather(res1, fineRegion));
-            out.kv("normComposite", vOps[0]->AMRNormLevel(res0, &res1, ref, ctx->proj.normType));
-            out.kv("normFine", vOps[1]->AMRNormLevel(res1, nullptr, IntVect::Unit, ctx->proj.normType));
+            // Known-answer hook for the composite operator: drv.in holds phi on every level (not a right-hand side);
+            // out = -L[phi] per level with a zero right-hand side, i.e. the level operator with inhomogeneous
+            // coarse-fine ghosts and / or the refluxed operator (PoissonOp.cpp:1156-1207, 1296-1440).
+            for (int l = 0; l < nlev; ++l) scatter(*phi[l], in.data() + off[l], vregion[l]);
+            compResidual(phi, "minusL", true);
+            g_amrNorms.clear();
             return 0;
         }
+        for (int l = 0; l < nlev; ++l) scatter(*rhs[l], in.data() + off[l], vregion[l]);
+        Elliptic::AMRHybridSolver amr;
+        amr.define(vOps, 0, nlev - 1, Elliptic::AMRHybridSolver::getDefaultOptions());
+        Vector<LDFAB*>       vphi(nlev);
+        Vector<const LDFAB*> vrhs(nlev);
+        for (int l = 0; l < nlev; ++l) { vphi[l] = &*phi[l]; vrhs[l] = &*rhs[l]; }
+        g_amrNorms.clear();
         const auto t0 = std::chrono::high_resolution_clock::now();
         Elliptic::SolverStatus st = amr.solve(vphi, vrhs, 0.0, true, true);
         const auto t1 = std::chrono::high_resolution_clock::now();
-        out.put("phi0", gather(phi0, domBox));
-        out.put("phi1", gather(phi1, fineRegion));
-        // Composite residual through the operators' public AMR interface (AMRMGOperator.H:137-175), before
-        // (phi = 0) and after the solve, and its composite norm (AMRNormLevel, PoissonOp.cpp:1215-1260):
-        // an evaluation that does not go through AMRHybridSolver's own bookkeeping.
+        // AMRHybridSolver::computeAMRResidual calls AMRNormLevel once per level, lmin..lmax, per evaluation: the tap
+        // holds the per-level norms of the initial residual and of every iteration (the solver keeps its history private)
+        out.put("amrLevelNorms", g_amrNorms);
+        for (int l = 0; l < nlev; ++l) out.put(tag("phi", l), gather(*phi[l], vregion[l]));
         {
-            LDFAB res0(grids, 1), res1(fineGrids, 1), z0(grids, 1, IntVect::Unit), z1(fineGrids, 1, IntVect::Unit);
-            for (DataIterator dit(grids); dit.ok(); ++dit) z0[dit].setVal(0.0);
-            for (DataIterator dit(fineGrids); dit.ok(); ++dit) z1[dit].setVal(0.0);
-            auto compNorm = [&](LDFAB& f1, LDFAB& f0, const char* tag) {
-                vOps[1]->AMRResidualNF(res1, f1, f0, rhs1, ref, 0.0, true);
-                vOps[0]->AMRResidualNC(res0, f1, f0, rhs0, ref, 0.0, true, *vOps[1]);
-                const Real n1 = vOps[1]->AMRNormLevel(res1, nullptr, IntVect::Unit, ctx->proj.normType);
-                const Real n0 = vOps[0]->AMRNormLevel(res0, &res1, ref, ctx->proj.normType);
-                out.kv(std::string(tag) + "Norm0", n0);
-                out.kv(std::string(tag) + "Norm1", n1);
-                out.put(std::string(tag) + "0", gather(res0, domBox));
-                out.put(std::string(tag) + "1", gather(res1, fineRegion));
-            };
-            compNorm(z1, z0, "res_init");
-            compNorm(phi1, phi0, "res_final");
+            std::vector<std::shared_ptr<LDFAB>> zero(nlev);
+            for (int l = 0; l < nlev; ++l) {
+                zero[l].reset(new LDFAB(vgrids[l], 1, IntVect::Unit));
+                for (DataIterator dit(vgrids[l]); dit.ok(); ++dit) (*zero[l])[dit].setVal(0.0);
+            }
+            compResidual(zero, "res_init", true);
+            compResidual(phi, "res_final", true);
         }
         out.kv("status", st.getSolverStatus());
         out.kv("initResNorm", st.getInitResNorm());
         out.kv("finalResNorm", st.getFinalResNorm());
         out.kv("solveTime", std::chrono::duration<double>(t1 - t0).count());
-        out.kv("numFineBoxes", fineBoxes.size());
+        out.kv("numLevels", nlev);
+        out.kv("numFineBoxes", vnumBoxes[nlev - 1]);
         return 0;
     }
 

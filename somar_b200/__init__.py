@@ -19,8 +19,8 @@ from . import capi
 from .capi import (CELL, FACE_X, FACE_Y, FACE_Z, MAP_CARTESIAN, MAP_STRETCHED, RELAX_GSRB, RELAX_VERTLINE, STATUS_NAMES,
                    MGOptions, SolverStatus, SomarB200Error)
 
-__all__ = ["Context", "PoissonOp", "Field", "MGSolver", "LevelHybridSolver", "make_base_grids", "assign_boxes_to_ranks",
-           "default_options", "SomarB200Error"]
+__all__ = ["Context", "PoissonOp", "Field", "MGSolver", "LevelHybridSolver", "AMRHybridSolver", "make_base_grids",
+           "assign_boxes_to_ranks", "default_options", "SomarB200Error"]
 
 
 def _i3(v):
@@ -230,8 +230,9 @@ class Field:
         capi.check(self.lib.sb_field_create(op.h, centering, C.byref(self.h)))
 
     def box(self, ghost=0):
-        lo = np.array(self.op.domain_lo) - ghost
-        hi = np.array(self.op.domain_hi) + ghost
+        """The box this level's data spans: the domain on a base level, the refined patch otherwise."""
+        lo = np.array(self.op.patch_lo) - ghost
+        hi = np.array(self.op.patch_hi) + ghost
         if self.centering >= 0:
             hi[self.centering] += 1
         return lo, hi
@@ -286,11 +287,15 @@ class PoissonOp:
 
     def __init__(self, ctx, domain_lo, domain_hi, dXi, box_lo, box_hi, box_rank=None, periodic=(0, 0, 0), dim=3,
                  map_kind=MAP_CARTESIAN, map_xmin=(0, 0, 0), map_xmax=(1, 1, 1), map_ampl=(0, 0, 0), bc_alpha=None, bc_beta=None,
-                 alpha=0.0, beta=1.0, relax_method=RELAX_VERTLINE, finalize=True, _handle=None):
+                 alpha=0.0, beta=1.0, relax_method=RELAX_VERTLINE, finalize=True, crse_op=None, _handle=None):
+        """crse_op: the PoissonOp of the next coarser AMR level (a_crseGrids of PoissonOp.cpp:33-43); the boxes then
+        describe a refined patch of a domain that is a refinement of crse_op's."""
         self.ctx, self.lib = ctx, ctx.lib
         self.dim = dim
         self.domain_lo, self.domain_hi = tuple(int(v) for v in domain_lo), tuple(int(v) for v in domain_hi)
+        self.patch_lo, self.patch_hi = self.domain_lo, self.domain_hi
         self.dXi = tuple(float(v) for v in dXi)
+        self.crse_op = crse_op
         if _handle is not None:
             self.h = _handle
             return
@@ -315,6 +320,14 @@ class PoissonOp:
                 d.bc_alpha[i][s] = 0.0 if bc_alpha is None else bc_alpha[i][s]
                 d.bc_beta[i][s] = 1.0 if bc_beta is None else bc_beta[i][s]
         d.alpha, d.beta, d.relax_method = alpha, beta, relax_method
+        if crse_op is not None:
+            d.num_crse_boxes = len(crse_op.box_lo)
+            d.crse_box_lo = crse_op.box_lo.ctypes.data_as(capi.IP)
+            d.crse_box_hi = crse_op.box_hi.ctypes.data_as(capi.IP)
+            d.crse_box_rank = crse_op.box_rank.ctypes.data_as(capi.IP)
+            d.crse_domain_lo, d.crse_domain_hi = _i3(crse_op.domain_lo), _i3(crse_op.domain_hi)
+            self.patch_lo = tuple(int(v) for v in self.box_lo.min(axis=0))
+            self.patch_hi = tuple(int(v) for v in self.box_hi.max(axis=0))
         self.h = C.c_void_p()
         capi.check(self.lib.sb_op_create(ctx.h, C.byref(d), C.byref(self.h)))
         if finalize:
@@ -428,6 +441,43 @@ class PoissonOp:
     def levelGradient(self, grad, phi, homog=True):
         capi.check(self.lib.sb_op_level_gradient(self.h, self._f3(grad), phi.h, int(homog)))
 
+    # -- AMRMGOperator surface (Elliptic/AMRMGOperator.H:43-218, PoissonOp.cpp:1156-1478)
+    def applyBCsAMR(self, phi, crse_phi=None, homog_phys=True, homog_cfi=True):
+        capi.check(self.lib.sb_op_apply_bcs_amr(self.h, phi.h, crse_phi.h if crse_phi else None, int(homog_phys), int(homog_cfi)))
+
+    def AMROperatorNF(self, lhs, phi, phi_crse, homog_phys=True):
+        capi.check(self.lib.sb_op_amr_operator_nf(self.h, lhs.h, phi.h, phi_crse.h, int(homog_phys)))
+
+    def AMROperatorNC(self, lhs, phi_fine, phi, finer_op, homog_phys=True):
+        capi.check(self.lib.sb_op_amr_operator_nc(self.h, lhs.h, phi_fine.h, phi.h, int(homog_phys), finer_op.h))
+
+    def AMROperator(self, lhs, phi_fine, phi, phi_crse, finer_op, homog_phys=True):
+        capi.check(self.lib.sb_op_amr_operator(self.h, lhs.h, phi_fine.h, phi.h, phi_crse.h, int(homog_phys), finer_op.h))
+
+    def AMRResidual(self, res, phi, rhs, phi_fine=None, finer_op=None, phi_crse=None, homog_phys=True):
+        """AMRResidual / AMRResidualNF (no finer level) / AMRResidualNC (no coarser level)."""
+        capi.check(self.lib.sb_op_amr_residual(self.h, res.h, phi_fine.h if phi_fine else None, phi.h, phi_crse.h if phi_crse else None,
+                                               rhs.h, int(homog_phys), finer_op.h if finer_op else None))
+
+    def AMRNormLevel(self, res, finer_op=None, p=2):
+        v = C.c_double()
+        capi.check(self.lib.sb_op_amr_norm_level(self.h, res.h, finer_op.h if finer_op else None, p, C.byref(v)))
+        return v.value
+
+    def getFlux(self, flux, phi):
+        capi.check(self.lib.sb_op_get_flux(self.h, self._f3(flux), phi.h))
+
+    def reflux(self, res, fine_phi, phi, finer_op):
+        capi.check(self.lib.sb_op_reflux(self.h, res.h, fine_phi.h, phi.h, finer_op.h))
+
+    def compDivergence(self, div, flux, fine_flux=None, finer_op=None):
+        ff = self._f3(fine_flux) if fine_flux is not None else None
+        capi.check(self.lib.sb_op_comp_divergence(self.h, div.h, self._f3(flux), ff, finer_op.h if finer_op else None))
+
+    def compGradient(self, grad, phi, crse_phi=None, homog_phys=True, homog_cfi=True):
+        capi.check(self.lib.sb_op_comp_gradient(self.h, self._f3(grad), phi.h, crse_phi.h if crse_phi else None, int(homog_phys),
+                                                int(homog_cfi)))
+
     def sendToAdvectingVelocity(self, vel, ghost=1):
         """AMRNSLevel::sendToAdvectingVelocity (AMRNSLevelFill.cpp:194-232), in place on device face fields."""
         capi.check(self.lib.sb_op_send_to_advecting_velocity(self.h, self._f3(vel), ghost))
@@ -501,6 +551,31 @@ class _SolverBase:
     def free(self):
         if self.h:
             self.lib.sb_solver_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class AMRHybridSolver:
+    """Elliptic::AMRHybridSolver::define(vAMRMGOps, lmin, lmax, opts) / solve(vphi, vrhs, ...)."""
+
+    def __init__(self, ops, lmin=0, lmax=None, opt=None):
+        self.ops, self.lib = list(ops), ops[-1].lib
+        self.lmin, self.lmax = lmin, len(ops) - 1 if lmax is None else lmax
+        opt = opt or default_options()
+        arr = (C.c_void_p * len(ops))(*[o.h if o is not None else None for o in ops])
+        self.h = C.c_void_p()
+        capi.check(self.lib.sb_amr_solver_create(arr, len(ops), self.lmin, self.lmax, C.byref(opt), C.byref(self.h)))
+
+    def solve(self, phi, rhs, homog=True, set_phi_to_zero=True, convergence_metric=-1.0):
+        n = len(self.ops)
+        pa = (C.c_void_p * n)(*[f.h if f is not None else None for f in phi])
+        ra = (C.c_void_p * n)(*[f.h if f is not None else None for f in rhs])
+        st = SolverStatus()
+        capi.check(self.lib.sb_amr_solver_solve(self.h, pa, ra, int(homog), int(set_phi_to_zero), convergence_metric, C.byref(st)))
+        return st
+
+    def free(self):
+        if self.h:
+            self.lib.sb_amr_solver_destroy(self.h)
             self.h = C.c_void_p()
 
 

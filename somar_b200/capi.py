@@ -45,6 +45,12 @@ class LevelDesc(C.Structure):
         ("alpha", C.c_double),
         ("beta", C.c_double),
         ("relax_method", C.c_int),
+        ("num_crse_boxes", C.c_int),
+        ("crse_box_lo", C.POINTER(C.c_int)),
+        ("crse_box_hi", C.POINTER(C.c_int)),
+        ("crse_box_rank", C.POINTER(C.c_int)),
+        ("crse_domain_lo", I3),
+        ("crse_domain_hi", I3),
     ]
 
 
@@ -135,6 +141,21 @@ PROTOTYPES = {
     "sb_op_flux_incr": (C.c_int, [P, F3, F3, C.c_double]),
     "sb_op_send_to_advecting_velocity": (C.c_int, [P, F3, C.c_int]),
     "sb_op_send_to_cartesian_velocity": (C.c_int, [P, F3, C.c_int]),
+    "sb_op_apply_bcs_amr": (C.c_int, [P, P, P, C.c_int, C.c_int]),
+    "sb_op_amr_operator": (C.c_int, [P, P, P, P, P, C.c_int, P]),
+    "sb_op_amr_operator_nf": (C.c_int, [P, P, P, P, C.c_int]),
+    "sb_op_amr_operator_nc": (C.c_int, [P, P, P, P, C.c_int, P]),
+    "sb_op_amr_residual": (C.c_int, [P, P, P, P, P, P, C.c_int, P]),
+    "sb_op_amr_norm_level": (C.c_int, [P, P, P, C.c_int, DP]),
+    "sb_op_get_flux": (C.c_int, [P, F3, P]),
+    "sb_op_reflux": (C.c_int, [P, P, P, P, P]),
+    "sb_op_reflux_flux": (C.c_int, [P, P, F3, F3, P]),
+    "sb_op_comp_divergence": (C.c_int, [P, P, F3, PP, P]),
+    "sb_op_comp_gradient": (C.c_int, [P, F3, P, P, C.c_int, C.c_int]),
+    "sb_op_get_patch": (C.c_int, [P, IP, IP, IP, IP]),
+    "sb_amr_solver_create": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, C.POINTER(MGOptions), PP]),
+    "sb_amr_solver_destroy": (C.c_int, [P]),
+    "sb_amr_solver_solve": (C.c_int, [P, PP, PP, C.c_int, C.c_int, C.c_double, C.POINTER(SolverStatus)]),
     "sb_mg_default_options": (None, [C.POINTER(MGOptions)]),
     "sb_mg_quick_and_dirty_options": (None, [C.POINTER(MGOptions)]),
     "sb_mgsolver_create": (C.c_int, [P, C.POINTER(MGOptions), IP, C.c_int, PP]),

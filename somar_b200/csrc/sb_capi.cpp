@@ -1,5 +1,7 @@
 // sb_capi.cpp -- the extern "C" boundary declared in include/somar_b200.h.  No exception and no
 // C++ type crosses it; failures set the thread-local message read by sb_last_error().
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "sb_comm.h"
@@ -417,6 +419,163 @@ int sb_op_flux_incr(sb_op* op, sb_field* const vel[3], sb_field* const grad[3], 
     for (int d = 0; d < 3; ++d) {
         if (op->op->dim == 2 && d == 1) continue;
         k::incr_valid(op->op->st(), op->op->lay, v[d], g[d], -scale, d);  // FArrayBox::plus(grad, -scale)
+    }
+    SB_END
+}
+
+// ---- AMRMGOperator surface ---------------------------------------------------------------------
+static sb::Op* opOf(sb_field* f) { return f ? f->f.op : nullptr; }
+int sb_op_apply_bcs_amr(sb_op* op, sb_field* phi, sb_field* crse_phi, int homog_phys, int homog_cfi)
+{
+    SB_TRY sameOp(op, {phi}); (void)homog_phys;
+    OPF(op).applyBCsAMR(D(phi), opOf(crse_phi), crse_phi ? D(crse_phi) : nullptr, homog_cfi != 0);
+    SB_END
+}
+int sb_op_amr_operator(sb_op* op, sb_field* lhs, sb_field* phi_fine, sb_field* phi, sb_field* phi_crse, int homog_phys, sb_op* finer_op)
+{
+    SB_TRY sameOp(op, {lhs, phi}); sameOp(finer_op, {phi_fine}); REQ(phi_crse); (void)homog_phys;
+    OPF(op).AMROperator(D(lhs), OPF(finer_op), D(phi_fine), D(phi), *opOf(phi_crse), D(phi_crse));
+    SB_END
+}
+int sb_op_amr_operator_nf(sb_op* op, sb_field* lhs, sb_field* phi, sb_field* phi_crse, int homog_phys)
+{
+    SB_TRY sameOp(op, {lhs, phi}); REQ(phi_crse); (void)homog_phys;
+    OPF(op).AMROperatorNF(D(lhs), D(phi), *opOf(phi_crse), D(phi_crse));
+    SB_END
+}
+int sb_op_amr_operator_nc(sb_op* op, sb_field* lhs, sb_field* phi_fine, sb_field* phi, int homog_phys, sb_op* finer_op)
+{
+    SB_TRY sameOp(op, {lhs, phi}); sameOp(finer_op, {phi_fine}); (void)homog_phys;
+    OPF(op).AMROperatorNC(D(lhs), OPF(finer_op), D(phi_fine), D(phi));
+    SB_END
+}
+int sb_op_amr_residual(sb_op* op, sb_field* res, sb_field* phi_fine, sb_field* phi, sb_field* phi_crse, sb_field* rhs, int homog_phys,
+                       sb_op* finer_op)
+{
+    SB_TRY sameOp(op, {res, phi, rhs}); (void)homog_phys;
+    if ((finer_op != nullptr) != (phi_fine != nullptr)) SB_FAIL("finer_op and phi_fine go together");
+    if (finer_op) sameOp(finer_op, {phi_fine});
+    OPF(op).AMRResidual(D(res), finer_op ? finer_op->op : nullptr, phi_fine ? D(phi_fine) : nullptr, D(phi), opOf(phi_crse),
+                        phi_crse ? D(phi_crse) : nullptr, D(rhs));
+    SB_END
+}
+int sb_op_amr_norm_level(sb_op* op, sb_field* res, sb_op* finer_op, int p, double* out)
+{
+    SB_TRY sameOp(op, {res}); REQ(out);
+    *out = OPF(op).AMRNormLevel(D(res), finer_op ? finer_op->op : nullptr, p);
+    SB_END
+}
+int sb_op_get_flux(sb_op* op, sb_field* const flux[3], sb_field* phi)
+{
+    SB_TRY sameOp(op, {phi});
+    double* g[3]; fluxPtrs(op, flux, g);
+    OPF(op).getFlux(g, D(phi));
+    SB_END
+}
+int sb_op_reflux(sb_op* op, sb_field* res, sb_field* fine_phi, sb_field* phi, sb_op* finer_op)
+{
+    SB_TRY sameOp(op, {res, phi}); sameOp(finer_op, {fine_phi});
+    OPF(op).reflux(D(res), OPF(finer_op), D(fine_phi), D(phi));
+    SB_END
+}
+int sb_op_reflux_flux(sb_op* op, sb_field* div, sb_field* const flux[3], sb_field* const fine_flux[3], sb_op* finer_op)
+{
+    SB_TRY sameOp(op, {div}); sameOp(finer_op, {});
+    double *f[3], *ff[3]; fluxPtrs(op, flux, f); fluxPtrs(finer_op, fine_flux, ff);
+    OPF(op).refluxFlux(D(div), f, OPF(finer_op), ff);
+    SB_END
+}
+int sb_op_comp_divergence(sb_op* op, sb_field* div, sb_field* const flux[3], sb_field* const fine_flux[3], sb_op* finer_op)
+{
+    SB_TRY sameOp(op, {div});
+    double *f[3], *ff[3] = {nullptr, nullptr, nullptr};
+    fluxPtrs(op, flux, f);
+    if ((finer_op != nullptr) != (fine_flux != nullptr)) SB_FAIL("finer_op and fine_flux go together");
+    if (finer_op) { sameOp(finer_op, {}); fluxPtrs(finer_op, fine_flux, ff); }
+    OPF(op).compDivergence(D(div), f, finer_op ? finer_op->op : nullptr, ff);
+    SB_END
+}
+int sb_op_comp_gradient(sb_op* op, sb_field* const grad[3], sb_field* phi, sb_field* crse_phi, int homog_phys, int homog_cfi)
+{
+    SB_TRY sameOp(op, {phi}); (void)homog_phys;
+    double* g[3]; fluxPtrs(op, grad, g);
+    Op& o = OPF(op);
+    o.applyBCsAMR(D(phi), opOf(crse_phi), crse_phi ? D(crse_phi) : nullptr, homog_cfi != 0);  // PoissonOp.cpp:1505
+    const double smallReal = 1.0e4 * 2.220446049250313e-16;
+    const bool   scaleBeta = !(std::abs(o.beta - 1.0) <= smallReal * std::max(std::abs(o.beta), 1.0));
+    for (int d = 0; d < 3; ++d) {
+        if (o.dim == 2 && d == 1) continue;
+        k::gradient(o.st(), o.lay, g[d], D(phi), o.Jgup[d], d, 1.0 / o.dXi[d], o.beta, scaleBeta);
+    }
+    SB_END
+}
+int sb_op_get_patch(sb_op* op, int patch_lo[3], int patch_hi[3], int tile_lo[3], int tile_hi[3])
+{
+    SB_TRY REQ(op);
+    for (int d = 0; d < 3; ++d) {
+        if (patch_lo) patch_lo[d] = op->op->patch.lo[d];
+        if (patch_hi) patch_hi[d] = op->op->patch.hi[d];
+        if (tile_lo) tile_lo[d] = op->op->tile.lo[d];
+        if (tile_hi) tile_hi[d] = op->op->tile.hi[d];
+    }
+    SB_END
+}
+
+// ---- AMRHybridSolver ---------------------------------------------------------------------------
+int sb_amr_solver_create(sb_op* const* ops, int num_levels, int lmin, int lmax, const sb_mg_options* opt, sb_amr_solver** s)
+{
+    SB_TRY REQ(ops); REQ(opt); REQ(s);
+    std::vector<Op*> v(num_levels, nullptr);
+    for (int l = 0; l < num_levels; ++l)
+        if (ops[l]) {
+            if (!ops[l]->op->finalized) SB_FAIL("sb_op_finalize has not been called on every level");
+            v[l] = ops[l]->op;
+        }
+    std::unique_ptr<sb_amr_solver> p(new sb_amr_solver);
+    p->s.define(v, lmin, lmax, *opt);
+    v[lmax]->ctx->sync();
+    *s = p.release();
+    SB_END
+}
+int sb_amr_solver_destroy(sb_amr_solver* s) { SB_TRY delete s; SB_END }
+int sb_amr_solver_solve(sb_amr_solver* s, sb_field* const* phi, sb_field* const* rhs, int homog, int set_phi_to_zero, double metric,
+                        sb_solver_status* status)
+{
+    SB_TRY REQ(s); REQ(phi); REQ(rhs);
+    AMRSolver& a = s->s;
+    std::vector<double*>       vphi(a.lmax + 1, nullptr);
+    std::vector<const double*> vrhs(a.lmax + 1, nullptr);
+    for (int l = a.lbase; l <= a.lmax; ++l) {
+        if (!phi[l]) SB_FAIL("phi missing on a level");
+        if (phi[l]->f.op != a.ops[l]) SB_FAIL("phi does not live on this level's operator");
+        vphi[l] = D(phi[l]);
+        if (l >= a.lmin) {
+            if (!rhs[l]) SB_FAIL("rhs missing on a level");
+            if (rhs[l]->f.op != a.ops[l]) SB_FAIL("rhs does not live on this level's operator");
+            vrhs[l] = D(rhs[l]);
+        }
+    }
+    Op& top = *a.ops[a.lmax];
+    cudaEvent_t e0, e1;
+    SB_CUDA(cudaEventCreate(&e0)); SB_CUDA(cudaEventCreate(&e1));
+    SB_CUDA(cudaEventRecord(e0, top.st()));
+    SolverStatus st = a.solve(vphi, vrhs, homog != 0, set_phi_to_zero != 0, metric);
+    SB_CUDA(cudaEventRecord(e1, top.st()));
+    top.ctx->sync();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (status) {
+        std::memset(status, 0, sizeof(*status));
+        status->status         = st.status;
+        status->num_iters      = a.lastIters;
+        status->init_res_norm  = st.initResNorm;
+        status->final_res_norm = st.finalResNorm;
+        status->num_norms      = (int)std::min<size_t>(a.absResNorms.size(), SB_MAX_HISTORY);
+        for (int i = 0; i < status->num_norms; ++i) status->res_norms[i] = a.absResNorms[i];
+        status->solve_mode = 0;
+        status->max_depth  = a.lmax - a.lmin;
+        status->device_ms  = ms;
     }
     SB_END
 }

@@ -158,6 +158,18 @@ void Comm::exchangeDir(Op& op, double* phi, int d, int ext0, int ext1)
         if (op.side[d][s].kind == SIDE_NEIGHBOR) k::unpack_face(ctx->st, op.lay, phi, d, s, op.xbuf[d][s][1], ext0, ext1);
 }
 
+void Comm::sendRecv(const std::vector<Msg>& msgs, cudaStream_t st)
+{
+    if (msgs.empty()) return;
+    if (!st) st = ctx->st;
+    SB_NCCL(api().GroupStart());
+    for (const Msg& m : msgs) {
+        if (m.send) SB_NCCL(api().Send(m.p, m.n, kNcclFloat64, m.peer, comm, st));
+        else SB_NCCL(api().Recv(m.p, m.n, kNcclFloat64, m.peer, comm, st));
+    }
+    SB_NCCL(api().GroupEnd());
+}
+
 // ---------------------------------------------------------------------------------------------
 // Agglomeration traffic.  A tile region (valid cells, plus the far face for face-centred data) is
 // copied into a dense staging buffer with a device-to-device 3-D copy, sent to / received from

@@ -23,6 +23,10 @@ struct Comm {
     // rank 0, one tile elsewhere.  centering: SB_CELL or the face direction.
     void gatherTiles(const Op& dist, const double* tileField, const Lay* full, double* fullField, int centering, double* buf);
     void scatterTiles(const Op& dist, double* tileField, const Lay* full, const double* fullField, double* buf);
+    // One NCCL group of point-to-point messages (the motion items of a Copier between ranks): every rank issues
+    // its sends and receives in the same global order, so messages between a pair of ranks match up.
+    struct Msg { double* p; size_t n; int peer; bool send; };
+    void sendRecv(const std::vector<Msg>& msgs, cudaStream_t st = nullptr);
 };
 
 }  // namespace sb

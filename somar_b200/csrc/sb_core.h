@@ -118,16 +118,42 @@ inline SLay makeSLay(const Lay& L, int zg = 0)
 }
 
 // What a side of the tile touches.
-enum SideKind { SIDE_PHYS = 0, SIDE_PERIODIC_SELF = 1, SIDE_NEIGHBOR = 2 };
+// SIDE_CF: the side of a refined AMR level's patch that borders the coarser level.  Its ghosts are
+// either interpolated from coarse data (inhomogeneous, sb_amr_kernels.cu: cf_interp_k) or, in every
+// relaxation / residual of a level solve, filled by the homogeneous formula of
+// CFInterp::homogInterpAtCFI (Grade3_Calculus/CFInterp.cpp:429-515, CFInterpF.ChF:305-370).
+enum SideKind { SIDE_PHYS = 0, SIDE_PERIODIC_SELF = 1, SIDE_NEIGHBOR = 2, SIDE_CF = 3 };
 
-// Robin ghost fill constants of one side (BCToolsF.ChF:222-337): a = alpha/8 (2 cells) or
-// alpha/2 (1 cell), bb = beta/dx.
+// Ghost fill constants of one side.  SIDE_PHYS: Robin (BCToolsF.ChF:222-337), a = alpha/8 (2 cells)
+// or alpha/2 (1 cell), bb = beta/dx.  SIDE_CF: ghost = a p1 + bb p2 with a = c1 = 2(dxc-dxf)/(dxc+dxf),
+// bb = c2 = -(dxc-dxf)/(dxc+3dxf) (twoCells) or ghost = a p1 with a = 1 - 2dxf/(dxf+dxc).
 struct SideBC {
     int    kind;       // SideKind
-    int    twoCells;   // numValidCells >= 2 (BCTools.cpp:381)
+    int    twoCells;   // numValidCells >= 2 (BCTools.cpp:381; CFInterp.cpp:445,455)
     double a, bb;      // as above
     int    neighbor;   // rank (SIDE_NEIGHBOR)
 };
+// a side whose ghosts are a function of the interior cells next to it (refreshed once per relaxation
+// iteration, PoissonOp.cpp:1957-1962), as opposed to copies of other valid cells
+__host__ __device__ inline bool sideIsBC(int kind) { return kind == SIDE_PHYS || kind == SIDE_CF; }
+// value of the ghost cell from the first (p0) and second (p1) interior cell
+__host__ __device__ inline double sideGhost(const SideBC& bc, double p0, double p1)
+{
+    if (bc.kind == SIDE_PHYS) {
+        if (bc.twoCells) {  // BCToolsF.ChF:313-331 (homogeneous branch)
+            const double cg = 3.0 * bc.a + bc.bb;
+            const double c0 = 6.0 * bc.a - bc.bb;
+            const double c1 = -1.0 * bc.a;
+            return -(c0 * p0 + c1 * p1) / cg;
+        }
+        const double cg = bc.a + bc.bb;  // BCToolsF.ChF:255-270
+        const double c0 = bc.a - bc.bb;
+        return -(c0 * p0) / cg;
+    }
+    // SIDE_CF: CFInterpF.ChF:305-336 (quadratic) / :340-370 (linear)
+    if (bc.twoCells) return bc.a * p0 + bc.bb * p1;
+    return bc.a * p0;
+}
 
 // Per-depth coefficient pointers handed to kernels.
 struct Coef {
@@ -238,8 +264,9 @@ void add_vertical_extrusion(cudaStream_t st, const Lay& L, const Lay& F, double*
 
 // Reductions.  op: 0 max|x|, 1 sum|x|, 2 sum x^2, 3 sum x*y, 4 sum (J*dv)*x and sum J*dv (2 outputs).
 // One result per box (or 2 for op 4) lands in out[] (device); partial is scratch.
+// mask (may be null): a box in tile-local indices whose cells count as zero (AMRNormLevel).
 void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, const double* x, const double* y,
-                  double dv, double* partial, double* out);
+                  double dv, double* partial, double* out, const Box3* mask = nullptr);
 int  reduce_partial_len(int nboxes);
 }  // namespace k
 

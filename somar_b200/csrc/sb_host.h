@@ -60,6 +60,29 @@ struct MapSpec {
 };
 
 struct Op;
+struct CFLink;  // sb_amr.cpp
+
+// A DisjointBoxLayout of another AMR level, as PoissonOp's constructor receives it (PoissonOp.cpp:33-43).
+struct LevelGrids {
+    std::vector<Box3> boxes;
+    std::vector<int>  rank;
+    Box3              domain{{0, 0, 0}, {-1, -1, -1}};
+    bool closed() const { return !boxes.empty(); }
+};
+
+// Chombo's Copier at tile granularity (BoxTools/Copier.cpp): regions of a source array that land in a destination
+// array, possibly on another rank and on another AMR level.  Every rank builds the same item list.
+struct LevelCopier {
+    struct Item { int srcRank, dstRank; Box3 box; size_t off; };
+    std::vector<Item> items;
+    size_t            sendLen = 0, recvLen = 0;  // staging (doubles) this rank needs
+    double *          sendBuf = nullptr, *recvBuf = nullptr;
+    // src[r] / dst[r]: the boxes (global indices) rank r holds / wants
+    void define(int rank, const std::vector<std::vector<Box3>>& src, const std::vector<std::vector<Box3>>& dst);
+    // dst(box) = src(box) (mode 0) or dst(box) += scale * src(box) (mode 1, the AddOp of AnisotropicFluxRegister.cpp:577-620)
+    void exec(Context* ctx, const Lay& srcLay, const double* src, const Lay& dstLay, double* dst, int mode = 0, double scale = 1.0);
+    ~LevelCopier();
+};
 
 struct Field {
     Op*     op;
@@ -82,6 +105,15 @@ struct Op {
     MapSpec  map;
     double   bcAlpha[3][2], bcBeta[3][2];
     int      depth = 0;
+    // AMR (PoissonOp.cpp:83-120): the grids of the next coarser level, if any.  A refined level's boxes form a
+    // rectangular patch that need not cover the domain; tile sides inside the domain without a neighbouring tile
+    // are coarse-fine sides (SIDE_CF).
+    LevelGrids crseGrids;
+    bool     refined = false;        // m_crseAMRGrids.isClosed()
+    int      crseRef[3] = {1, 1, 1};  // refinement ratio to the coarser AMR level (depth 0 only)
+    double   amrCrseDXi[3] = {0, 0, 0};  // m_amrCrseDXi: the same at every MG depth (PoissonOp.cpp:345)
+    Box3     patch;                  // bounding box of all boxes of this level (= domain on a base level)
+    std::shared_ptr<CFLink> cf;      // coarse-fine interpolation, inter-level copiers, fine flux register (depth 0 of a refined level)
     bool     flatZ = false;  // horizontal-only operator of the leptic solver (PoissonOp.cpp:411-505): one layer, no vertical coupling
 
     std::vector<Box3> boxes;    // all ranks
@@ -177,11 +209,29 @@ struct Op {
     void   scaleVelocity(double* const vel[3], int ghost, bool toAdvecting);
     void   checkPivot();
     double* alloc() const;
+
+    // ---- AMRMGOperator surface (Elliptic/AMRMGOperator.H:43-218, PoissonOp.cpp:1156-1478); sb_amr.cpp ----
+    void   defineCF();  // m_cfInterp.define(m_grids, m_dXi, m_crseAMRGrids) + copiers (PoissonOp.cpp:118-120)
+    // PoissonOp::applyBCs(phi, crsePhiPtr, time, homogPhys, homogCFI) (PoissonOp.cpp:726-763)
+    void   applyBCsAMR(double* phi, const Op* crseOp, const double* crsePhi, bool homogCFI);
+    void   interpAtCFI(double* phi, const Op& crseOp, const double* crsePhi);  // CFInterp.cpp:387-416 -> MappedQuadCFInterp
+    void   AMROperatorNF(double* lhs, double* phi, const Op& crseOp, const double* crsePhi);
+    void   AMROperatorNC(double* lhs, Op& fineOp, double* finePhi, double* phi);
+    void   AMROperator(double* lhs, Op& fineOp, double* finePhi, double* phi, const Op& crseOp, const double* crsePhi);
+    // rhs - L[phi] for whichever neighbours exist (AMRMGOperator.H:107-175); fineOp / crseOp may be null
+    void   AMRResidual(double* res, Op* fineOp, double* finePhi, double* phi, const Op* crseOp, const double* crsePhi,
+                       const double* rhs);
+    void   reflux(double* res, Op& fineOp, double* finePhi, const double* phi);          // PoissonOp.cpp:1333-1418
+    void   refluxFlux(double* div, double* const flux[3], Op& fineOp, double* const fineFlux[3]);  // :1425-1477
+    double AMRNormLevel(const double* res, const Op* fineOp, int p);                      // :1225-1286
+    void   getFlux(double* const flux[3], const double* phi);                             // :1295-1326, all boxes
+    void   compDivergence(double* div, double* const flux[3], Op* fineOp, double* const fineFlux[3]);  // :1618-1631
 };
 
+// partial: the boxes form a rectangular patch inside the domain (refined AMR level) instead of covering it
 void planDecomposition(const std::vector<Box3>& boxes, const std::vector<int>& boxRank, const Box3& domain,
                        const int periodic[3], int rank, int nranks, std::vector<Box3>& tiles, std::vector<int>& local,
-                       SideBC side[3][2]);
+                       SideBC side[3][2], bool partial = false);
 std::vector<std::array<int, 3>> createMGRefScheduleBoxes(int dim, const Box3& domain, const double dXi[3],
                                                          const std::vector<Box3>& boxes, int maxDepth, bool horizStrategy,
                                                          bool doVertCoarsening);
@@ -189,7 +239,7 @@ std::vector<std::array<int, 3>> createMGRefScheduleBoxes(int dim, const Box3& do
 // Stencil records of the quadratic coarse-fine ghost interpolation for one side of one fine box (sb_amr_plan.cpp)
 void planCFStencils(const Box3& dom, const int periodic[3], const int ref[3], const std::vector<Box3>& fineBoxes, int box, int dir,
                     int side, std::vector<int>& cells, std::vector<double>& wFirst, std::vector<double>& wSecond,
-                    std::vector<double>& wMixed);
+                    std::vector<double>& wMixed, int dim = 3, const std::vector<Box3>* crseBoxes = nullptr);
 
 // SemicoarseningStrategy / HorizCoarseningStrategy (Elliptic/MGCoarseningStrategy.cpp)
 std::vector<std::array<int, 3>> createMGRefSchedule(const Op& top, int maxDepth, bool horizStrategy, bool doVertCoarsening);
@@ -288,8 +338,29 @@ struct HybridSolver {
     SolverStatus solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double convergenceMetric);
 };
 
+// Elliptic::AMRHybridSolver (Elliptic/AMRHybridSolver.cpp): composite solve over AMR levels lmin..lmax; the smoothers
+// of its V-cycle are whole level solves (LevelHybridSolver), the levels talk through the operators' AMR interface.
+struct AMRSolver {
+    std::vector<Op*>                           ops;
+    int                                        lbase = 0, lmin = 0, lmax = 0;
+    sb_mg_options                              opt;
+    std::vector<std::unique_ptr<HybridSolver>> hybrid;
+    std::vector<double*>                       ve, vr, scratch;  // m_ve, m_vr, m_vScratchPhi (m_vResC lives in the level's CFLink)
+    SolverStatus                               status;
+    std::vector<double>                        absResNorms;
+    int                                        lastIters = 0;
+    void define(const std::vector<Op*>& ops, int lmin, int lmax, const sb_mg_options& o);
+    ~AMRSolver();
+    SolverStatus solve(std::vector<double*>& phi, const std::vector<const double*>& rhs, bool homog, bool setPhiToZero, double metric);
+    void   amrVCycle_residualEq(std::vector<double*>& phi, std::vector<double*>& rhs, int lev);
+    double computeAMRResidual(std::vector<double*>& res, const std::vector<double*>& phi, const std::vector<const double*>& rhs,
+                              bool computeNorm);
+    void   computeAMRResidualLevel(double* res, double* finePhi, double* phi, const double* crsePhi, const double* rhs, int lev);
+};
+
 }  // namespace sb
 
+struct sb_amr_solver { sb::AMRSolver s; };
 struct sb_context { sb::Context c; sb_context(int d, int r, int n) : c(d, r, n) {} };
 struct sb_op { sb::Op* op; bool owned; };
 struct sb_field { sb::Field f; sb_field(sb::Op* op, int c) : f(op, c) {} };

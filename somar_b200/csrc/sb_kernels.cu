@@ -115,19 +115,8 @@ __global__ void fill_ghosts_dir_k(Lay L, double* phi, int dir, SideBC lo, SideBC
         const long long g  = side ? base + sn * nn : base - sn;             // ghost
         const long long p0 = side ? base + sn * (nn - 1) : base;            // first interior
         const long long p1 = side ? base + sn * (nn - 2) : base + sn;       // second interior
-        if (bc.kind == SIDE_PHYS) {
-            if (bc.twoCells) {
-                // BCToolsF.ChF:313-331 (homogeneous branch)
-                const double cg = 3.0 * bc.a + bc.bb;
-                const double c0 = 6.0 * bc.a - bc.bb;
-                const double c1 = -1.0 * bc.a;
-                phi[g]          = -(c0 * phi[p0] + c1 * phi[p1]) / cg;
-            } else {
-                // BCToolsF.ChF:255-270
-                const double cg = bc.a + bc.bb;
-                const double c0 = bc.a - bc.bb;
-                phi[g]          = -(c0 * phi[p0]) / cg;
-            }
+        if (sideIsBC(bc.kind)) {
+            phi[g] = sideGhost(bc, phi[p0], phi[p1]);
         } else if (bc.kind == SIDE_PERIODIC_SELF) {
             phi[g] = side ? phi[base] : phi[base + sn * (nn - 1)];
         }
@@ -191,7 +180,7 @@ void extrap_domain_edges(cudaStream_t st, const Lay& L, double* phi, const SideB
             if (dim == 2 && (a == 1 || b == 1)) continue;
             for (int as = 0; as < 2; ++as)
                 for (int bs = 0; bs < 2; ++bs) {
-                    if (bc[a][as].kind != SIDE_PHYS || bc[b][bs].kind != SIDE_PHYS) continue;
+                    if (!sideIsBC(bc[a][as].kind) || !sideIsBC(bc[b][bs].kind)) continue;
                     const int c  = 3 - a - b;
                     const int nc = c == 0 ? L.nx : (c == 1 ? L.ny : L.nz);
                     extrap_edge_k<<<(nc + 127) / 128, 128, 0, st>>>(L, phi, a, as, b, bs);
@@ -1020,8 +1009,10 @@ __device__ __forceinline__ double block_reduce(double v, int op, double* sm)
 // Threads are arranged as bxw columns (a power of two >= 32 covering the box width, at most the
 // block) by blockDim.x / bxw rows, and every thread keeps four rows in flight; the assignment of
 // cells to threads is fixed, so the result is reproducible run to run.
+// mlo / mhi: a box (tile-local indices, empty if mlo0 > mhi0) whose cells count as zero -- the cells
+// covered by the finer AMR level in PoissonOp::AMRNormLevel (PoissonOp.cpp:1250-1276).
 __global__ void reduce1_k(Lay L, BoxList bl, int op, const double* __restrict__ x, const double* __restrict__ y, double dv,
-                          double* __restrict__ partial, int bxw)
+                          double* __restrict__ partial, int bxw, int mlo0, int mlo1, int mlo2, int mhi0, int mhi1, int mhi2)
 {
     __shared__ double sm[32];
     const int bx = blockIdx.y, ch = blockIdx.x;
@@ -1046,9 +1037,11 @@ __global__ void reduce1_k(Lay L, BoxList bl, int op, const double* __restrict__ 
                 const long long r = r0 + (long long)RCH * by * u;
                 v[u] = 0.0; w[u] = 0.0;
                 if (r < rows) {
-                    const long long q = L.idx(lo0 + i, lo1 + (int)(r % n1), lo2 + (int)(r / n1));
+                    const int       jj = lo1 + (int)(r % n1), kk = lo2 + (int)(r / n1);
+                    const long long q  = L.idx(lo0 + i, jj, kk);
                     v[u] = x[q];
                     if (two) w[u] = y[q];
+                    if (lo0 + i >= mlo0 && lo0 + i <= mhi0 && jj >= mlo1 && jj <= mhi1 && kk >= mlo2 && kk <= mhi2) v[u] = 0.0;
                 }
             }
 #pragma unroll
@@ -1081,11 +1074,14 @@ __global__ void reduce2_k(int op, const double* __restrict__ partial, double* __
 }
 int  reduce_partial_len(int nboxes) { return 2 * RCH * nboxes; }
 void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, const double* x, const double* y, double dv,
-                  double* partial, double* out)
+                  double* partial, double* out, const Box3* mask)
 {
     int bxw = 32;
     while (bxw < 256 && bxw < boxes.maxnx) bxw <<= 1;
-    reduce1_k<<<dim3(RCH, boxes.n), 256, 0, st>>>(L, boxes, op, x, y, dv, partial, bxw);
+    const Box3 none{{1, 1, 1}, {0, 0, 0}};
+    const Box3& m = mask ? *mask : none;
+    reduce1_k<<<dim3(RCH, boxes.n), 256, 0, st>>>(L, boxes, op, x, y, dv, partial, bxw, m.lo[0], m.lo[1], m.lo[2], m.hi[0], m.hi[1],
+                                                  m.hi[2]);
     LAUNCHED();
     reduce2_k<<<boxes.n, 64, 0, st>>>(op, partial, out);
     LAUNCHED();

@@ -30,6 +30,10 @@ Op::Op(const Op& f, HorizTag) : ctx(f.ctx)
     std::memcpy(dXi, f.dXi, sizeof(dXi));
     dXi[2]      = 1.0;
     periodic[2] = 0;
+    // a refined patch keeps its coarse-fine sides in the horizontal problem (PoissonOp.cpp:1649-1672, 469-479)
+    refined = f.refined;
+    for (int d = 0; d < 3; ++d) amrCrseDXi[d] = f.amrCrseDXi[d];
+    amrCrseDXi[2] = 1.0;  // flat domains on both levels: ratio 1, dXi_z = 1
     domain      = f.domain;
     domain.lo[2] = domain.hi[2] = 0;
     boxRank = f.boxRank;

@@ -151,19 +151,9 @@ __device__ __forceinline__ void ghost_one(const SLay& S, double* s0, double* s1,
     p0[a] = side ? nn - 1 : 0;      p0[b] = t;
     p1[a] = side ? nn - 2 : 1;      p1[b] = t;
     w[a]  = side ? 0 : nn - 1;      w[b] = t;
-    if (bc.kind == SIDE_PHYS) {
+    if (sideIsBC(bc.kind)) {
         if (!physToo) return;
-        double v;
-        if (bc.twoCells) {
-            const double cg = 3.0 * bc.a + bc.bb;
-            const double c0 = 6.0 * bc.a - bc.bb;
-            const double c1 = -1.0 * bc.a;
-            v = -(c0 * *scell(S, s0, s1, p0[0], p0[1], k) + c1 * *scell(S, s0, s1, p1[0], p1[1], k)) / cg;
-        } else {
-            const double cg = bc.a + bc.bb;
-            const double c0 = bc.a - bc.bb;
-            v = -(c0 * *scell(S, s0, s1, p0[0], p0[1], k)) / cg;
-        }
+        const double v = sideGhost(bc, *scell(S, s0, s1, p0[0], p0[1], k), *scell(S, s0, s1, p1[0], p1[1], k));
         *scell(S, s0, s1, g[0], g[1], k) = v;
     } else if (bc.kind == SIDE_PERIODIC_SELF) {
         *scell(S, s0, s1, g[0], g[1], k) = *scell(S, s0, s1, w[0], w[1], k);
@@ -184,7 +174,7 @@ __global__ void fill_ghosts_split_k(SLay S, double* s0, double* s1, SideBC xlo, 
 }
 void fill_ghosts_split(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC bc[3][2], int dim, bool physToo)
 {
-    auto idle = [&](const SideBC& b) { return b.kind == SIDE_NEIGHBOR || b.kind < 0 || (b.kind == SIDE_PHYS && !physToo); };
+    auto idle = [&](const SideBC& b) { return b.kind == SIDE_NEIGHBOR || b.kind < 0 || (sideIsBC(b.kind) && !physToo); };
     const bool doY = dim == 3;
     if (idle(bc[0][0]) && idle(bc[0][1]) && (!doY || (idle(bc[1][0]) && idle(bc[1][1])))) return;
     const int n = S.ny + (doY ? S.nx : 0);
@@ -203,19 +193,9 @@ __global__ void fill_ghosts_split_z_k(SLay S, double* s0, double* s1, SideBC lo,
     for (int side = 0; side < 2; ++side) {
         const SideBC& bc = side ? hi : lo;
         const int g = side ? S.nz : -1, p0 = side ? S.nz - 1 : 0, p1 = side ? S.nz - 2 : 1, wv = side ? 0 : S.nz - 1;
-        if (bc.kind == SIDE_PHYS) {
+        if (sideIsBC(bc.kind)) {
             if (!physToo) continue;
-            double v;
-            if (bc.twoCells) {
-                const double cg = 3.0 * bc.a + bc.bb;
-                const double c0 = 6.0 * bc.a - bc.bb;
-                const double c1 = -1.0 * bc.a;
-                v = -(c0 * a[S.idx(i, j, p0)] + c1 * a[S.idx(i, j, p1)]) / cg;
-            } else {
-                const double cg = bc.a + bc.bb;
-                const double c0 = bc.a - bc.bb;
-                v = -(c0 * a[S.idx(i, j, p0)]) / cg;
-            }
+            const double v = sideGhost(bc, a[S.idx(i, j, p0)], a[S.idx(i, j, p1)]);
             a[S.idx(i, j, g)] = v;
         } else if (bc.kind == SIDE_PERIODIC_SELF) {
             a[S.idx(i, j, g)] = a[S.idx(i, j, wv)];
@@ -224,7 +204,7 @@ __global__ void fill_ghosts_split_z_k(SLay S, double* s0, double* s1, SideBC lo,
 }
 void fill_ghosts_split_z(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC& lo, const SideBC& hi, bool physToo)
 {
-    auto idle = [&](const SideBC& b) { return b.kind == SIDE_NEIGHBOR || b.kind < 0 || (b.kind == SIDE_PHYS && !physToo); };
+    auto idle = [&](const SideBC& b) { return b.kind == SIDE_NEIGHBOR || b.kind < 0 || (sideIsBC(b.kind) && !physToo); };
     if (S.zg == 0 || (idle(lo) && idle(hi))) return;
     const dim3 b(64, 4, 1);
     fill_ghosts_split_z_k<<<dim3((S.nx + 63) / 64, (S.ny + 3) / 4), b, 0, st>>>(S, s0, s1, lo, hi, physToo ? 1 : 0);

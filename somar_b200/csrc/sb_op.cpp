@@ -188,6 +188,27 @@ Op::Op(Context* c, const sb_level_desc& d) : ctx(c)
         boxRank[b] = d.box_rank ? d.box_rank[b] : 0;
         if (boxRank[b] < 0 || boxRank[b] >= ctx->nranks) SB_FAIL("box_rank out of range");
     }
+    // AMR stuff (PoissonOp.cpp:83-93, 118-120)
+    if (d.num_crse_boxes > 0) {
+        if (!d.crse_box_lo || !d.crse_box_hi) SB_FAIL("num_crse_boxes > 0 without crse_box_lo / crse_box_hi");
+        refined = true;
+        crseGrids.boxes.resize(d.num_crse_boxes);
+        crseGrids.rank.resize(d.num_crse_boxes);
+        for (int b = 0; b < d.num_crse_boxes; ++b) {
+            for (int i = 0; i < 3; ++i) { crseGrids.boxes[b].lo[i] = d.crse_box_lo[3 * b + i]; crseGrids.boxes[b].hi[i] = d.crse_box_hi[3 * b + i]; }
+            crseGrids.rank[b] = d.crse_box_rank ? d.crse_box_rank[b] : 0;
+            if (crseGrids.rank[b] < 0 || crseGrids.rank[b] >= ctx->nranks) SB_FAIL("crse_box_rank out of range");
+        }
+        for (int i = 0; i < 3; ++i) {
+            crseGrids.domain.lo[i] = d.crse_domain_lo[i]; crseGrids.domain.hi[i] = d.crse_domain_hi[i];
+            // calculateRefinementRatio(crseDomBox, domBox)
+            const int nc = crseGrids.domain.size(i), nf = domain.size(i);
+            if (nc <= 0 || nf % nc != 0) SB_FAIL("the domain is not a refinement of the coarser AMR level's domain");
+            crseRef[i] = nf / nc;
+            if (crseGrids.domain.lo[i] * crseRef[i] != domain.lo[i]) SB_FAIL("the domain is not a refinement of the coarser AMR level's domain");
+            amrCrseDXi[i] = dXi[i] * (double)crseRef[i];
+        }
+    }
     setupLayout();
     J = alloc();
     for (int i = 0; i < 3; ++i) Jgup[i] = alloc();
@@ -199,7 +220,7 @@ Op::Op(Context* c, const sb_level_desc& d) : ctx(c)
 // (BoxTools/Copier.cpp:784); here ranks own rectangles of boxes, so it is per tile.
 void planDecomposition(const std::vector<Box3>& boxes, const std::vector<int>& boxRank, const Box3& domain,
                        const int periodic[3], int rank, int nr, std::vector<Box3>& tiles, std::vector<int>& local,
-                       SideBC side[3][2])
+                       SideBC side[3][2], bool partial)
 {
     tiles.assign(nr, Box3{{0, 0, 0}, {-1, -1, -1}});
     std::vector<long long> pts(nr, 0);
@@ -221,7 +242,16 @@ void planDecomposition(const std::vector<Box3>& boxes, const std::vector<int>& b
         if (pts[r] != tiles[r].numPts()) SB_FAIL("the boxes of one rank must tile a rectangle (horizontal box decomposition)");
         total += pts[r];
     }
-    if (total != domain.numPts()) SB_FAIL("boxes do not cover the domain (single-level operator)");
+    if (!partial) {
+        if (total != domain.numPts()) SB_FAIL("boxes do not cover the domain (single-level operator)");
+    } else {
+        Box3 patch = tiles[0];
+        for (int r = 1; r < nr; ++r)
+            for (int i = 0; i < 3; ++i) { patch.lo[i] = std::min(patch.lo[i], tiles[r].lo[i]); patch.hi[i] = std::max(patch.hi[i], tiles[r].hi[i]); }
+        if (total != patch.numPts()) SB_FAIL("the boxes of a refined AMR level must form one rectangular patch");
+        for (int i = 0; i < 3; ++i)
+            if (patch.lo[i] < domain.lo[i] || patch.hi[i] > domain.hi[i]) SB_FAIL("refined patch outside the domain");
+    }
     const Box3& tile = tiles[rank];
 
     // What does each side of the tile touch?
@@ -244,16 +274,25 @@ void planDecomposition(const std::vector<Box3>& boxes, const std::vector<int>& b
                     if (o != d && (t.lo[o] != tile.lo[o] || t.hi[o] != tile.hi[o])) ok = false;
                 if (ok) found = r;
             }
-            if (found < 0) SB_FAIL("rank tiles do not form a process grid (no neighbour across a tile side)");
+            if (found < 0) {
+                if (!partial) SB_FAIL("rank tiles do not form a process grid (no neighbour across a tile side)");
+                // no tile of this level across the side: the coarser AMR level is there (a patch that reaches a
+                // periodic boundary without spanning the domain borders coarse cells through the wrap as well)
+                sd.kind = SIDE_CF;
+                continue;
+            }
             sd.kind = SIDE_NEIGHBOR; sd.neighbor = found;
         }
 }
 
 void Op::setupLayout()
 {
-    planDecomposition(boxes, boxRank, domain, periodic, ctx->rank, ctx->nranks, tiles, local, side);
+    planDecomposition(boxes, boxRank, domain, periodic, ctx->rank, ctx->nranks, tiles, local, side, refined);
     tile = tiles[ctx->rank];
     lay  = makeLay(tile);
+    patch = tiles[0];
+    for (const Box3& t : tiles)
+        for (int i = 0; i < 3; ++i) { patch.lo[i] = std::min(patch.lo[i], t.lo[i]); patch.hi[i] = std::max(patch.hi[i], t.hi[i]); }
     if (flatZ) side[2][0].kind = side[2][1].kind = -1;  // inactive direction: no BCs, no exchange (activeSides, PoissonOp.cpp:483-487)
 
     // device-side box list (tile-local indices) and reduction buffers
@@ -355,6 +394,8 @@ void Op::fillMetricFromMap()
 Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
 {
     dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth + 1; flatZ = f.flatZ;
+    refined = f.refined;  // the coarse-fine sides stay (coarsened CFRegion, PoissonOp.cpp:392-396), with homogeneous ghosts only
+    std::memcpy(amrCrseDXi, f.amrCrseDXi, sizeof(amrCrseDXi));  // not scaled (PoissonOp.cpp:345)
     std::memcpy(periodic, f.periodic, sizeof(periodic));
     std::memcpy(bcAlpha, f.bcAlpha, sizeof(bcAlpha));
     std::memcpy(bcBeta, f.bcBeta, sizeof(bcBeta));
@@ -386,6 +427,8 @@ Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
 Op::Op(Context* single, const Op& f) : ctx(single)
 {
     dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth; flatZ = f.flatZ;
+    refined = f.refined;
+    std::memcpy(amrCrseDXi, f.amrCrseDXi, sizeof(amrCrseDXi));
     std::memcpy(periodic, f.periodic, sizeof(periodic));
     std::memcpy(bcAlpha, f.bcAlpha, sizeof(bcAlpha));
     std::memcpy(bcBeta, f.bcBeta, sizeof(bcBeta));
@@ -438,6 +481,21 @@ void Op::cacheMatrixElements()
     for (int d = 0; d < 3; ++d)
         for (int s = 0; s < 2; ++s) {
             SideBC& sd = side[d][s];
+            if (sd.kind == SIDE_CF && !(dim == 2 && d == 1) && !(flatZ && d == 2)) {
+                // CFInterp::homogInterpAtCFI(phi, m_dXi, m_amrCrseDXi, m_cfiIter) (PoissonOp.cpp:745, CFInterp.cpp:429-515):
+                // quadratic through the ghost's two interior neighbours and a zero coarse value, linear for one-cell boxes
+                int minSize = std::numeric_limits<int>::max();
+                for (int lb : local) {
+                    const Box3& b = boxes[lb];
+                    if ((s ? b.hi[d] == tile.hi[d] : b.lo[d] == tile.lo[d])) minSize = std::min(minSize, b.size(d));
+                }
+                const double dxf = dXi[d], dxc = amrCrseDXi[d];
+                if (!(dxc > 0.0)) SB_FAIL("coarse-fine side without a coarser AMR level");
+                sd.twoCells = minSize > 1;
+                if (sd.twoCells) { sd.a = 2.0 * (dxc - dxf) / (dxc + dxf); sd.bb = -(dxc - dxf) / (dxc + 3.0 * dxf); }
+                else { sd.a = 1.0 - 2.0 * dxf / (dxf + dxc); sd.bb = 0.0; }
+                continue;
+            }
             if (sd.kind != SIDE_PHYS || (dim == 2 && d == 1) || (flatZ && d == 2)) continue;
             const int face = s ? domain.hi[d] + 1 : domain.lo[d];
             const double dx = map.dxdXi(d, dXi[d], face, 1, 1, dXi[d])[0];
@@ -613,6 +671,7 @@ void Op::finalize()
     // RealCmp::neq(alpha, 0) (SOMAR_Constants.H:94-105)
     const bool alphaIsZero = std::abs(alpha - 0.0) <= smallReal * std::max(std::abs(alpha), 0.0);
     hasNullSpace = alphaIsZero ? checkForNullSpace() : false;
+    defineCF();
     finalized    = true;
 }
 
@@ -626,18 +685,21 @@ void Op::exchange(double* phi)
     for (int d = 0; d < 3; ++d)
         for (int s = 0; s < 2; ++s) {
             only[d][s] = side[d][s];
-            if (only[d][s].kind == SIDE_PHYS) only[d][s].kind = -1;
+            if (sideIsBC(only[d][s].kind)) only[d][s].kind = -1;
             if (only[d][s].kind == SIDE_PERIODIC_SELF) any = true;
         }
     if (any) k::fill_ghosts(st(), lay, phi, only, dim);
     if (ctx->nranks > 1) ctx->comm->exchangeFaces(*this, phi);
 }
 
-// PoissonOp::applyBCs (PoissonOp.H:139-163, PoissonOp.cpp:726-763): exchange, (no CFI on a
-// single level), physical BCs.
+// PoissonOp::applyBCs (PoissonOp.H:139-163, PoissonOp.cpp:726-763): exchange, homogeneous coarse-fine
+// ghosts on the sides of a refined patch (CFInterp::homogInterpAtCFI), physical BCs.  The boundary
+// conditions of this ABI are Robin pairs (alpha, beta) with no boundary data (the projector's
+// HomogNeumBC, AMRNSLevelBC.cpp:48-52), so a_homogPhysBCs = false gives the same ghosts: both values
+// are accepted (AMRNSLevel::projectPredict passes false, AMRNSLevelProject.cpp:123,147).
 void Op::applyBCs(double* phi, bool homog)
 {
-    if (!homog) SB_FAIL("inhomogeneous BCs are not part of the projection path (HomogNeumBC)");
+    (void)homog;
     k::fill_ghosts(st(), lay, phi, side, dim);
     if (ctx->nranks > 1) ctx->comm->exchangeFaces(*this, phi);
 }

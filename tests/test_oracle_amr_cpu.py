@@ -23,7 +23,8 @@ from _oracle import have_ref, run_ref
 from amr_cases import AMR_CASES, composite_integral, composite_rhs, fine_shape, ref_kwargs_amr
 
 pytestmark = pytest.mark.skipif(not (have_ref(3) and have_ref(2)), reason="oracle/_ref/d{2,3}/somar_ref not built")
-CASES3D = sorted(n for n, c in AMR_CASES.items() if len(c["nx"]) == 3)
+CASES3D = sorted(n for n, c in AMR_CASES.items() if len(c["nx"]) == 3 and "region2" not in c)
+TWO_LEVEL = sorted(n for n, c in AMR_CASES.items() if "region2" not in c)
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -73,7 +74,7 @@ def test_cf_interpolation_reproduces_quadratics(name):
     assert checked >= 5
 
 
-@pytest.mark.parametrize("name", sorted(AMR_CASES))
+@pytest.mark.parametrize("name", TWO_LEVEL)
 def test_two_level_solve_converges_and_is_conservative(name):
     c = AMR_CASES[name]
     r0, r1 = composite_rhs(c, 3)
@@ -103,16 +104,7 @@ def test_amr_oracle_reproduces_golden(path):
     assert np.array_equal(r["phi1"], z["phi1"].ravel(order="F"))
 
 
-# Patches that stress the one-sided / order-dropping branches of the coarse derivative stencils
-# (used for the interpolation spec only, not solved).
-SPEC_CASES = dict({n: AMR_CASES[n] for n in CASES3D}, **{
-    "corner": dict(nx=(16, 16, 16), L=(2.0, 1.0, 1.0), offset=(0, 0, -16), max_box=(8, 8, 0), bf=4, periodic=(0, 0, 0), relax=5,
-                   ref=(2, 2, 2), region=(0, 0, -16, 7, 5, -9), fine_max_box=16),
-    "thin": dict(nx=(16, 16, 16), L=(1.0, 1.0, 1.0), offset=(0, 0, 0), max_box=(8, 8, 0), bf=4, periodic=(0, 0, 0), relax=5,
-                 ref=(2, 2, 2), region=(4, 6, 4, 11, 7, 11), fine_max_box=8),
-    "near_wall": dict(nx=(16, 16, 16), L=(1.0, 1.0, 1.0), offset=(0, 0, 0), max_box=(8, 8, 0), bf=4, periodic=(0, 0, 0), relax=5,
-                      ref=(4, 2, 2), region=(1, 1, 1, 8, 14, 10), fine_max_box=16),
-})
+from amr_cases import SPEC_CASES  # noqa: E402
 
 
 @pytest.mark.parametrize("name", sorted(SPEC_CASES))
@@ -167,3 +159,22 @@ def test_composite_operator_numpy_spec_matches_the_reference(name):
     uncovered[region_slices(c)] = False
     assert np.max(np.abs(m1 - R1)) <= 1e-13 * np.max(np.abs(R1))
     assert np.max(np.abs(m0 - R0)[uncovered]) <= 1e-13 * np.max(np.abs(R0))
+
+
+THREE_LEVEL = sorted(n for n, c in AMR_CASES.items() if "region2" in c)
+
+
+@pytest.mark.parametrize("name", THREE_LEVEL)
+def test_three_level_solve_converges(name):
+    """Base level + two nested refined patches (the BuoyantVortexRing deck's hierarchy in miniature): the middle level
+    goes through AMRResidual with both neighbours (AMRHybridSolver.cpp:603-626)."""
+    from amr_cases import composite_rhs_levels, ref_kwargs_amr3
+    c = AMR_CASES[name]
+    rhs, _ = composite_rhs_levels(c, 3)
+    r = run_ref("amr", inp=rhs, **ref_kwargs_amr3(c))
+    assert int(r.kv["numLevels"]) == 3 and int(r.kv["status"]) == 1
+    norms = r["amrLevelNorms"].reshape(-1, 3)
+    comp = np.sqrt((norms ** 2).sum(axis=1))
+    assert comp[-1] <= 1e-6 * comp[0]
+    for l in range(3):
+        assert r.kv[f"res_finalNorm{l}"] <= 2e-6 * comp[0]
