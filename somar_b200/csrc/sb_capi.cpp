@@ -19,6 +19,27 @@ static thread_local std::string g_err;
     catch (...) { g_err = "unknown error"; return 1; }
 #define REQ(p) if (!(p)) SB_FAIL("null argument: " #p)
 
+// Every entry point runs on its context's device whatever the caller's current device is (a host that
+// drives several GPUs from one thread), and restores the caller's device on the way out.
+namespace {
+struct DeviceGuard {
+    int prev = -1, dev;
+    explicit DeviceGuard(int d) : dev(d)
+    {
+        if (dev < 0) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+int devOf(sb_context* c) { return c ? c->c.device : -1; }
+int devOf(sb_op* o) { return o && o->op ? o->op->ctx->device : -1; }
+int devOf(sb_field* f) { return f && f->f.op ? f->f.op->ctx->device : -1; }
+int devOf(sb_solver* s) { return s && s->s.op ? s->s.op->ctx->device : -1; }
+int devOf(sb_amr_solver* s) { return s && !s->s.ops.empty() && s->s.ops[s->s.lmax] ? s->s.ops[s->s.lmax]->ctx->device : -1; }
+}  // namespace
+#define DEVG(h) DeviceGuard devg__(devOf(h));
+
 extern "C" {
 
 const char* sb_last_error(void) { return g_err.c_str(); }
@@ -31,13 +52,13 @@ int sb_context_create(sb_context** ctx, int device, int rank, int nranks)
     *ctx = new sb_context(device, rank, nranks);
     SB_END
 }
-int sb_context_destroy(sb_context* ctx) { SB_TRY delete ctx; SB_END }
-int sb_context_sync(sb_context* ctx) { SB_TRY REQ(ctx); ctx->c.sync(); SB_END }
+int sb_context_destroy(sb_context* ctx) { SB_TRY DEVG(ctx) delete ctx; SB_END }
+int sb_context_sync(sb_context* ctx) { SB_TRY DEVG(ctx) REQ(ctx); ctx->c.sync(); SB_END }
 long long sb_context_launch_count(sb_context* ctx) { return ctx ? k::launch_count() - ctx->c.launches0 : -1; }
 int sb_comm_get_unique_id(void* id128) { SB_TRY REQ(id128); Comm::getUniqueId(id128); SB_END }
 int sb_comm_init(sb_context* ctx, const void* id128)
 {
-    SB_TRY REQ(ctx); REQ(id128);
+    SB_TRY DEVG(ctx) REQ(ctx); REQ(id128);
     if (ctx->c.comm) SB_FAIL("communicator already initialised");
     ctx->c.comm = new Comm(&ctx->c, id128);
     SB_END
@@ -45,7 +66,7 @@ int sb_comm_init(sb_context* ctx, const void* id128)
 
 int sb_context_timer_start(sb_context* ctx)
 {
-    SB_TRY REQ(ctx);
+    SB_TRY DEVG(ctx) REQ(ctx);
     Context& c = ctx->c;
     if (!c.tm0) { SB_CUDA(cudaEventCreate(&c.tm0)); SB_CUDA(cudaEventCreate(&c.tm1)); }
     SB_CUDA(cudaEventRecord(c.tm0, c.st));
@@ -53,7 +74,7 @@ int sb_context_timer_start(sb_context* ctx)
 }
 int sb_context_timer_stop(sb_context* ctx, double* ms)
 {
-    SB_TRY REQ(ctx); REQ(ms);
+    SB_TRY DEVG(ctx) REQ(ctx); REQ(ms);
     Context& c = ctx->c;
     if (!c.tm0) SB_FAIL("timer not started");
     SB_CUDA(cudaEventRecord(c.tm1, c.st));
@@ -65,7 +86,7 @@ int sb_context_timer_stop(sb_context* ctx, double* ms)
 }
 int sb_context_profile(sb_context* ctx, int enable)
 {
-    SB_TRY REQ(ctx);
+    SB_TRY DEVG(ctx) REQ(ctx);
     ctx->c.profResolve();
     if (enable) ctx->c.prof.clear();
     ctx->c.profiling = enable != 0;
@@ -73,7 +94,7 @@ int sb_context_profile(sb_context* ctx, int enable)
 }
 int sb_context_profile_get(sb_context* ctx, const char* key, double* total_ms, long long* count)
 {
-    SB_TRY REQ(ctx); REQ(key); REQ(total_ms); REQ(count);
+    SB_TRY DEVG(ctx) REQ(ctx); REQ(key); REQ(total_ms); REQ(count);
     ctx->c.profResolve();
     auto it = ctx->c.prof.find(key);
     *total_ms = it == ctx->c.prof.end() ? 0.0 : it->second.ms;
@@ -149,13 +170,13 @@ int sb_plan_schedule(const sb_level_desc* d, int max_depth, int* schedule, int c
 // ---- PoissonOp ------------------------------------------------------------------------------
 int sb_op_create(sb_context* ctx, const sb_level_desc* desc, sb_op** op)
 {
-    SB_TRY REQ(ctx); REQ(desc); REQ(op);
+    SB_TRY DEVG(ctx) REQ(ctx); REQ(desc); REQ(op);
     *op = new sb_op{new Op(&ctx->c, *desc), true};
     SB_END
 }
 int sb_op_destroy(sb_op* op)
 {
-    SB_TRY if (op) { if (op->owned) delete op->op; delete op; }
+    SB_TRY DEVG(op) if (op) { if (op->owned) delete op->op; delete op; }
     SB_END
 }
 
@@ -193,7 +214,7 @@ static void copy3d(Op& o, int centering, double* dev, double* host, const int lo
 
 int sb_op_set_metric(sb_op* op, int centering, int box_id, const double* host, const int lo[3], const int hi[3])
 {
-    SB_TRY REQ(op); REQ(host);
+    SB_TRY DEVG(op) REQ(op); REQ(host);
     Op& o = *op->op;
     if (box_id < 0 || box_id >= (int)o.boxes.size()) SB_FAIL("box_id out of range");
     if (o.boxRank[box_id] != o.ctx->rank) return 0;
@@ -204,6 +225,7 @@ int sb_op_set_metric(sb_op* op, int centering, int box_id, const double* host, c
     for (int d = 0; d < 3; ++d) {
         clo[d] = std::max(lo[d], b.lo[d]);
         chi[d] = std::min(hi[d], b.hi[d] + (d == centering ? 1 : 0));
+        if (chi[d] < clo[d]) return 0;  // the host array misses this box
     }
     // stage through a contiguous sub-box copy: cudaMemcpy3D handles the strides
     const size_t hnx = (size_t)(hi[0] - lo[0] + 1), hny = (size_t)(hi[1] - lo[1] + 1);
@@ -220,11 +242,11 @@ int sb_op_set_metric(sb_op* op, int centering, int box_id, const double* host, c
     o.ctx->sync();
     SB_END
 }
-int sb_op_finalize(sb_op* op) { SB_TRY REQ(op); op->op->finalize(); op->op->ctx->sync(); SB_END }
-int sb_op_has_null_space(sb_op* op, int* out) { SB_TRY REQ(op); REQ(out); *out = op->op->hasNullSpace; SB_END }
+int sb_op_finalize(sb_op* op) { SB_TRY DEVG(op) REQ(op); op->op->finalize(); op->op->ctx->sync(); SB_END }
+int sb_op_has_null_space(sb_op* op, int* out) { SB_TRY DEVG(op) REQ(op); REQ(out); *out = op->op->hasNullSpace; SB_END }
 int sb_op_new_mg_operator(sb_op* op, const int ref[3], sb_op** crse)
 {
-    SB_TRY REQ(op); REQ(crse);
+    SB_TRY DEVG(op) REQ(op); REQ(crse);
     if (!op->op->finalized) SB_FAIL("sb_op_finalize first");
     if (ref[0] == 1 && ref[1] == 1 && ref[2] == 1) SB_FAIL("newMGOperator(Unit) clones are not needed: reuse the handle");
     *crse = new sb_op{new Op(*op->op, ref), true};
@@ -232,7 +254,7 @@ int sb_op_new_mg_operator(sb_op* op, const int ref[3], sb_op** crse)
 }
 int sb_op_get_info(sb_op* op, int domain_lo[3], int domain_hi[3], double dXi[3], int* num_local_boxes)
 {
-    SB_TRY REQ(op);
+    SB_TRY DEVG(op) REQ(op);
     for (int d = 0; d < 3; ++d) {
         if (domain_lo) domain_lo[d] = op->op->domain.lo[d];
         if (domain_hi) domain_hi[d] = op->op->domain.hi[d];
@@ -243,7 +265,7 @@ int sb_op_get_info(sb_op* op, int domain_lo[3], int domain_hi[3], double dXi[3],
 }
 int sb_op_get_coefficient(sb_op* op, int which, double* host, long long capacity)
 {
-    SB_TRY REQ(op); REQ(host);
+    SB_TRY DEVG(op) REQ(op); REQ(host);
     Op& o = *op->op;
     if (which >= 2 && which <= 4) {
         const auto& m = o.hM[which - 2];
@@ -269,22 +291,22 @@ int sb_op_get_coefficient(sb_op* op, int which, double* host, long long capacity
 // ---- fields ---------------------------------------------------------------------------------
 int sb_field_create(sb_op* op, int centering, sb_field** f)
 {
-    SB_TRY REQ(op); REQ(f);
+    SB_TRY DEVG(op) REQ(op); REQ(f);
     if (centering < -1 || centering > 2) SB_FAIL("bad centering");
     *f = new sb_field(op->op, centering);
     SB_END
 }
-int sb_field_destroy(sb_field* f) { SB_TRY delete f; SB_END }
+int sb_field_destroy(sb_field* f) { SB_TRY DEVG(f) delete f; SB_END }
 int sb_field_upload(sb_field* f, const double* host, const int lo[3], const int hi[3])
 {
-    SB_TRY REQ(f); REQ(host);
+    SB_TRY DEVG(f) REQ(f); REQ(host);
     copy3d(*f->f.op, f->f.centering, f->f.d, const_cast<double*>(host), lo, hi, true);
     f->f.op->ctx->sync();
     SB_END
 }
 int sb_field_download(sb_field* f, double* host, const int lo[3], const int hi[3])
 {
-    SB_TRY REQ(f); REQ(host);
+    SB_TRY DEVG(f) REQ(f); REQ(host);
     copy3d(*f->f.op, f->f.centering, f->f.d, host, lo, hi, false);
     f->f.op->ctx->sync();
     SB_END
@@ -292,21 +314,23 @@ int sb_field_download(sb_field* f, double* host, const int lo[3], const int hi[3
 
 int sb_field_upload_async(sb_field* f, const double* host, const int lo[3], const int hi[3])
 {
-    SB_TRY REQ(f); REQ(host);
+    SB_TRY DEVG(f) REQ(f); REQ(host);
     Op& o = *f->f.op;
+    // the field's zero fill ran on the compute stream: a late memset must not overwrite this copy
+    SB_CUDA(cudaStreamWaitEvent(o.ctx->stream(SB_STREAM_H2D), f->f.ready, 0));
     copy3d(o, f->f.centering, f->f.d, const_cast<double*>(host), lo, hi, true, o.ctx->stream(SB_STREAM_H2D));
     SB_END
 }
 int sb_field_download_async(sb_field* f, double* host, const int lo[3], const int hi[3])
 {
-    SB_TRY REQ(f); REQ(host);
+    SB_TRY DEVG(f) REQ(f); REQ(host);
     Op& o = *f->f.op;
     copy3d(o, f->f.centering, f->f.d, host, lo, hi, false, o.ctx->stream(SB_STREAM_D2H));
     SB_END
 }
 int sb_context_stream_wait(sb_context* ctx, int waiter, int signaller)
 {
-    SB_TRY REQ(ctx);
+    SB_TRY DEVG(ctx) REQ(ctx);
     cudaEvent_t e;
     SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     SB_CUDA(cudaEventRecord(e, ctx->c.stream(signaller)));
@@ -316,7 +340,7 @@ int sb_context_stream_wait(sb_context* ctx, int waiter, int signaller)
 }
 int sb_context_stream_sync(sb_context* ctx, int which)
 {
-    SB_TRY REQ(ctx); SB_CUDA(cudaStreamSynchronize(ctx->c.stream(which))); SB_END
+    SB_TRY DEVG(ctx) REQ(ctx); SB_CUDA(cudaStreamSynchronize(ctx->c.stream(which))); SB_END
 }
 
 // ---- operator methods ------------------------------------------------------------------------
@@ -331,45 +355,45 @@ static void sameOp(sb_op* op, std::initializer_list<sb_field*> fs)
         if (f->f.op != op->op) SB_FAIL("field belongs to another operator / MG depth");
     }
 }
-int sb_op_apply_bcs(sb_op* op, sb_field* phi, int homog) { SB_TRY sameOp(op, {phi}); OPF(op).applyBCs(D(phi), homog); SB_END }
+int sb_op_apply_bcs(sb_op* op, sb_field* phi, int homog) { SB_TRY DEVG(op) sameOp(op, {phi}); OPF(op).applyBCs(D(phi), homog); SB_END }
 int sb_op_apply_op(sb_op* op, sb_field* lhs, sb_field* phi, int homog)
 {
-    SB_TRY sameOp(op, {lhs, phi}); OPF(op).applyOp(D(lhs), D(phi), homog); SB_END
+    SB_TRY DEVG(op) sameOp(op, {lhs, phi}); OPF(op).applyOp(D(lhs), D(phi), homog); SB_END
 }
 int sb_op_residual(sb_op* op, sb_field* res, sb_field* phi, sb_field* rhs, int homog)
 {
-    SB_TRY sameOp(op, {res, phi, rhs}); OPF(op).residual(D(res), D(phi), D(rhs), homog); SB_END
+    SB_TRY DEVG(op) sameOp(op, {res, phi, rhs}); OPF(op).residual(D(res), D(phi), D(rhs), homog); SB_END
 }
 int sb_op_relax(sb_op* op, sb_field* cor, sb_field* res, int iters)
 {
-    SB_TRY sameOp(op, {cor, res}); OPF(op).relax(D(cor), D(res), iters);
+    SB_TRY DEVG(op) sameOp(op, {cor, res}); OPF(op).relax(D(cor), D(res), iters);
     if (OPF(op).relaxMethod == SB_RELAX_VERTLINE) OPF(op).checkPivot();
     SB_END
 }
-int sb_op_precond(sb_op* op, sb_field* phi, sb_field* rhs, int it) { SB_TRY sameOp(op, {phi, rhs}); OPF(op).preCond(D(phi), D(rhs), it); SB_END }
-int sb_op_remove_kernel(sb_op* op, sb_field* phi) { SB_TRY sameOp(op, {phi}); OPF(op).removeKernel(D(phi)); SB_END }
+int sb_op_precond(sb_op* op, sb_field* phi, sb_field* rhs, int it) { SB_TRY DEVG(op) sameOp(op, {phi, rhs}); OPF(op).preCond(D(phi), D(rhs), it); SB_END }
+int sb_op_remove_kernel(sb_op* op, sb_field* phi) { SB_TRY DEVG(op) sameOp(op, {phi}); OPF(op).removeKernel(D(phi)); SB_END }
 int sb_op_norm(sb_op* op, sb_field* x, int p, double pow_scale, double* out)
 {
-    SB_TRY sameOp(op, {x}); REQ(out); *out = OPF(op).norm(D(x), p, pow_scale); SB_END
+    SB_TRY DEVG(op) sameOp(op, {x}); REQ(out); *out = OPF(op).norm(D(x), p, pow_scale); SB_END
 }
-int sb_op_dot(sb_op* op, sb_field* a, sb_field* b, double* out) { SB_TRY sameOp(op, {a, b}); REQ(out); *out = OPF(op).dotProduct(D(a), D(b)); SB_END }
-int sb_op_incr(sb_op* op, sb_field* lhs, sb_field* x, double s) { SB_TRY sameOp(op, {lhs, x}); OPF(op).incr(D(lhs), D(x), s); SB_END }
+int sb_op_dot(sb_op* op, sb_field* a, sb_field* b, double* out) { SB_TRY DEVG(op) sameOp(op, {a, b}); REQ(out); *out = OPF(op).dotProduct(D(a), D(b)); SB_END }
+int sb_op_incr(sb_op* op, sb_field* lhs, sb_field* x, double s) { SB_TRY DEVG(op) sameOp(op, {lhs, x}); OPF(op).incr(D(lhs), D(x), s); SB_END }
 int sb_op_axby(sb_op* op, sb_field* lhs, sb_field* x, sb_field* y, double a, double b)
 {
-    SB_TRY sameOp(op, {lhs, x, y}); OPF(op).axby(D(lhs), D(x), D(y), a, b); SB_END
+    SB_TRY DEVG(op) sameOp(op, {lhs, x, y}); OPF(op).axby(D(lhs), D(x), D(y), a, b); SB_END
 }
-int sb_op_scale(sb_op* op, sb_field* lhs, double s) { SB_TRY sameOp(op, {lhs}); OPF(op).scale(D(lhs), s); SB_END }
-int sb_op_set_to_zero(sb_op* op, sb_field* lhs) { SB_TRY sameOp(op, {lhs}); OPF(op).setToZero(D(lhs)); SB_END }
-int sb_op_assign_local(sb_op* op, sb_field* dst, sb_field* src) { SB_TRY sameOp(op, {dst, src}); OPF(op).assignLocal(D(dst), D(src)); SB_END }
+int sb_op_scale(sb_op* op, sb_field* lhs, double s) { SB_TRY DEVG(op) sameOp(op, {lhs}); OPF(op).scale(D(lhs), s); SB_END }
+int sb_op_set_to_zero(sb_op* op, sb_field* lhs) { SB_TRY DEVG(op) sameOp(op, {lhs}); OPF(op).setToZero(D(lhs)); SB_END }
+int sb_op_assign_local(sb_op* op, sb_field* dst, sb_field* src) { SB_TRY DEVG(op) sameOp(op, {dst, src}); OPF(op).assignLocal(D(dst), D(src)); SB_END }
 int sb_op_mg_restrict(sb_op* fine, sb_op* crse, sb_field* crse_res, sb_field* fine_res)
 {
-    SB_TRY sameOp(fine, {fine_res}); sameOp(crse, {crse_res});
+    SB_TRY DEVG(fine) sameOp(fine, {fine_res}); sameOp(crse, {crse_res});
     OPF(fine).MGRestrict(OPF(crse), D(crse_res), D(fine_res));
     SB_END
 }
 int sb_op_mg_prolong(sb_op* fine, sb_op* crse, sb_field* fine_phi, sb_field* crse_cor, int order)
 {
-    SB_TRY sameOp(fine, {fine_phi}); sameOp(crse, {crse_cor});
+    SB_TRY DEVG(fine) sameOp(fine, {fine_phi}); sameOp(crse, {crse_cor});
     OPF(fine).MGProlong(OPF(crse), D(fine_phi), D(crse_cor), order);
     SB_END
 }
@@ -386,35 +410,35 @@ static void fluxPtrs(sb_op* op, sb_field* const f[3], double* out[3])
 }
 int sb_op_level_divergence(sb_op* op, sb_field* div, sb_field* const vel[3])
 {
-    SB_TRY sameOp(op, {div});
+    SB_TRY DEVG(op) sameOp(op, {div});
     double* v[3]; fluxPtrs(op, vel, v);
     OPF(op).levelDivergence(D(div), v);
     SB_END
 }
 int sb_op_level_gradient(sb_op* op, sb_field* const grad[3], sb_field* phi, int homog)
 {
-    SB_TRY sameOp(op, {phi});
+    SB_TRY DEVG(op) sameOp(op, {phi});
     double* g[3]; fluxPtrs(op, grad, g);
     OPF(op).levelGradient(g, D(phi), homog);
     SB_END
 }
 int sb_op_send_to_advecting_velocity(sb_op* op, sb_field* const vel[3], int ghost)
 {
-    SB_TRY sameOp(op, {});
+    SB_TRY DEVG(op) sameOp(op, {});
     double* v[3]; fluxPtrs(op, vel, v);
     OPF(op).scaleVelocity(v, ghost, true);
     SB_END
 }
 int sb_op_send_to_cartesian_velocity(sb_op* op, sb_field* const vel[3], int ghost)
 {
-    SB_TRY sameOp(op, {});
+    SB_TRY DEVG(op) sameOp(op, {});
     double* v[3]; fluxPtrs(op, vel, v);
     OPF(op).scaleVelocity(v, ghost, false);
     SB_END
 }
 int sb_op_flux_incr(sb_op* op, sb_field* const vel[3], sb_field* const grad[3], double scale)
 {
-    SB_TRY sameOp(op, {});
+    SB_TRY DEVG(op) sameOp(op, {});
     double *v[3], *g[3]; fluxPtrs(op, vel, v); fluxPtrs(op, grad, g);
     for (int d = 0; d < 3; ++d) {
         if (op->op->dim == 2 && d == 1) continue;
@@ -427,32 +451,32 @@ int sb_op_flux_incr(sb_op* op, sb_field* const vel[3], sb_field* const grad[3], 
 static sb::Op* opOf(sb_field* f) { return f ? f->f.op : nullptr; }
 int sb_op_apply_bcs_amr(sb_op* op, sb_field* phi, sb_field* crse_phi, int homog_phys, int homog_cfi)
 {
-    SB_TRY sameOp(op, {phi}); (void)homog_phys;
+    SB_TRY DEVG(op) sameOp(op, {phi}); (void)homog_phys;
     OPF(op).applyBCsAMR(D(phi), opOf(crse_phi), crse_phi ? D(crse_phi) : nullptr, homog_cfi != 0);
     SB_END
 }
 int sb_op_amr_operator(sb_op* op, sb_field* lhs, sb_field* phi_fine, sb_field* phi, sb_field* phi_crse, int homog_phys, sb_op* finer_op)
 {
-    SB_TRY sameOp(op, {lhs, phi}); sameOp(finer_op, {phi_fine}); REQ(phi_crse); (void)homog_phys;
+    SB_TRY DEVG(op) sameOp(op, {lhs, phi}); sameOp(finer_op, {phi_fine}); REQ(phi_crse); (void)homog_phys;
     OPF(op).AMROperator(D(lhs), OPF(finer_op), D(phi_fine), D(phi), *opOf(phi_crse), D(phi_crse));
     SB_END
 }
 int sb_op_amr_operator_nf(sb_op* op, sb_field* lhs, sb_field* phi, sb_field* phi_crse, int homog_phys)
 {
-    SB_TRY sameOp(op, {lhs, phi}); REQ(phi_crse); (void)homog_phys;
+    SB_TRY DEVG(op) sameOp(op, {lhs, phi}); REQ(phi_crse); (void)homog_phys;
     OPF(op).AMROperatorNF(D(lhs), D(phi), *opOf(phi_crse), D(phi_crse));
     SB_END
 }
 int sb_op_amr_operator_nc(sb_op* op, sb_field* lhs, sb_field* phi_fine, sb_field* phi, int homog_phys, sb_op* finer_op)
 {
-    SB_TRY sameOp(op, {lhs, phi}); sameOp(finer_op, {phi_fine}); (void)homog_phys;
+    SB_TRY DEVG(op) sameOp(op, {lhs, phi}); sameOp(finer_op, {phi_fine}); (void)homog_phys;
     OPF(op).AMROperatorNC(D(lhs), OPF(finer_op), D(phi_fine), D(phi));
     SB_END
 }
 int sb_op_amr_residual(sb_op* op, sb_field* res, sb_field* phi_fine, sb_field* phi, sb_field* phi_crse, sb_field* rhs, int homog_phys,
                        sb_op* finer_op)
 {
-    SB_TRY sameOp(op, {res, phi, rhs}); (void)homog_phys;
+    SB_TRY DEVG(op) sameOp(op, {res, phi, rhs}); (void)homog_phys;
     if ((finer_op != nullptr) != (phi_fine != nullptr)) SB_FAIL("finer_op and phi_fine go together");
     if (finer_op) sameOp(finer_op, {phi_fine});
     OPF(op).AMRResidual(D(res), finer_op ? finer_op->op : nullptr, phi_fine ? D(phi_fine) : nullptr, D(phi), opOf(phi_crse),
@@ -461,33 +485,33 @@ int sb_op_amr_residual(sb_op* op, sb_field* res, sb_field* phi_fine, sb_field* p
 }
 int sb_op_amr_norm_level(sb_op* op, sb_field* res, sb_op* finer_op, int p, double* out)
 {
-    SB_TRY sameOp(op, {res}); REQ(out);
+    SB_TRY DEVG(op) sameOp(op, {res}); REQ(out);
     *out = OPF(op).AMRNormLevel(D(res), finer_op ? finer_op->op : nullptr, p);
     SB_END
 }
 int sb_op_get_flux(sb_op* op, sb_field* const flux[3], sb_field* phi)
 {
-    SB_TRY sameOp(op, {phi});
+    SB_TRY DEVG(op) sameOp(op, {phi});
     double* g[3]; fluxPtrs(op, flux, g);
     OPF(op).getFlux(g, D(phi));
     SB_END
 }
 int sb_op_reflux(sb_op* op, sb_field* res, sb_field* fine_phi, sb_field* phi, sb_op* finer_op)
 {
-    SB_TRY sameOp(op, {res, phi}); sameOp(finer_op, {fine_phi});
+    SB_TRY DEVG(op) sameOp(op, {res, phi}); sameOp(finer_op, {fine_phi});
     OPF(op).reflux(D(res), OPF(finer_op), D(fine_phi), D(phi));
     SB_END
 }
 int sb_op_reflux_flux(sb_op* op, sb_field* div, sb_field* const flux[3], sb_field* const fine_flux[3], sb_op* finer_op)
 {
-    SB_TRY sameOp(op, {div}); sameOp(finer_op, {});
+    SB_TRY DEVG(op) sameOp(op, {div}); sameOp(finer_op, {});
     double *f[3], *ff[3]; fluxPtrs(op, flux, f); fluxPtrs(finer_op, fine_flux, ff);
     OPF(op).refluxFlux(D(div), f, OPF(finer_op), ff);
     SB_END
 }
 int sb_op_comp_divergence(sb_op* op, sb_field* div, sb_field* const flux[3], sb_field* const fine_flux[3], sb_op* finer_op)
 {
-    SB_TRY sameOp(op, {div});
+    SB_TRY DEVG(op) sameOp(op, {div});
     double *f[3], *ff[3] = {nullptr, nullptr, nullptr};
     fluxPtrs(op, flux, f);
     if ((finer_op != nullptr) != (fine_flux != nullptr)) SB_FAIL("finer_op and fine_flux go together");
@@ -497,7 +521,7 @@ int sb_op_comp_divergence(sb_op* op, sb_field* div, sb_field* const flux[3], sb_
 }
 int sb_op_comp_gradient(sb_op* op, sb_field* const grad[3], sb_field* phi, sb_field* crse_phi, int homog_phys, int homog_cfi)
 {
-    SB_TRY sameOp(op, {phi}); (void)homog_phys;
+    SB_TRY DEVG(op) sameOp(op, {phi}); (void)homog_phys;
     double* g[3]; fluxPtrs(op, grad, g);
     Op& o = OPF(op);
     o.applyBCsAMR(D(phi), opOf(crse_phi), crse_phi ? D(crse_phi) : nullptr, homog_cfi != 0);  // PoissonOp.cpp:1505
@@ -511,7 +535,7 @@ int sb_op_comp_gradient(sb_op* op, sb_field* const grad[3], sb_field* phi, sb_fi
 }
 int sb_op_get_patch(sb_op* op, int patch_lo[3], int patch_hi[3], int tile_lo[3], int tile_hi[3])
 {
-    SB_TRY REQ(op);
+    SB_TRY DEVG(op) REQ(op);
     for (int d = 0; d < 3; ++d) {
         if (patch_lo) patch_lo[d] = op->op->patch.lo[d];
         if (patch_hi) patch_hi[d] = op->op->patch.hi[d];
@@ -524,7 +548,7 @@ int sb_op_get_patch(sb_op* op, int patch_lo[3], int patch_hi[3], int tile_lo[3],
 // ---- AMRHybridSolver ---------------------------------------------------------------------------
 int sb_amr_solver_create(sb_op* const* ops, int num_levels, int lmin, int lmax, const sb_mg_options* opt, sb_amr_solver** s)
 {
-    SB_TRY REQ(ops); REQ(opt); REQ(s);
+    SB_TRY DEVG(ops && lmax >= 0 && lmax < num_levels ? ops[lmax] : (sb_op*)nullptr) REQ(ops); REQ(opt); REQ(s);
     std::vector<Op*> v(num_levels, nullptr);
     for (int l = 0; l < num_levels; ++l)
         if (ops[l]) {
@@ -537,11 +561,11 @@ int sb_amr_solver_create(sb_op* const* ops, int num_levels, int lmin, int lmax, 
     *s = p.release();
     SB_END
 }
-int sb_amr_solver_destroy(sb_amr_solver* s) { SB_TRY delete s; SB_END }
+int sb_amr_solver_destroy(sb_amr_solver* s) { SB_TRY DEVG(s) delete s; SB_END }
 int sb_amr_solver_solve(sb_amr_solver* s, sb_field* const* phi, sb_field* const* rhs, int homog, int set_phi_to_zero, double metric,
                         sb_solver_status* status)
 {
-    SB_TRY REQ(s); REQ(phi); REQ(rhs);
+    SB_TRY DEVG(s) REQ(s); REQ(phi); REQ(rhs);
     AMRSolver& a = s->s;
     std::vector<double*>       vphi(a.lmax + 1, nullptr);
     std::vector<const double*> vrhs(a.lmax + 1, nullptr);
@@ -583,7 +607,7 @@ int sb_amr_solver_solve(sb_amr_solver* s, sb_field* const* phi, sb_field* const*
 // ---- solvers ---------------------------------------------------------------------------------
 int sb_mgsolver_create(sb_op* top, const sb_mg_options* opt, const int* schedule, int num_sched, sb_solver** s)
 {
-    SB_TRY sameOp(top, {}); REQ(opt); REQ(s);
+    SB_TRY DEVG(top) sameOp(top, {}); REQ(opt); REQ(s);
     std::vector<std::array<int, 3>> sched;
     for (int i = 0; i < num_sched; ++i) sched.push_back({schedule[3 * i], schedule[3 * i + 1], schedule[3 * i + 2]});
     std::unique_ptr<sb_solver> p(new sb_solver);
@@ -598,7 +622,7 @@ int sb_mgsolver_create(sb_op* top, const sb_mg_options* opt, const int* schedule
 }
 int sb_hybrid_solver_create(sb_op* top, const sb_mg_options* opt, sb_solver** s)
 {
-    SB_TRY sameOp(top, {}); REQ(opt); REQ(s);
+    SB_TRY DEVG(top) sameOp(top, {}); REQ(opt); REQ(s);
     std::unique_ptr<sb_solver> p(new sb_solver);
     p->s.isHybrid = true;
     p->s.define(*top->op, *opt);
@@ -606,10 +630,10 @@ int sb_hybrid_solver_create(sb_op* top, const sb_mg_options* opt, sb_solver** s)
     *s = p.release();
     SB_END
 }
-int sb_solver_destroy(sb_solver* s) { SB_TRY delete s; SB_END }
+int sb_solver_destroy(sb_solver* s) { SB_TRY DEVG(s) delete s; SB_END }
 int sb_solver_get_schedule(sb_solver* s, int* schedule, int capacity, int* num_sched)
 {
-    SB_TRY REQ(s); REQ(num_sched);
+    SB_TRY DEVG(s) REQ(s); REQ(num_sched);
     const auto& sc = s->s.mg.refSchedule;
     *num_sched     = (int)sc.size();
     if (schedule) {
@@ -621,8 +645,10 @@ int sb_solver_get_schedule(sb_solver* s, int* schedule, int capacity, int* num_s
 }
 int sb_solver_set_options(sb_solver* s, const sb_mg_options* opt)
 {
-    SB_TRY REQ(s); REQ(opt);
-    s->s.mg.modifyOptionsExceptMaxDepth(*opt);
+    // LevelHybridSolver::modifyOptionsExceptMaxDepth (LevelHybridSolver.cpp:65-81): both sub-solvers follow
+    SB_TRY DEVG(s) REQ(s); REQ(opt);
+    if (!s->s.mg.ops.empty()) s->s.mg.modifyOptionsExceptMaxDepth(*opt);
+    if (s->s.leptic) s->s.leptic->modifyOptionsExceptMaxDepth(*opt);
     const int md = s->s.opt.maxDepth;
     s->s.opt = *opt; s->s.opt.maxDepth = md;
     SB_END
@@ -647,7 +673,7 @@ static void fillStatus(sb_solver* s, const SolverStatus& st, sb_solver_status* o
 int sb_solver_solve(sb_solver* s, sb_field* phi, sb_field* rhs, int homog, int set_phi_to_zero, double metric,
                     sb_solver_status* status)
 {
-    SB_TRY REQ(s); REQ(phi); REQ(rhs);
+    SB_TRY DEVG(s) REQ(s); REQ(phi); REQ(rhs);
     Op& o = *s->s.op;
     if (phi->f.op != &o || rhs->f.op != &o) SB_FAIL("fields do not live on the solver's top operator");
     cudaEvent_t e0, e1;
@@ -664,21 +690,23 @@ int sb_solver_solve(sb_solver* s, sb_field* phi, sb_field* rhs, int homog, int s
 }
 int sb_solver_vcycle(sb_solver* s, sb_field* cor, sb_field* res)
 {
-    SB_TRY REQ(s); REQ(cor); REQ(res);
+    SB_TRY DEVG(s) REQ(s); REQ(cor); REQ(res);
     Op& o = *s->s.op;
     if (cor->f.op != &o || res->f.op != &o) SB_FAIL("fields do not live on the solver's top operator");
     if (s->s.mg.ops.empty()) SB_FAIL("this hybrid solver runs in pure leptic mode: it has no MGSolver to V-cycle with");
     s->s.mg.vCycle_residualEq(D(cor), D(res), 0);
+    if (o.relaxMethod == SB_RELAX_VERTLINE) s->s.mg.checkPivotAll();
     SB_END
 }
 
 int sb_solver_precond_vcycle(sb_solver* s, sb_field* cor, sb_field* res)
 {
-    SB_TRY REQ(s); REQ(cor); REQ(res);
+    SB_TRY DEVG(s) REQ(s); REQ(cor); REQ(res);
     Op& o = *s->s.op;
     if (cor->f.op != &o || res->f.op != &o) SB_FAIL("fields do not live on the solver's top operator");
     if (s->s.mg.ops.empty()) SB_FAIL("this hybrid solver runs in pure leptic mode: it has no MGSolver to V-cycle with");
     s->s.mg.vCycle_residualEq(D(cor), D(res), 0, true);
+    if (o.relaxMethod == SB_RELAX_VERTLINE) s->s.mg.checkPivotAll();
     SB_END
 }
 
@@ -686,7 +714,7 @@ int sb_solver_precond_vcycle(sb_solver* s, sb_field* cor, sb_field* res)
 int sb_project_host(sb_solver* s, double* const vel[3], double* phi, double* p, double proj_dt, double* init_div_norm,
                     double* final_div_norm, sb_solver_status* status)
 {
-    SB_TRY REQ(s); REQ(vel);
+    SB_TRY DEVG(s) REQ(s); REQ(vel);
     Op& o = *s->s.op;
     if (o.ctx->nranks != 1) SB_FAIL("sb_project_host takes whole-domain host arrays: single rank only (use the field API per rank)");
     struct Tmp {

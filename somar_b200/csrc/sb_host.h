@@ -88,6 +88,7 @@ struct Field {
     Op*     op;
     int     centering;  // SB_CELL or face dir
     double* d = nullptr;
+    cudaEvent_t ready = nullptr;  // recorded on the compute stream after the zero fill of alloc(): the copy streams wait on it
     Field(Op* op, int centering);
     ~Field();
     Field(const Field&) = delete;
@@ -114,6 +115,7 @@ struct Op {
     double   amrCrseDXi[3] = {0, 0, 0};  // m_amrCrseDXi: the same at every MG depth (PoissonOp.cpp:345)
     Box3     patch;                  // bounding box of all boxes of this level (= domain on a base level)
     std::shared_ptr<CFLink> cf;      // coarse-fine interpolation, inter-level copiers, fine flux register (depth 0 of a refined level)
+    bool     gsrbNatural = false;    // SB_GSRB_KERNEL=natural at creation: point GSRB stays on the natural layout (tests)
     bool     flatZ = false;  // horizontal-only operator of the leptic solver (PoissonOp.cpp:411-505): one layer, no vertical coupling
 
     std::vector<Box3> boxes;    // all ranks
@@ -208,6 +210,7 @@ struct Op {
     // AMRNSLevel::sendToAdvectingVelocity (toAdvecting) / sendToCartesianVelocity, AMRNSLevelFill.cpp:194-280
     void   scaleVelocity(double* const vel[3], int ghost, bool toAdvecting);
     void   checkPivot();
+    int    readPivotFlag(bool reset);
     double* alloc() const;
 
     // ---- AMRMGOperator surface (Elliptic/AMRMGOperator.H:43-218, PoissonOp.cpp:1156-1478); sb_amr.cpp ----
@@ -286,6 +289,9 @@ struct MGSolver {
     void aggGather(const double* tileField, double* fullField, int centering, const Op& distOp);
     void aggScatter(double* tileField, const double* fullField, const Op& distOp);
     void checkPivotAll();
+    bool needPivotCheck = false;
+    int  localPivotFlag(bool reset);
+    bool usesGeneralLineKernel() const;
 
     void define(Op& top, const sb_mg_options& opt, std::vector<std::array<int, 3>> sched, bool useBottomSolver = true);
     ~MGSolver();
@@ -313,6 +319,9 @@ struct LepticSolver {
     double *corTotal = nullptr, *cor = nullptr, *rhsA = nullptr, *rhsB = nullptr, *gam = nullptr;  // on op
     double *excess = nullptr, *hiBC = nullptr, *hPhi = nullptr, *hRhs = nullptr, *ones = nullptr; // on hOp
     void define(Op& top, const sb_mg_options& proj);
+    // LevelLepticSolver::modifyOptionsExceptMaxDepth (LevelLepticSolver.cpp:100-110): the leptic fields follow the
+    // new (proj.*-shaped) options; the horizontal MGSolver keeps the options it was defined with, as in the reference
+    void modifyOptionsExceptMaxDepth(const sb_mg_options& proj);
     ~LepticSolver();
     SolverStatus solve(double* phi, const double* rhs, bool homog, bool setPhiToZero);
     void computeVerticalExcess(const double* rhs);

@@ -115,6 +115,11 @@ void LepticSolver::define(Op& top, const sb_mg_options& proj)
     k::fill(top.st(), ones, hOp->lay.n, 1.0);
 }
 
+void LepticSolver::modifyOptionsExceptMaxDepth(const sb_mg_options& proj)
+{
+    absTol = proj.absTol; relTol = proj.relTol; maxOrder = proj.maxIters; normType = proj.normType; hang = proj.hang;
+}
+
 // LevelLepticSolver::computeVerticalExcess (:711-770)
 void LepticSolver::computeVerticalExcess(const double* rhs)
 {

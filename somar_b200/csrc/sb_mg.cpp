@@ -286,6 +286,9 @@ void MGSolver::define(Op& top, const sb_mg_options& a_opt, std::vector<IV> sched
         bottom->opt = opt.bottom;
     }
     status.clear();
+    double need = usesGeneralLineKernel() ? 1.0 : 0.0;
+    if (!top.ctx->parent) top.ctx->allreduceMax(&need, 1);  // (the agglomerated solver on rank 0 answers through its owner)
+    needPivotCheck = need != 0.0;
 }
 void MGSolver::defineAgglomeration()
 {
@@ -326,10 +329,32 @@ void MGSolver::aggScatter(double* tileField, const double* fullField, const Op& 
 {
     distOp.ctx->comm->scatterTiles(distOp, tileField, aggTop ? &aggTop->lay : nullptr, fullField, aggBuf);
 }
+// Only the general line kernel (vertline_k) can raise the flag; whether any depth on any rank uses it is settled once
+// in define(), so the shared-matrix path pays nothing here.  The flags of all depths (agglomerated ones included, which
+// exist on rank 0 only) are combined over the ranks before anyone throws: every rank fails together instead of one rank
+// leaving the others in the next collective.
+int MGSolver::localPivotFlag(bool reset)
+{
+    int f = 0;
+    for (Op* o : ops)
+        if (o->relaxMethod == SB_RELAX_VERTLINE && !o->lineFast) f |= o->readPivotFlag(reset);
+    if (agg) f |= agg->localPivotFlag(reset);
+    return f;
+}
+bool MGSolver::usesGeneralLineKernel() const
+{
+    for (Op* o : ops)
+        if (o->relaxMethod == SB_RELAX_VERTLINE && !o->lineFast) return true;
+    return agg ? agg->usesGeneralLineKernel() : false;
+}
 void MGSolver::checkPivotAll()
 {
-    for (Op* o : ops) o->checkPivot();
-    if (agg) agg->checkPivotAll();
+    if (!needPivotCheck || ops.empty()) return;
+    double f = (double)localPivotFlag(true);
+    ops[0]->ctx->allreduceMax(&f, 1);
+    if (f != 0.0)
+        SB_FAIL("vertical line relaxation met a column where LAPACK dgtsv pivots or is singular (flag " + std::to_string((int)f) +
+                "); the B200 path does not reproduce that branch");
 }
 MGSolver::~MGSolver()
 {

@@ -156,8 +156,17 @@ std::vector<double> MapSpec::dxdXi(int mu, double dXi_, int lo, int n, int nodeT
 }
 
 // ---------------------------------------------------------------------------------------------
-Field::Field(Op* op_, int c) : op(op_), centering(c) { d = op->alloc(); }
-Field::~Field() { if (d) cudaFree(d); }
+Field::Field(Op* op_, int c) : op(op_), centering(c)
+{
+    d = op->alloc();
+    SB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    SB_CUDA(cudaEventRecord(ready, op->ctx->st));
+}
+Field::~Field()
+{
+    if (ready) cudaEventDestroy(ready);
+    if (d) cudaFree(d);
+}
 
 double* Op::alloc() const
 {
@@ -181,6 +190,7 @@ Op::Op(Context* c, const sb_level_desc& d) : ctx(c)
     if (dim == 2 && domain.size(1) != 1) SB_FAIL("dim == 2 requires a single layer in slot 1");
     map.kind = d.map_kind; map.fn = d.map_fn; map.user = d.map_user;
     alpha = d.alpha; beta = d.beta; relaxMethod = d.relax_method;
+    { const char* gk = getenv("SB_GSRB_KERNEL"); gsrbNatural = gk && std::string(gk) == "natural"; }  // test knob, read at creation
     if (d.num_boxes <= 0) SB_FAIL("empty box list");
     boxes.resize(d.num_boxes); boxRank.resize(d.num_boxes);
     for (int b = 0; b < d.num_boxes; ++b) {
@@ -394,6 +404,7 @@ void Op::fillMetricFromMap()
 Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
 {
     dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth + 1; flatZ = f.flatZ;
+    gsrbNatural = f.gsrbNatural;
     refined = f.refined;  // the coarse-fine sides stay (coarsened CFRegion, PoissonOp.cpp:392-396), with homogeneous ghosts only
     std::memcpy(amrCrseDXi, f.amrCrseDXi, sizeof(amrCrseDXi));  // not scaled (PoissonOp.cpp:345)
     std::memcpy(periodic, f.periodic, sizeof(periodic));
@@ -427,7 +438,7 @@ Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
 Op::Op(Context* single, const Op& f) : ctx(single)
 {
     dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth; flatZ = f.flatZ;
-    refined = f.refined;
+    refined = f.refined; gsrbNatural = f.gsrbNatural;
     std::memcpy(amrCrseDXi, f.amrCrseDXi, sizeof(amrCrseDXi));
     std::memcpy(periodic, f.periodic, sizeof(periodic));
     std::memcpy(bcAlpha, f.bcAlpha, sizeof(bcAlpha));
@@ -732,13 +743,21 @@ void Op::residual(double* res, double* phi, const double* rhs, bool homog)
     ctx->profEnd("residual", depth, e0);
 }
 
-void Op::checkPivot()
+int Op::readPivotFlag(bool reset)
 {
     int flag = 0;
     SB_CUDA(cudaMemcpyAsync(&flag, pivotFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
     ctx->sync();
+    if (flag && reset) SB_CUDA(cudaMemset(pivotFlag, 0, sizeof(int)));
+    return flag;
+}
+void Op::checkPivot()
+{
+    if (relaxMethod != SB_RELAX_VERTLINE || lineFast) return;  // only vertline_k raises the flag
+    double f = (double)readPivotFlag(true);
+    ctx->allreduceMax(&f, 1);
+    const int flag = (int)f;
     if (flag) {
-        SB_CUDA(cudaMemset(pivotFlag, 0, sizeof(int)));
         SB_FAIL("vertical line relaxation met a column where LAPACK dgtsv pivots or is singular (flag " + std::to_string(flag) +
                 "); the B200 path does not reproduce that branch");
     }
@@ -893,8 +912,7 @@ void Op::linePasses(int iters)
 
 void Op::relax(double* cor, const double* res, int iters, bool resUnchanged, int pre)
 {
-    const char* const gk          = getenv("SB_GSRB_KERNEL");  // "natural" keeps point GSRB on the natural layout (tests)
-    const bool        gsrbNatural = gk && std::string(gk) == "natural";
+
     const bool gsrbSplit = relaxMethod == SB_RELAX_GSRB && iters >= 2 && !gsrbNatural;
     if (pre != RELAX_PRE_NONE) {
         if (relaxMethod == SB_RELAX_VERTLINE && lineSplit && iters >= 2) { relaxLineSplit(cor, res, iters, resUnchanged, pre); return; }

@@ -12,6 +12,12 @@ CASES = {
     "gsrb_cart": dict(nx=(32, 32, 32), L=(1.0, 1.0, 8.0), max_box=(16, 16, 0), bf=4, periodic=(0, 0, 0), relax=5, map="cartesian", ampl=(0, 0, 0)),
     "gsrb_stretch": dict(nx=(32, 16, 32), L=(1.0, 1.0, 6.0), max_box=(16, 16, 0), bf=4, periodic=(0, 0, 0), relax=5, map="stretched", ampl=(0.04, 0.0, 0.3)),
     "gsrb_perxy": dict(nx=(16, 16, 32), L=(1.0, 1.0, 6.0), max_box=(8, 8, 0), bf=4, periodic=(1, 1, 0), relax=5, map="cartesian", ampl=(0, 0, 0)),
+    # the S-family of SURVEY.md 8d at depths that are multiples of 64, so that the production instance of the line kernel
+    # (vertline_fused_k<8,4,2,ALIGNED=true>, the one bench.py times) meets the oracle directly
+    "s_line64": dict(nx=(64, 64, 64), L=(1.0, 1.0, 1.0), max_box=(32, 32, 0), bf=16, periodic=(0, 0, 0), relax=6, map="cartesian", ampl=(0, 0, 0)),
+    "s_line64_zstretch": dict(nx=(64, 32, 64), L=(1.0, 0.5, 1.0), max_box=(32, 32, 0), bf=16, periodic=(0, 0, 0), relax=6, map="stretched", ampl=(0, 0, -0.1)),
+    "s_line128": dict(nx=(128, 128, 128), L=(2.0, 2.0, 1.0), max_box=(64, 64, 0), bf=16, periodic=(0, 0, 0), relax=6, map="cartesian", ampl=(0, 0, 0)),
+    "s_line256": dict(nx=(128, 128, 256), L=(2.0, 2.0, 1.0), max_box=(0, 0, 0), bf=16, periodic=(0, 0, 0), relax=6, map="cartesian", ampl=(0, 0, 0)),
     "onebox": dict(nx=(16, 16, 8), L=(1.0, 1.0, 1.0), max_box=(0, 0, 0), bf=4, periodic=(0, 0, 0), relax=6, map="cartesian", ampl=(0, 0, 0)),
 }
 

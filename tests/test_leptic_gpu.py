@@ -117,6 +117,26 @@ def test_leptic_solve_2d(ctx, name):
 
 
 @pytest.mark.skipif(not have_ref(2), reason="oracle/_ref/d2/somar_ref not built")
+@pytest.mark.parametrize("tol", [1e-8, 1e-9])
+def test_c2_djl_lev2_swap_counts_above_the_floor(ctx, tol):
+    """The DJL grid at the resolution of its finest AMR level (Leptic_MG) with tolerances ABOVE the fp64 residual floor of
+    that grid (5e-11 |r_0|): the number of leptic / V-cycle swaps, i.e. the length of the history, must be the reference's
+    (test_leptic_solve_2d[c2_djl_lev2] runs the deck's own 1e-12 and can only compare the common prefix)."""
+    c, mode = LEPTIC2D["c2_djl_lev2"]
+    over = {"absTol": 1e-12, "relTol": tol}
+    op = t2.make_op(ctx, c)
+    rhs0 = t2.rand_field(c, 4, zero_mean=True)
+    ref = run_ref("solve", inp=[rhs0], extra=_proj_overrides(over), **t2.ref_kwargs(c))
+    solver = sb.LevelHybridSolver(op, sb.default_options(**over))
+    phi, rhs = op.field(), op.field(data=t2.up(rhs0))
+    st = solver.solve(phi, rhs)
+    assert st.status == 1 and int(ref.kv["status"]) == 1
+    check(st, phi.download(), ref, mode)     # equal history length asserted inside
+    solver.free()
+    op.free()
+
+
+@pytest.mark.skipif(not have_ref(2), reason="oracle/_ref/d2/somar_ref not built")
 def test_c2_djl_projection(ctx):
     """BASELINE.json configs[1] on its base level: projection of a random, wall-compatible velocity."""
     c, mode = LEPTIC2D["c2_djl_base"]
