@@ -34,6 +34,7 @@ NX = (1024, 1024, 256)
 LDOM = (16.0, 16.0, 1.0)
 BOX = (128, 128, 0)
 BLOCK_FACTOR = 16
+LINE_KERNEL = "vertline_fused_k<8,4,2,true>"
 METRIC = "pressure-solve DOF/s per V-cycle"
 UNIT = "DOF/s"
 # Bytes per cell of one full line-relaxation iteration (both colours).
@@ -45,9 +46,41 @@ UNIT = "DOF/s"
 #    survey-convention number is given next to it.
 RELAX_BYTES_PER_CELL_ITER_SURVEY = 40.0
 RELAX_BYTES_PER_CELL_ITER = 24.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one depth-0 launch on one GPU, from the ncu --set full
-# capture summarised in profiles/r1_v4_summary.md
-NCU_TRAFFIC_PER_LAUNCH_N1 = 3.2286e9
+# dram__bytes_read.sum + dram__bytes_write.sum of one depth-0 launch on one GPU come from the tracked ncu --set full
+# summary of the round (profiles/traffic.json, written by tools/summarize_profile.py from the capture's raw CSV)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")
+# Decomposition-independent results of the N = 1 run (norms are per reference box, the right-hand side is built per
+# reference box): every run at any N must reproduce them to 1e-10 of the initial residual norm.
+CHECK_FILE = os.path.join(ROOT, "tests", "golden", "bench_s5_checks.json")
+
+
+def ncu_traffic(kernel_prefix):
+    try:
+        with open(TRAFFIC_FILE) as f:
+            d = json.load(f)
+        for k, v in d.get("kernels", {}).items():
+            if k.startswith(kernel_prefix):
+                return float(v["dram_bytes_per_launch"]), d.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
+def verify_checks(checks, world):
+    """Compare this run's decomposition-independent numbers with the committed N = 1 values."""
+    if not os.path.exists(CHECK_FILE):
+        return {"ok": None, "note": "tests/golden/bench_s5_checks.json not committed yet"}
+    with open(CHECK_FILE) as f:
+        want = json.load(f)
+    scale = want["res_norm_init"]
+    bad = {}
+    for k in ("res_norm_init", "cor_norm_after_step", "res_norm_after_step", "solve_final_res_norm", "dot_cor_res"):
+        tol = 1e-10 * (scale if "res" in k else abs(want[k]))
+        if abs(checks[k] - want[k]) > tol:
+            bad[k] = [checks[k], want[k]]
+    if checks["solve_iters"] != want["solve_iters"] or checks["solve_status"] != want["solve_status"]:
+        bad["solve_iters/status"] = [[checks["solve_iters"], checks["solve_status"]], [want["solve_iters"], want["solve_status"]]]
+    return {"ok": not bad, "against": "tests/golden/bench_s5_checks.json (N = 1)", "tolerance": "1e-10 of the initial residual norm", "mismatch": bad}
 
 
 def read_peaks():
@@ -258,6 +291,7 @@ def run_ours(args):
             f.free()
         return wall / steps
 
+    failed = False
     if args.profile_mode:
         step()
         ms, wall_ms, launches = timed(step, args.steps)
@@ -292,6 +326,15 @@ def run_ours(args):
                   "what": "MGSolver::solve (FMG, reference defaults) on the same grid and right-hand side, device time on rank 0"}
     phi_s.free()
 
+    # Decomposition-independent checks: the same numbers at every N.
+    step()
+    tmp = op.field()
+    op.residual(tmp, cor, res)
+    checks = {"res_norm_init": op.norm(res, 2), "cor_norm_after_step": op.norm(cor, 2), "res_norm_after_step": op.norm(tmp, 2),
+              "dot_cor_res": op.dotProduct(cor, res), "solve_final_res_norm": float(st_solve.final_res_norm),
+              "solve_iters": int(st_solve.num_iters), "solve_status": int(st_solve.status)}
+    tmp.free()
+
     # end to end with host buffers
     step_e2e()
     e_ms, e_wall, _ = timed(step_e2e, max(1, min(args.steps, 3)))
@@ -302,6 +345,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = read_peaks()
+        traffic, traffic_src = ncu_traffic("vertline_fused_k")
         ms_per_step = ms / args.steps
         value = ncell / (ms_per_step * 1e-3)
         cells_per_launch = ncell_tile  # one colour pass sweeps the whole tile (half the columns are solved)
@@ -327,9 +371,9 @@ def run_ours(args):
             "gpu_launches": launches,
             "solve": solve_info,
             "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": {"bound": "hbm", "kernel": "vertline_split_k (one colour pass of vertical line relaxation, depth 0)",
+            "roofline": {"bound": "hbm", "kernel": LINE_KERNEL + " (one colour pass of vertical line relaxation, depth 0)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_PER_LAUNCH_N1 if world == 1 else None,
+                         "traffic": traffic if world == 1 else None, "traffic_source": traffic_src,
                          "bytes_counted": "12 B per grid cell per colour pass: phi(other colour) read, rhs + phi(own colour) read/write; "
                                           "the kernel has no J/Dinv operands",
                          "survey_convention": {"bytes_per_cell_per_pass": RELAX_BYTES_PER_CELL_ITER_SURVEY / 2.0, "achieved": survey,
@@ -340,13 +384,23 @@ def run_ours(args):
                          "share_of_step": tot_line / (ms_per_step if ms_per_step > 0 else 1.0),
                          "residual_launch_ms": r_ms / max(r_n, 1)},
             "clocks": clocks,
+            "checks": dict(checks, verify=verify_checks(checks, world)),
         }
+        if args.write_checks and world == 1:
+            with open(CHECK_FILE, "w") as f:
+                json.dump(checks, f, indent=1)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(cores=None, reps=1)
         print(json.dumps(out))
+        if out["checks"]["verify"]["ok"] is False and not args.no_verify:
+            sys.stderr.write("bench.py: decomposition-independent checks differ from the committed N = 1 values: %s\n"
+                             % json.dumps(out["checks"]["verify"]["mismatch"]))
+            failed = True
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if failed:
+        raise SystemExit(3)
 
 
 def ref_binary():
@@ -378,6 +432,15 @@ def _run_ref_copies(cores, reps, td):
     return n, np.array(times)
 
 
+def toolchain_probe():
+    """the genuine MPI + Fortran build of the reference needs mpirun, gfortran and LAPACK."""
+    import shutil
+    have = {t: shutil.which(t) is not None for t in ("mpirun", "gfortran", "scons")}
+    if all(have.values()):
+        return "mpirun, gfortran and scons are on this host, but the oracle build (restated Fortran leaves, serial) is what is timed"
+    return "no " + "/".join(t for t, h in have.items() if not h) + " on this host, so the MPI + Fortran build cannot be made"
+
+
 def cpu_baseline(cores=None, reps=1):
     if not os.path.exists(ref_binary()):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/d3/somar_ref not built"}
@@ -388,7 +451,7 @@ def cpu_baseline(cores=None, reps=1):
     per_copy = t.mean(axis=1)  # seconds per V-cycle of each copy
     value = float(sum(ncell / s for s in per_copy))
     return {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": f"{cores} concurrent copies (1 per core, no MPI available) of the reference's vCycle_residualEq on one S5 box "
+            "sample": f"{cores} concurrent copies (1 per core; {toolchain_probe()}) of the reference's vCycle_residualEq on one S5 box "
                       f"{n[0]}x{n[1]}x{n[2]} (same dXi, same 16+16 smoothing), {reps} V-cycle(s) each; "
                       f"{float(per_copy.mean()):.2f} s per V-cycle per core"}
 
@@ -401,18 +464,19 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/d3/somar_ref not built (needs /root/reference at build time)"}))
         return
     cores = min(os.cpu_count() or 1, 32)
-    warm, steps = max(args.warmup, 0), max(args.steps, 1)
-    # bounded: each step is one V-cycle on one box per core (~10 s); cap the total
-    warm, steps = min(warm, 1), min(steps, 3)
+    # bounded: each step is one V-cycle on one box per core (~6 s): 3 warm-up + 5 timed whatever K and W ask for
+    warm, steps = 3, 5
     t0 = time.perf_counter()
     with tempfile.TemporaryDirectory() as td:
         n, t = _run_ref_copies(cores, warm + steps, td)
     ncell = n[0] * n[1] * n[2]
+    import numpy as np
     t = t[:, warm:]
-    per_copy = t.mean(axis=1)
+    per_copy = np.median(t, axis=1)
     value = float(sum(ncell / s for s in per_copy))
-    sample = (f"{cores} concurrent copies (1 per core; the reference is MPI-only and there is no MPI here) of the reference's "
-              f"preCond + vCycle_residualEq on one S5 box {n[0]}x{n[1]}x{n[2]} (same dXi and smoothing); {steps} timed V-cycles each")
+    sample = (f"{cores} concurrent copies (1 per core; the reference parallelises by MPI rank over boxes; {toolchain_probe()}) of the "
+              f"reference's vCycle_residualEq on one S5 box {n[0]}x{n[1]}x{n[2]} (same dXi and smoothing, no halo exchange paid); "
+              f"{warm} warm-up + {steps} timed V-cycles each, median per copy")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": float(per_copy.mean() * 1e3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -432,6 +496,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="report the decomposition-independent checks without failing on a mismatch")
+    ap.add_argument("--write-checks", action="store_true", help="N = 1 only: (re)write tests/golden/bench_s5_checks.json from this run")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: one warm-up step, K timed steps, no e2e / cpu legs (numbers printed are not bench values)")
     args = ap.parse_args()

@@ -243,6 +243,10 @@ int sb_op_reflux_flux(sb_op* op, sb_field* div, sb_field* const flux[3], sb_fiel
 int sb_op_comp_divergence(sb_op* op, sb_field* div, sb_field* const flux[3], sb_field* const fine_flux[3], sb_op* finer_op);
 /* levelGradient / compGradient(gradPhi, phi, crsePhiPtr, time, homogPhys, homogCFI) (PoissonOp.cpp:1486-1561) */
 int sb_op_comp_gradient(sb_op* op, sb_field* const grad[3], sb_field* phi, sb_field* crse_phi, int homog_phys, int homog_cfi);
+/* CFInterp::coarsen(crse, fine, false, NULL) (CFInterp.cpp:846-865), what AMRNSLevel::averageDown does to the composite
+ * right-hand side before the sync projection's solve (AMRNSLevelUtil.cpp:748-781, AMRNSLevelProject.cpp:752): the cells
+ * of the coarser level under the fine level become the block averages of the fine data. */
+int sb_op_average_down(sb_op* fine_op, sb_field* crse, sb_field* fine);
 /* Bounding box of the level's boxes (the refined patch; the domain on a base level) and this rank's tile. */
 int sb_op_get_patch(sb_op* op, int patch_lo[3], int patch_hi[3], int tile_lo[3], int tile_hi[3]);
 

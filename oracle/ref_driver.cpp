@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "BCTools.H"
+#include "CFInterp.H"
 #include "CartesianMap.H"
 #include "DisjointBoxLayout.H"
 #include "FluxBox.H"
@@ -415,7 +416,9 @@ main(int argc, char* argv[])
             for (DataIterator dit(vgrids[l]); dit.ok(); ++dit) { (*phi[l])[dit].setVal(0.0); (*rhs[l])[dit].setVal(0.0); }
             off[l + 1] = off[l] + vregion[l].numPts();
         }
-        if (in.size() < off[nlev]) MayDay::Error("drv.in too short for the level data");
+        int compProjectEarly = 0;
+        drv.query("compProject", compProjectEarly);
+        if (!compProjectEarly && in.size() < off[nlev]) MayDay::Error("drv.in too short for the level data");
         auto tag = [&](const char* base, int l) { return std::string(base) + char('0' + l); };
 
         int cfOnly = 0;
@@ -471,6 +474,66 @@ main(int argc, char* argv[])
             for (int l = 0; l < nlev; ++l) scatter(*phi[l], in.data() + off[l], vregion[l]);
             compResidual(phi, "minusL", true);
             g_amrNorms.clear();
+            return 0;
+        }
+        int compProject = 0;
+        drv.query("compProject", compProject);
+        if (compProject) {
+            // The composite (sync) projection, AMRNSLevel::projectDownToThis (Grade5_SOMAR/AMRNSLevelProject.cpp:740-860),
+            // restated around the reference's own operator calls (Grade5 is not part of this build): compDivergence with
+            // refluxing per level, averageDown of the right-hand side (AMRNSLevelUtil.cpp:748-781 -> CFInterp::coarsen),
+            // AMRHybridSolver::solve, compGradient with coarse-level CF BCs, vel -= grad, final compDivergence.
+            //   drv.in: per level, the D face fields of the advecting velocity over the level's region.
+            std::vector<std::shared_ptr<LevelData<FluxBox>>> vel(nlev), grad(nlev);
+            size_t                                           o = 0;
+            for (int l = 0; l < nlev; ++l) {
+                vel[l].reset(new LevelData<FluxBox>(vgrids[l], 1));
+                grad[l].reset(new LevelData<FluxBox>(vgrids[l], 1));
+                for (int d = 0; d < SpaceDim; ++d) {
+                    const Box fc = surroundingNodes(vregion[l], d);
+                    if (in.size() < o + fc.numPts()) MayDay::Error("drv.in too short for the level velocities");
+                    for (DataIterator dit(vgrids[l]); dit.ok(); ++dit) scatterFAB((*vel[l])[dit][d], vgrids[l][dit], in.data() + o, fc);
+                    o += fc.numPts();
+                }
+            }
+            std::vector<const PoissonOp*> pops(nlev);
+            for (int l = 0; l < nlev; ++l) pops[l] = static_cast<const PoissonOp*>(&*vOps[l]);
+            auto compDiv = [&](const char* name) {
+                for (int l = 0; l < nlev; ++l) pops[l]->compDivergence(*rhs[l], *vel[l], l + 1 < nlev ? &*vel[l + 1] : nullptr);
+                for (int l = 0; l < nlev; ++l) out.put(tag(name, l), gather(*rhs[l], vregion[l]));
+            };
+            compDiv("div_init");
+            for (int l = nlev - 1; l > 0; --l) {
+                CFInterp interp;
+                interp.define(vgrids[l], (l == 0 ? levGeo : *vgeo[l]).getDXi(), vgrids[l - 1]);
+                interp.coarsen(*rhs[l - 1], *rhs[l], false, nullptr);
+            }
+            for (int l = 0; l < nlev; ++l) out.put(tag("rhs", l), gather(*rhs[l], vregion[l]));
+            Elliptic::AMRHybridSolver amr;
+            amr.define(vOps, 0, nlev - 1, Elliptic::AMRHybridSolver::getDefaultOptions());
+            Vector<LDFAB*>       vphi(nlev);
+            Vector<const LDFAB*> vrhs(nlev);
+            for (int l = 0; l < nlev; ++l) { vphi[l] = &*phi[l]; vrhs[l] = &*rhs[l]; }
+            g_amrNorms.clear();
+            Elliptic::SolverStatus st = amr.solve(vphi, vrhs, 0.0, true, true);
+            out.put("amrLevelNorms", g_amrNorms);
+            out.kv("status", st.getSolverStatus());
+            for (int l = 0; l < nlev; ++l) {
+                pops[l]->compGradient(*grad[l], *phi[l], l > 0 ? &*phi[l - 1] : nullptr, 0.0, true, false);
+                for (DataIterator dit(vgrids[l]); dit.ok(); ++dit)
+                    for (int d = 0; d < SpaceDim; ++d) (*vel[l])[dit][d].plus((*grad[l])[dit][d], -1.0);
+            }
+            for (int l = 0; l < nlev; ++l) {
+                out.put(tag("phi", l), gather(*phi[l], vregion[l]));
+                for (int d = 0; d < SpaceDim; ++d) {
+                    const Box           fc = surroundingNodes(vregion[l], d);
+                    std::vector<double> v(fc.numPts(), 0.0);
+                    for (DataIterator dit(vgrids[l]); dit.ok(); ++dit) gatherFAB(v, (*vel[l])[dit][d], vgrids[l][dit], fc);
+                    out.put(std::string("vel") + char('0' + l) + "_" + char('0' + d), v);
+                }
+            }
+            compDiv("div_final");
+            out.kv("numLevels", nlev);
             return 0;
         }
         for (int l = 0; l < nlev; ++l) scatter(*rhs[l], in.data() + off[l], vregion[l]);

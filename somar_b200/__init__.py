@@ -474,6 +474,10 @@ class PoissonOp:
         ff = self._f3(fine_flux) if fine_flux is not None else None
         capi.check(self.lib.sb_op_comp_divergence(self.h, div.h, self._f3(flux), ff, finer_op.h if finer_op else None))
 
+    def averageDown(self, crse, fine):
+        """CFInterp::coarsen: this (fine) level's data averaged onto the coarser level's covered cells."""
+        capi.check(self.lib.sb_op_average_down(self.h, crse.h, fine.h))
+
     def compGradient(self, grad, phi, crse_phi=None, homog_phys=True, homog_cfi=True):
         capi.check(self.lib.sb_op_comp_gradient(self.h, self._f3(grad), phi.h, crse_phi.h if crse_phi else None, int(homog_phys),
                                                 int(homog_cfi)))

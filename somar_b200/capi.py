@@ -152,6 +152,7 @@ PROTOTYPES = {
     "sb_op_reflux_flux": (C.c_int, [P, P, F3, F3, P]),
     "sb_op_comp_divergence": (C.c_int, [P, P, F3, PP, P]),
     "sb_op_comp_gradient": (C.c_int, [P, F3, P, P, C.c_int, C.c_int]),
+    "sb_op_average_down": (C.c_int, [P, P, P]),
     "sb_op_get_patch": (C.c_int, [P, IP, IP, IP, IP]),
     "sb_amr_solver_create": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, C.POINTER(MGOptions), PP]),
     "sb_amr_solver_destroy": (C.c_int, [P]),

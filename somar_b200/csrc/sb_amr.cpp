@@ -388,6 +388,14 @@ void Op::compDivergence(double* div, double* const flux[3], Op* fineOp, double* 
     if (fineOp) refluxFlux(div, flux, *fineOp, fineFlux);
 }
 
+void Op::averageDownTo(Op& crseOp, double* crse, const double* fine)
+{
+    checkCrse(*this, crseOp);
+    CFLink& L = *cf;
+    k::restrict_avg(st(), lay, L.cfLay, L.ref, L.cfA, fine);        // localCoarsen -> CFINTERP_UNMAPPEDAVERAGE
+    L.cfToCrse.exec(ctx, L.cfLay, L.cfA, crseOp.lay, crse);         // localCrse.copyTo(a_crse, m_crseToUserCopier)
+}
+
 // PoissonOp::AMRNormLevel (PoissonOp.cpp:1225-1286): per box, the cells under the finer level count as zero and
 // numPts stays the box's (FArrayBox::norm(validBox, p)); powScale = prod(dXi).
 double Op::AMRNormLevel(const double* x, const Op* fineOp, int p)

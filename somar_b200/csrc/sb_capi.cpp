@@ -533,6 +533,12 @@ int sb_op_comp_gradient(sb_op* op, sb_field* const grad[3], sb_field* phi, sb_fi
     }
     SB_END
 }
+int sb_op_average_down(sb_op* fine_op, sb_field* crse, sb_field* fine)
+{
+    SB_TRY DEVG(fine_op) sameOp(fine_op, {fine}); REQ(crse);
+    OPF(fine_op).averageDownTo(*crse->f.op, D(crse), D(fine));
+    SB_END
+}
 int sb_op_get_patch(sb_op* op, int patch_lo[3], int patch_hi[3], int tile_lo[3], int tile_hi[3])
 {
     SB_TRY DEVG(op) REQ(op);

@@ -229,6 +229,9 @@ struct Op {
     double AMRNormLevel(const double* res, const Op* fineOp, int p);                      // :1225-1286
     void   getFlux(double* const flux[3], const double* phi);                             // :1295-1326, all boxes
     void   compDivergence(double* div, double* const flux[3], Op* fineOp, double* const fineFlux[3]);  // :1618-1631
+    // CFInterp::coarsen(crse, fine, harmonic = false, J = nullptr) (CFInterp.cpp:846-865): block average of this (fine)
+    // level's data onto the cells of the coarser level it covers -- AMRNSLevel::averageDown (AMRNSLevelUtil.cpp:748-781)
+    void   averageDownTo(Op& crseOp, double* crse, const double* fine);
 };
 
 // partial: the boxes form a rectangular patch inside the domain (refined AMR level) instead of covering it

@@ -205,3 +205,34 @@ SPEC_CASES = dict({n: c for n, c in AMR_CASES.items() if len(c["nx"]) == 3 and "
 })
 
 
+
+
+def rand_velocity_levels(c, seed):
+    """Random advecting face velocity on every level: D face arrays over the level's region, zero normal component on
+    non-periodic domain walls, equal values on periodic images (so the composite divergence integrates to zero)."""
+    rng = np.random.default_rng(seed)
+    D = ndim(c)
+    pick = (lambda v: np.array([v[0], v[2]])) if D == 2 else (lambda v: np.array(v))
+    out = []
+    for s, sh in zip(level_specs(c), level_shapes(c)):
+        lo, hi = pick(s["reg_lo"]), pick(s["reg_hi"])
+        dlo, dhi = pick(s["dom_lo"]), pick(s["dom_hi"])
+        lev = []
+        for d in range(D):
+            shape = list(sh)
+            shape[d] += 1
+            u = rng.standard_normal(tuple(shape))
+            first, last = [slice(None)] * D, [slice(None)] * D
+            first[d], last[d] = 0, -1
+            at_lo, at_hi = lo[d] == dlo[d], hi[d] == dhi[d]
+            if c["periodic"][d]:
+                if at_lo and at_hi:
+                    u[tuple(last)] = u[tuple(first)]
+            else:
+                if at_lo:
+                    u[tuple(first)] = 0.0
+                if at_hi:
+                    u[tuple(last)] = 0.0
+            lev.append(np.asfortranarray(u))
+        out.append(lev)
+    return out
