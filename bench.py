@@ -75,7 +75,7 @@ def verify_checks(checks, world):
     scale = want["res_norm_init"]
     bad = {}
     for k in ("res_norm_init", "cor_norm_after_step", "res_norm_after_step", "solve_final_res_norm", "dot_cor_res"):
-        tol = 1e-10 * (scale if "res" in k else abs(want[k]))
+        tol = 1e-10 * (scale if "res_norm" in k else abs(want[k]))
         if abs(checks[k] - want[k]) > tol:
             bad[k] = [checks[k], want[k]]
     if checks["solve_iters"] != want["solve_iters"] or checks["solve_status"] != want["solve_status"]:
