@@ -210,10 +210,11 @@ size_t vertline_smem_bytes(int nz);
 void vertline_smem_pass(cudaStream_t st, const Lay& L, const Coef& c, const double* tab, double* phi, const double* rhs, int pass);
 // colour-split storage (SLay): conversion, ghost fill / face pack of directions x and y, and the
 // line relaxation on it.  s[c] = array of colour c.
+// scale (per level) or scaleJ / beta (per cell: value / (beta * scaleJ)) may be given, not both
 void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1, const double* scale,
-                 const double* shift = nullptr);
+                 const double* shift = nullptr, const double* scaleJ = nullptr, double beta = 1.0);
 void split_precond(cudaStream_t st, const Lay& L, const SLay& S, const double* res, const double* Dinv, const double* scale,
-                   double* c0, double* c1, double* r0, double* r1);
+                   double* c0, double* c1, double* r0, double* r1, const double* scaleJ = nullptr, double beta = 1.0);
 void unsplit_field(cudaStream_t st, const Lay& L, const SLay& S, double* nat, const double* s0, const double* s1);
 void fill_ghosts_split(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC bc[3][2], int dim, bool physToo);
 // vertical sides of a split field with z ghosts (S.zg = 1): Robin / periodic, as fill_ghosts_dir_k

@@ -6,6 +6,7 @@
 #include <map>
 
 #include "sb_core.h"
+#include "sb_line_tma.h"
 
 namespace sb {
 
@@ -147,6 +148,15 @@ struct Op {
     double* lineTabS = nullptr;
     bool    lineSplit = false;
     double* sp[4] = {nullptr, nullptr, nullptr, nullptr};
+    // TMA-staged persistent line kernel (sb_line_tma.cu).  lineTma: use it for the shared-matrix case on this depth (large
+    // enough, aligned); lineGeneral: horizontally varying metric -- the per-column factorisation is recomputed in the kernel
+    // (tables [MzL | MzR], gstart) and the right-hand side is scaled by 1 / (beta J) cell by cell.
+    bool    lineTma = false, lineGeneral = false, lineTmaAllowed = true, tmaMapsReady = false;
+    LineTmaMap tmaOth[2], tmaRhs[2];   // tensor maps of sp[0], sp[1] (as the other colour) and sp[2], sp[3] (right-hand sides)
+    double* lineTabG = nullptr;         // general: [MzL | MzR]
+    double* gstart = nullptr;           // general: [NW - 1][ny][nx]
+    double  lineSLo = 0.0, lineSHi = 0.0;
+    void    linePass(int pass, int region = 0, int nbMask = 0);  // one colour pass on sp[], whichever kernel applies
     const double* splitResSrc = nullptr;  // natural-layout field whose split copy sp[2], sp[3] hold
     // point GSRB on colour-split storage with z ghosts (sb_line.cu: gsrb_split_k): cor, rhs, J, Dinv x 2 colours
     SLay    slayG;
@@ -175,6 +185,7 @@ struct Op {
     void    fillMetricFromMap();          // LevelGeometry::createMetricCache, LevelGeometry.cpp:238-277
     void    cacheMatrixElements();        // PoissonOp.cpp:510-665
     void    buildLineTables(double sLo, double sHi);
+    void    buildGeneralLine(double sLo, double sHi);
     bool    checkForNullSpace();          // PoissonOp.cpp:670-696
     void    finalize();                   // setAlphaAndBeta, PoissonOp.cpp:707-718
     Coef    coef() const;

@@ -46,7 +46,8 @@ __device__ __forceinline__ double* scell(const SLay& S, double* s0, double* s1, 
 // null-space removal of PoissonOp::removeKernel (PoissonOp.cpp:838-842) that would otherwise be a
 // pass of its own.
 __global__ void split_field_k(Lay L, SLay S, const double* __restrict__ nat, double* __restrict__ s0, double* __restrict__ s1,
-                              const double* __restrict__ scale, const double* __restrict__ shift)
+                              const double* __restrict__ scale, const double* __restrict__ shift, const double* __restrict__ scaleJ,
+                              double beta)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -60,6 +61,10 @@ __global__ void split_field_k(Lay L, SLay S, const double* __restrict__ nat, dou
     if (two) { const double2 v = *reinterpret_cast<const double2*>(nat + q); e = v.x; o = v.y; }
     else e = nat[q];
     if (scale) { e = e * f; o = o * f; }
+    if (scaleJ) {  // mapped grid: 1 / (beta J) differs from cell to cell
+        e = e * (1.0 / (beta * scaleJ[q]));
+        if (two) o = o * (1.0 / (beta * scaleJ[q + 1]));
+    }
     if (shift) { const double avg = shift[0] / shift[1]; e = e - avg; o = o - avg; }
     const int       ce = S.colour(i, j);
     const long long d  = S.idx(i, j, k);
@@ -71,15 +76,16 @@ __global__ void split_field_k(Lay L, SLay S, const double* __restrict__ nat, dou
 // res and Dinv.
 __global__ void split_precond_k(Lay L, SLay S, const double* __restrict__ res, const double* __restrict__ Dinv,
                                 const double* __restrict__ scale, double* __restrict__ c0, double* __restrict__ c1,
-                                double* __restrict__ r0, double* __restrict__ r1)
+                                double* __restrict__ r0, double* __restrict__ r1, const double* __restrict__ scaleJ, double beta)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = blockIdx.z;
     const int i = 2 * t;
     if (i >= L.nx || j >= L.ny) return;
-    const double    f = scale[k];
     const long long q = L.idx(i, j, k);
+    double          f = scale ? scale[k] : 0.0, f2 = f;
+    if (scaleJ) { f = 1.0 / (beta * scaleJ[q]); f2 = i + 1 < L.nx ? 1.0 / (beta * scaleJ[q + 1]) : 0.0; }
     double          re, ro = 0.0, de, dd = 0.0;
     const bool      two = i + 1 < L.nx;
     if (two) {
@@ -91,7 +97,7 @@ __global__ void split_precond_k(Lay L, SLay S, const double* __restrict__ res, c
     const long long d  = S.idx(i, j, k);
     (ce ? c1 : c0)[d] = re * de;
     (ce ? r1 : r0)[d] = re * f;
-    if (two) { (ce ? c0 : c1)[d] = ro * dd; (ce ? r0 : r1)[d] = ro * f; }
+    if (two) { (ce ? c0 : c1)[d] = ro * dd; (ce ? r0 : r1)[d] = ro * f2; }
 }
 __global__ void unsplit_field_k(Lay L, SLay S, double* __restrict__ nat, const double* __restrict__ s0,
                                 const double* __restrict__ s1)
@@ -111,19 +117,19 @@ __global__ void unsplit_field_k(Lay L, SLay S, double* __restrict__ nat, const d
     } else nat[q] = e;
 }
 void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1, const double* scale,
-                 const double* shift)
+                 const double* shift, const double* scaleJ, double beta)
 {
     const dim3 b(64, 4, 1);
     const dim3 g(((L.nx + 1) / 2 + 63) / 64, (L.ny + 3) / 4, L.nz);
-    split_field_k<<<g, b, 0, st>>>(L, S, nat, s0, s1, scale, shift);
+    split_field_k<<<g, b, 0, st>>>(L, S, nat, s0, s1, scale, shift, scaleJ, beta);
     note_launch();
 }
 void split_precond(cudaStream_t st, const Lay& L, const SLay& S, const double* res, const double* Dinv, const double* scale,
-                   double* c0, double* c1, double* r0, double* r1)
+                   double* c0, double* c1, double* r0, double* r1, const double* scaleJ, double beta)
 {
     const dim3 b(64, 4, 1);
     const dim3 g(((L.nx + 1) / 2 + 63) / 64, (L.ny + 3) / 4, L.nz);
-    split_precond_k<<<g, b, 0, st>>>(L, S, res, Dinv, scale, c0, c1, r0, r1);
+    split_precond_k<<<g, b, 0, st>>>(L, S, res, Dinv, scale, c0, c1, r0, r1, scaleJ, beta);
     note_launch();
 }
 void unsplit_field(cudaStream_t st, const Lay& L, const SLay& S, double* nat, const double* s0, const double* s1)

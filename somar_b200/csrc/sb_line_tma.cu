@@ -1,0 +1,410 @@
+// sb_line_tma.cu -- vertical line relaxation, one colour pass, as a persistent warp-specialised kernel whose
+// operands arrive by TMA (cp.async.bulk.tensor, sm_100a): vertline_tma_k.
+//
+// Reference: PoissonOp::vertLineGSRB_relax (Grade3_Calculus/Elliptic/PoissonOp.cpp:1927-2010),
+// FORT_POISSONOP_VERTLINEGSRB_3D (Elliptic/PoissonOpF.ChF:851-1019) + LAPACK dgtsv (no-interchange branch).
+//
+// Why.  vertline_fused_k (sb_line.cu) moves exactly the bytes it has to (12 B per grid cell per pass) but
+// reaches 0.68 of the copy bandwidth: its loads are held in registers (128 per thread, 2 CTAs per SM) and
+// stop while a CTA resolves its carries and streams its backward sweep out (profiles/r1_v4_summary.md).
+// Here one CTA per SM walks over tiles (32 columns of one colour in one grid row, all levels):
+//   * a producer thread issues 3-D tensor-map loads -- the other colour's rows j-1, j, j+1 (34 wide: west
+//     and east neighbours come out of the same box) and this colour's right-hand side -- KZ levels per box,
+//     one ring of S stages per consumer warp, completion on mbarriers.  Bytes in flight cost shared memory,
+//     not registers, and the ring runs ahead across tile boundaries, so HBM requests never stop;
+//   * NW consumer warps each own a chunk of nz / NW levels and run the chunked Thomas sweeps of
+//     vertline_fused_k (same arithmetic, operation for operation: results are bit-identical).
+//
+// GENERAL = true is the mapped-grid form of the same kernel: with a horizontally varying metric the row-scaled
+// tridiagonal matrix of a column is T_z - h(i, j) I, h = MxL + MxR + MyL + MyR, so its Thomas factorisation
+// differs from column to column.  It is recomputed in the kernel, per lane (one reciprocal per cell), from the
+// 1-D tables M_x, M_y, M_z and the value of g = 1 / d' at the level below each chunk (a small 2-D table built
+// once per operator by line_gstart_k); the prefix products that vertline_fused_k reads from 1-D tables become
+// running products, and the chunk's g values are parked in shared memory for the fix-up and backward sweeps.
+// No J / Dinv operand, no HBM scratch: still 12 B per grid cell per pass (vertline_k: 43 B measured).
+#include <cuda.h>
+
+#include "sb_core.h"
+#include "sb_line_tma.h"
+
+namespace sb {
+namespace k {
+
+void note_launch();  // sb_kernels.cu (launch counter)
+
+namespace {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Blocks until the phase with the given parity has completed.  A watchdog turns a protocol error (a load that never
+// lands) into a launch failure instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    uint32_t       done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (spin > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void consumer_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+constexpr int OTHW = 34;  // box width of the other colour's rows: cells m0 - 1 .. m0 + 32
+__host__ __device__ constexpr int othBytes(int KZ) { return ((OTHW * 3 * KZ * 8 + 127) / 128) * 128; }
+__host__ __device__ constexpr int rhsBytes(int KZ) { return ((32 * KZ * 8 + 127) / 128) * 128; }
+}  // namespace
+
+// tab (shared matrix): {a', g}[N] | {P', c}[N] | R[N] | Pend[NW] | T[NW] | Rend[NW]   (Op::buildLineTables)
+// tab (general):       MzL[N] | MzR[N]
+template <int NW, int KZ, int S, bool GENERAL>
+__global__ void __launch_bounds__((NW + 1) * 32, 1)
+    vertline_tma_k(const __grid_constant__ CUtensorMap mapOth, const __grid_constant__ CUtensorMap mapRhs, SLay Sl, LineTmaArgs A)
+{
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int N  = Sl.nz;
+    const int CL = N / NW;
+    constexpr int OB = othBytes(KZ), RB = rhsBytes(KZ), SB = OB + RB;
+    unsigned char* const stages = smraw;                                   // [S][NW][SB]
+    double* const  sy  = reinterpret_cast<double*>(smraw + (size_t)S * NW * SB);  // [N][32]
+    double* const  sg  = sy + (size_t)N * 32;                              // [N][32] (GENERAL)
+    double* const  sum = sg + (GENERAL ? (size_t)N * 32 : 0);              // [2 sets][NSUM][NW][32]
+    constexpr int  NSUM = GENERAL ? 5 : 2;
+    double* const  ts  = sum + 2 * NSUM * NW * 32;                         // tables
+    const int      ntab = GENERAL ? 2 * N : 5 * N + 3 * NW;
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(ts + ((ntab + 1) & ~1));  // full[S][NW], empty[S][NW]
+    uint64_t* const full = bars;
+    uint64_t* const empt = bars + S * NW;
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nbx = A.nbx, ntiles = A.ntiles, nby = Sl.ny;
+    auto in_region = [&](int t) -> bool {
+        if (A.region == 0) return true;
+        const int  bx = t % nbx, j = t / nbx;
+        const bool edge = ((A.nbMask & 1) && bx == 0) || ((A.nbMask & 2) && bx == nbx - 1) || ((A.nbMask & 4) && j == 0) ||
+                          ((A.nbMask & 8) && j == nby - 1);
+        return edge == (A.region == 1);
+    };
+    auto next_tile = [&](int t) { do { t += gridDim.x; } while (t < ntiles && !in_region(t)); return t; };
+    int t0 = blockIdx.x;
+    while (t0 < ntiles && !in_region(t0)) t0 += gridDim.x;
+
+    for (int k = threadIdx.x; k < ntab; k += (NW + 1) * 32) ts[k] = A.tab[k];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2 * S * NW; ++i) mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nslab = CL / KZ;
+
+    if (w == NW) {
+        // ===== producer: one thread feeds every consumer warp's ring =====
+        if (lane == 0) {
+            int      stage = 0;
+            uint32_t phase = 0;
+            for (int t = t0; t < ntiles; t = next_tile(t)) {
+                const int bx = t % nbx, j = t / nbx;
+                const int x0 = SOX + bx * 32 - 1;  // element of cell m0 - 1 in a row of a colour array
+                for (int sl = 0; sl < nslab; ++sl) {
+                    for (int v = 0; v < NW; ++v) {
+                        uint64_t* fb = full + stage * NW + v;
+                        mbar_wait(empt + stage * NW + v, phase ^ 1);
+                        unsigned char* dst = stages + (size_t)(stage * NW + v) * SB;
+                        mbar_expect_tx(fb, OTHW * 3 * KZ * 8 + 32 * KZ * 8);
+                        tma_load_3d(dst, &mapOth, x0, j, v * CL + sl * KZ, fb);             // rows j-1 .. j+1 (array rows j .. j+2)
+                        tma_load_3d(dst + OB, &mapRhs, x0 + 1, j + 1, v * CL + sl * KZ, fb);  // row j
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const double2* const T1 = reinterpret_cast<const double2*>(ts);          // shared: {a', g}
+    const double2* const T2 = reinterpret_cast<const double2*>(ts + 2 * N);  // shared: {P', c}
+    const double*  const tR = ts + 4 * N;
+    const double*  const tPend = ts + 5 * N;
+    const double*  const tT    = tPend + NW;
+    const double*  const tRend = tT + NW;
+    const double*  const zl_ = ts;       // general: MzL
+    const double*  const zr_ = ts + N;   // general: MzR
+    const int       k0 = w * CL, k1 = k0 + CL;
+    const long long szl = Sl.sz;
+    int             stage = 0;
+    uint32_t        phase = 0;
+    int             set = 0;
+    for (int t = t0; t < ntiles; t = next_tile(t)) {
+        const int  bx = t % nbx, j = t / nbx;
+        const int  i0 = (A.pass + Sl.par + j) & 1;  // own cells of this row: i = 2 m + i0
+        const int  m  = bx * 32 + lane;
+        const bool act = 2 * m + i0 < Sl.nx;
+        const int  ii = 2 * (act ? m : 0) + i0;     // idle lanes shadow column 0 (their boxes are zero-filled) and never store
+        const double mxl = A.mx[ii], mxr = A.mx[Sl.nx + ii], myl = A.my[j], myr = A.my[Sl.ny + j];
+        double* const cz = sum + (size_t)set * NSUM * NW * 32;
+        double* const ca = cz + NW * 32;
+        double zl = 0.0, acc = 0.0;
+        // general: running products of the chunk and the factorisation carried in from the level below it
+        double P = 1.0, R = 1.0, T = 0.0, g = 0.0, h = 0.0;
+        if (GENERAL) {
+            h = mxl + mxr + myl + myr;
+            if (w > 0) g = A.gstart[(size_t)(w - 1) * Sl.nx * Sl.ny + (size_t)j * Sl.nx + ii];
+        }
+        // P1: right-hand sides, local forward sweep, the chunk's contribution to its first unknown
+        for (int sl = 0; sl < nslab; ++sl) {
+            const double* const bo = reinterpret_cast<const double*>(stages + (size_t)(stage * NW + w) * SB);
+            const double* const br = bo + OB / 8;
+            mbar_wait(full + stage * NW + w, phase);
+            double a[KZ][5];
+#pragma unroll
+            for (int u = 0; u < KZ; ++u) {
+                a[u][0] = bo[(u * 3 + 1) * OTHW + lane + i0];      // west
+                a[u][1] = bo[(u * 3 + 1) * OTHW + lane + i0 + 1];  // east
+                a[u][2] = bo[(u * 3 + 0) * OTHW + lane + 1];       // south
+                a[u][3] = bo[(u * 3 + 2) * OTHW + lane + 1];       // north
+                a[u][4] = br[u * 32 + lane];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empt + stage * NW + w);  // the box is in registers: hand the slot back
+            if (++stage == S) { stage = 0; phase ^= 1; }
+#pragma unroll
+            for (int u = 0; u < KZ; ++u) {
+                const int    k    = k0 + sl * KZ + u;
+                const double lphi = fma(myr, a[u][3], fma(myl, a[u][2], fma(mxr, a[u][1], mxl * a[u][0])));
+                const double b    = a[u][4] - lphi;
+                if (!GENERAL) {
+                    const double2 tt = T1[k];
+                    zl  = fma(tt.x, zl, tt.y * b);
+                    acc = fma(tR[k], zl, acc);
+                } else {
+                    // row k of the column system divided by beta J_k (sb_op.cpp: Op::buildLineTables, the same statements)
+                    const double ml = zl_[k], mr = zr_[k];
+                    double       diag = A.aob - h - ml - mr;
+                    if (k == 0) diag += -ml * A.sLo;
+                    if (k == N - 1) diag += -mr * A.sHi;
+                    double d = diag;
+                    if (k > 0) d = diag - (ml * g) * zr_[k - 1];
+                    g = 1.0 / d;
+                    const double aa = k > 0 ? -(ml * g) : 0.0;
+                    const double cc = k < N - 1 ? -(mr * g) : 0.0;
+                    zl  = fma(aa, zl, g * b);
+                    P   = P * aa;
+                    acc = fma(R, zl, acc);
+                    T   = fma(R, P, T);
+                    R   = R * cc;
+                    sg[k * 32 + lane] = g;
+                }
+                sy[k * 32 + lane] = zl;
+            }
+        }
+        cz[w * 32 + lane] = zl;
+        ca[w * 32 + lane] = acc;
+        if (GENERAL) {
+            cz[(2 * NW + w) * 32 + lane] = P;
+            cz[(3 * NW + w) * 32 + lane] = T;
+            cz[(4 * NW + w) * 32 + lane] = R;
+        }
+        consumer_bar(NW * 32);
+
+        // Carries.  Zs[v]: true z just below chunk v; X: true x just above this warp's chunk.
+        double Zs[NW];
+        double Z = 0.0, Zm = 0.0;
+#pragma unroll
+        for (int v = 0; v < NW; ++v) {
+            Zs[v] = Z;
+            if (v == w) Zm = Z;
+            const double pe = GENERAL ? cz[(2 * NW + v) * 32 + lane] : tPend[v];
+            Z = fma(pe, Z, cz[v * 32 + lane]);
+        }
+        double X = 0.0;
+#pragma unroll
+        for (int v = NW - 1; v >= 1; --v)
+            if (v > w) {
+                const double re = GENERAL ? cz[(4 * NW + v) * 32 + lane] : tRend[v];
+                const double tv = GENERAL ? cz[(3 * NW + v) * 32 + lane] : tT[v];
+                X = fma(re, X, fma(Zs[v], tv, ca[v * 32 + lane]));
+            }
+
+        // P2: true backward sweep of this chunk, straight to HBM.
+        const long long base = (long long)(SOX + (act ? m : 0)) + Sl.sy * (long long)(1 + j);
+        double* po = A.own + base + (long long)(k1 - 1) * szl;
+        double  xl = X;
+        if (GENERAL) {
+            // true forward values first: z_k = zl_k + P'_k Z (P'_k recomputed exactly as in P1)
+            double Pp = 1.0;
+            for (int k = k0; k < k1; ++k) {
+                const double aa = k > 0 ? -(zl_[k] * sg[k * 32 + lane]) : 0.0;
+                Pp = Pp * aa;
+                sy[k * 32 + lane] = fma(Pp, Zm, sy[k * 32 + lane]);
+            }
+#pragma unroll 4
+            for (int k = k1 - 1; k >= k0; --k) {
+                const double cc = k < N - 1 ? -(zr_[k] * sg[k * 32 + lane]) : 0.0;
+                xl = fma(cc, xl, sy[k * 32 + lane]);
+                if (act) *po = xl;
+                po -= szl;
+            }
+        } else {
+#pragma unroll 4
+            for (int k = k1 - 1; k >= k0; --k) {
+                const double2 tt = T2[k];
+                xl = fma(tt.y, xl, fma(tt.x, Zm, sy[k * 32 + lane]));
+                if (act) *po = xl;
+                po -= szl;
+            }
+        }
+        set ^= 1;
+    }
+}
+
+// g = 1 / d' of the column factorisation at the level below every chunk but the first (levels w CL - 1), one thread per
+// column; flag: dgtsv would have interchanged rows (|D'_k| < |DL_{k+1}| on the unscaled system) or met a zero pivot.
+__global__ void line_gstart_k(Lay L, const double* __restrict__ J, const double* __restrict__ mx, const double* __restrict__ my,
+                              const double* __restrict__ mz, double aob, double sLo, double sHi, int CL, double* __restrict__ gstart,
+                              int* __restrict__ flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= L.nx || j >= L.ny) return;
+    const int    N = L.nz;
+    const double h = mx[i] + mx[L.nx + i] + my[j] + my[L.ny + j];
+    double       g = 0.0, dprev = 0.0;
+    int          bad = 0;
+    for (int k = 0; k < N; ++k) {
+        const double ml = mz[k], mr = mz[N + k];
+        double       diag = aob - h - ml - mr;
+        if (k == 0) diag += -ml * sLo;
+        if (k == N - 1) diag += -mr * sHi;
+        double d = diag;
+        if (k > 0) {
+            const double jk = J[L.idx(i, j, k)], jp = J[L.idx(i, j, k - 1)];
+            if (!(fabs(jp * dprev) >= fabs(jk * ml)) || dprev == 0.0) bad = 1;
+            d = diag - (ml * g) * mz[N + k - 1];
+        }
+        if (d == 0.0) bad = 1;
+        g     = 1.0 / d;
+        dprev = d;
+        if ((k + 1) % CL == 0 && k + 1 < N) gstart[(size_t)((k + 1) / CL - 1) * L.nx * L.ny + (size_t)j * L.nx + i] = g;
+    }
+    if (bad) atomicOr(flag, 1);
+}
+void line_gstart(cudaStream_t st, const Lay& L, const double* J, const double* mx, const double* my, const double* mz, double aob,
+                 double sLo, double sHi, int CL, double* gstart, int* flag)
+{
+    const dim3 b(32, 4, 1);
+    line_gstart_k<<<dim3((L.nx + 31) / 32, (L.ny + 3) / 4), b, 0, st>>>(L, J, mx, my, mz, aob, sLo, sHi, CL, gstart, flag);
+    note_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side: tensor maps and launch.
+// ------------------------------------------------------------------------------------------
+namespace {
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                CUtensorMapFloatOOBfill);
+EncodeTiled encoder()
+{
+    static EncodeTiled fn = nullptr;
+    if (!fn) {
+        void*                           p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+            SB_FAIL("cuTensorMapEncodeTiled is not available from this driver");
+        fn = (EncodeTiled)p;
+    }
+    return fn;
+}
+constexpr int TNW = 8, TKZ = 4;
+size_t tma_smem(int nz, bool general, int S)
+{
+    const int    nsum = general ? 5 : 2;
+    const size_t ntab = general ? 2 * (size_t)nz : 5 * (size_t)nz + 3 * TNW;
+    return (size_t)S * TNW * (othBytes(TKZ) + rhsBytes(TKZ)) + ((size_t)nz * 32 * (general ? 2 : 1) + 2 * nsum * TNW * 32 + ((ntab + 1) & ~(size_t)1)) * 8 +
+           2 * (size_t)S * TNW * 8;
+}
+}  // namespace
+
+int  vertline_tma_nw() { return TNW; }
+bool vertline_tma_fits(int nz, bool general)
+{
+    if (nz % (TNW * TKZ) != 0) return false;
+    return tma_smem(nz, general, 2) <= 227 * 1024;
+}
+void vertline_tma_make_map(const SLay& S, const double* array, int boxw, int boxrows, LineTmaMap* out)
+{
+    static_assert(sizeof(LineTmaMap) >= sizeof(CUtensorMap), "LineTmaMap too small");
+    const cuuint64_t dims[3]    = {(cuuint64_t)S.px, (cuuint64_t)S.py, (cuuint64_t)(S.nz + 2 * S.zg)};
+    const cuuint64_t strides[2] = {(cuuint64_t)S.sy * 8, (cuuint64_t)S.sz * 8};
+    const cuuint32_t box[3]     = {(cuuint32_t)boxw, (cuuint32_t)boxrows, (cuuint32_t)TKZ};
+    const cuuint32_t estr[3]    = {1, 1, 1};
+    const CUresult   r = encoder()(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(array), dims,
+                                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) SB_FAIL("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+}
+void vertline_tma_make_maps(const SLay& S, const double* oth, const double* rhs, LineTmaMap* mapOth, LineTmaMap* mapRhs)
+{
+    vertline_tma_make_map(S, oth, OTHW, 3, mapOth);
+    vertline_tma_make_map(S, rhs, 32, 1, mapRhs);
+}
+
+void vertline_tma_pass(cudaStream_t st, const SLay& S, const LineTmaMap& mapOth, const LineTmaMap& mapRhs, const LineTmaArgs& args,
+                       bool general)
+{
+    static int nsm = 0;
+    if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+    LineTmaArgs A = args;
+    A.nbx    = ((S.nx + 1) / 2 + 31) / 32;
+    A.ntiles = A.nbx * S.ny;
+    const int grid = A.ntiles < nsm ? A.ntiles : nsm;
+    const CUtensorMap& mo = reinterpret_cast<const CUtensorMap&>(mapOth);
+    const CUtensorMap& mr = reinterpret_cast<const CUtensorMap&>(mapRhs);
+#define SB_TMA_LAUNCH(STG, GEN)                                                                                                  \
+    {                                                                                                                            \
+        const size_t  sh = tma_smem(S.nz, GEN, STG);                                                                             \
+        static size_t configured = 0;                                                                                            \
+        if (sh > configured) {                                                                                                   \
+            SB_CUDA(cudaFuncSetAttribute(vertline_tma_k<TNW, TKZ, STG, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); \
+            configured = sh;                                                                                                     \
+        }                                                                                                                        \
+        vertline_tma_k<TNW, TKZ, STG, GEN><<<grid, (TNW + 1) * 32, sh, st>>>(mo, mr, S, A);                                       \
+    }
+    // as deep a ring as the 227 KB of shared memory allow
+    if (!general) {
+        if (tma_smem(S.nz, false, 4) <= 227 * 1024) SB_TMA_LAUNCH(4, false)
+        else if (tma_smem(S.nz, false, 3) <= 227 * 1024) SB_TMA_LAUNCH(3, false)
+        else SB_TMA_LAUNCH(2, false)
+    } else {
+        if (tma_smem(S.nz, true, 3) <= 227 * 1024) SB_TMA_LAUNCH(3, true)
+        else SB_TMA_LAUNCH(2, true)
+    }
+#undef SB_TMA_LAUNCH
+    note_launch();
+}
+
+}  // namespace k
+}  // namespace sb

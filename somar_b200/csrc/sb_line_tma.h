@@ -1,0 +1,29 @@
+// sb_line_tma.h -- host interface of the TMA-staged line relaxation kernel (sb_line_tma.cu).
+#pragma once
+#include "sb_core.h"
+
+namespace sb {
+
+struct LineTmaMap { alignas(64) unsigned char bytes[128]; };  // a CUtensorMap (opaque here: cuda.h stays out of the host headers)
+
+struct LineTmaArgs {
+    const double* mx;      // [MxL | MxR] over the tile (nx each)
+    const double* my;      // [MyL | MyR] (ny each)
+    const double* tab;     // shared matrix: the tables of vertline_fused_k; general: [MzL | MzR] (nz each)
+    double*       own;     // colour being updated
+    const double* gstart;  // general: g = 1 / d' at the level below chunks 1 .. NW-1, [NW-1][ny][nx] (natural i)
+    double        aob, sLo, sHi;  // general: alpha / beta and the vertical BC factors (PoissonOpF.ChF:676-688)
+    int           pass, region, nbMask;
+    int           nbx, ntiles;    // filled by the launcher
+};
+
+namespace k {
+int  vertline_tma_nw();                      // chunks per column (consumer warps)
+bool vertline_tma_fits(int nz, bool general);
+void vertline_tma_make_maps(const SLay& S, const double* oth, const double* rhs, LineTmaMap* mapOth, LineTmaMap* mapRhs);
+void vertline_tma_pass(cudaStream_t st, const SLay& S, const LineTmaMap& mapOth, const LineTmaMap& mapRhs, const LineTmaArgs& args,
+                       bool general);
+void line_gstart(cudaStream_t st, const Lay& L, const double* J, const double* mx, const double* my, const double* mz, double aob,
+                 double sLo, double sHi, int CL, double* gstart, int* flag);
+}  // namespace k
+}  // namespace sb

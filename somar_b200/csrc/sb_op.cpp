@@ -191,6 +191,7 @@ Op::Op(Context* c, const sb_level_desc& d) : ctx(c)
     map.kind = d.map_kind; map.fn = d.map_fn; map.user = d.map_user;
     alpha = d.alpha; beta = d.beta; relaxMethod = d.relax_method;
     { const char* gk = getenv("SB_GSRB_KERNEL"); gsrbNatural = gk && std::string(gk) == "natural"; }  // test knob, read at creation
+    { const char* tk = getenv("SB_LINE_TMA"); lineTmaAllowed = !(tk && std::string(tk) == "0"); }     // "0": keep vertline_fused_k (tests)
     if (d.num_boxes <= 0) SB_FAIL("empty box list");
     boxes.resize(d.num_boxes); boxRank.resize(d.num_boxes);
     for (int b = 0; b < d.num_boxes; ++b) {
@@ -339,7 +340,7 @@ Op::~Op()
 {
     cudaFree(J); cudaFree(Dinv);
     for (int i = 0; i < 3; ++i) cudaFree(Jgup[i]);
-    cudaFree(lineTab); cudaFree(lineTabS);
+    cudaFree(lineTab); cudaFree(lineTabS); cudaFree(lineTabG); cudaFree(gstart);
     for (double* q : sp) cudaFree(q);
     for (double* q : sg) cudaFree(q);
     for (auto& kv : relaxGraphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -404,7 +405,7 @@ void Op::fillMetricFromMap()
 Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
 {
     dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth + 1; flatZ = f.flatZ;
-    gsrbNatural = f.gsrbNatural;
+    gsrbNatural = f.gsrbNatural; lineTmaAllowed = f.lineTmaAllowed;
     refined = f.refined;  // the coarse-fine sides stay (coarsened CFRegion, PoissonOp.cpp:392-396), with homogeneous ghosts only
     std::memcpy(amrCrseDXi, f.amrCrseDXi, sizeof(amrCrseDXi));  // not scaled (PoissonOp.cpp:345)
     std::memcpy(periodic, f.periodic, sizeof(periodic));
@@ -438,7 +439,7 @@ Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
 Op::Op(Context* single, const Op& f) : ctx(single)
 {
     dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth; flatZ = f.flatZ;
-    refined = f.refined; gsrbNatural = f.gsrbNatural;
+    refined = f.refined; gsrbNatural = f.gsrbNatural; lineTmaAllowed = f.lineTmaAllowed;
     std::memcpy(amrCrseDXi, f.amrCrseDXi, sizeof(amrCrseDXi));
     std::memcpy(periodic, f.periodic, sizeof(periodic));
     std::memcpy(bcAlpha, f.bcAlpha, sizeof(bcAlpha));
@@ -548,10 +549,14 @@ void Op::buildLineTables(double sLo, double sHi)
     relaxGraphs.clear();
     lineFast  = false;
     lineSplit = false;
-    const char* force = getenv("SB_LINE_KERNEL");  // "general" disables the fast path (tests)
+    lineTma = lineGeneral = false;
+    lineSLo = sLo; lineSHi = sHi;
+    const char* force = getenv("SB_LINE_KERNEL");  // "general" keeps vertline_k, "mapped" forces the per-column kernel (tests)
     if (force && std::string(force) == "general") return;
     const int N = lay.nz;
-    if (k::vertline_smem_bytes(N) > 200 * 1024 || beta == 0.0) return;
+    if (beta == 0.0) return;
+    if (force && std::string(force) == "mapped") { buildGeneralLine(sLo, sHi); return; }
+    if (k::vertline_smem_bytes(N) > 200 * 1024) { buildGeneralLine(sLo, sHi); return; }
     // h = MxL+MxR+MyL+MyR constant over the whole domain?
     double hmin = 1e300, hmax = -1e300;
     for (int d = 0; d < 2; ++d) {
@@ -562,7 +567,7 @@ void Op::buildLineTables(double sLo, double sHi)
             const double v = hM[d][i] + hM[d][Nd + i];
             lo = std::min(lo, v); hi = std::max(hi, v);
         }
-        if (hi - lo > 1e-13 * std::abs(hi)) return;
+        if (hi - lo > 1e-13 * std::abs(hi)) { buildGeneralLine(sLo, sHi); return; }
         (void)hmin; (void)hmax;
     }
     double h = hM[0][0] + hM[0][domain.size(0)];
@@ -579,7 +584,7 @@ void Op::buildLineTables(double sLo, double sHi)
     SB_CUDA(cudaMemcpyAsync(&dev, redOut, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
     ctx->sync();
     ctx->allreduceMax(&dev, 1);
-    if (!(dev <= 1e-13)) return;
+    if (!(dev <= 1e-13)) { buildGeneralLine(sLo, sHi); return; }
     if (ctx->nranks > 1) {  // every rank must use the same column of J: take rank 0's via max (values agree to 1e-13)
         ctx->allreduceMax(jcol.data(), std::min(N, 64));
         if (N > 64) for (int o = 64; o < N; o += 64) ctx->allreduceMax(jcol.data() + o, std::min(64, N - o));
@@ -659,6 +664,36 @@ void Op::buildLineTables(double sLo, double sHi)
     SB_CUDA(cudaMemcpy(lineTabS, u.data(), u.size() * sizeof(double), cudaMemcpyHostToDevice));
     slay      = makeSLay(lay);
     lineSplit = true;
+    // The TMA-staged persistent kernel takes over where there is enough work to keep every SM's ring busy; its
+    // arithmetic is vertline_fused_k's, operation for operation.
+    static int nsm = 0;
+    if (!nsm) { int dv = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dv); }
+    const long long ntiles = (long long)(((lay.nx + 1) / 2 + 31) / 32) * lay.ny;
+    lineTma = lineTmaAllowed && k::vertline_split_fused() && k::vertline_split_nw() == k::vertline_tma_nw() && k::vertline_tma_fits(N, false) &&
+              ntiles >= 2LL * nsm;
+}
+
+// Line relaxation for a horizontally varying metric (any map with x / y stretching): the columns no longer share one
+// matrix, so the Thomas factorisation is recomputed per column inside vertline_tma_k<GENERAL>; what is prepared here is
+// g = 1 / d' below every chunk (line_gstart_k), the vertical tables and the dgtsv-would-pivot check.
+void Op::buildGeneralLine(double sLo, double sHi)
+{
+    const int N = lay.nz;
+    if (!lineTmaAllowed || !k::vertline_tma_fits(N, true)) return;  // vertline_k stays (small or odd depths)
+    const int NWc = k::vertline_tma_nw(), CL = N / NWc;
+    if (!gstart) SB_CUDA(cudaMalloc((void**)&gstart, (size_t)(NWc - 1) * lay.nx * lay.ny * sizeof(double)));
+    SB_CUDA(cudaMemsetAsync(pivotFlag, 0, sizeof(int), ctx->st));
+    const Coef c = coef();
+    k::line_gstart(st(), lay, J, c.mxl, c.myl, c.mzl, alpha / beta, sLo, sHi, CL, gstart, pivotFlag);
+    double bad = (double)readPivotFlag(true);
+    ctx->allreduceMax(&bad, 1);
+    if (bad != 0.0) return;  // dgtsv would interchange rows somewhere: the general kernel reports that at run time
+    if (!lineTabG) SB_CUDA(cudaMalloc((void**)&lineTabG, 2 * (size_t)N * sizeof(double)));
+    SB_CUDA(cudaMemcpyAsync(lineTabG, c.mzl, 2 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->st));  // MzL | MzR are contiguous in mtab
+    slay        = makeSLay(lay);
+    lineSplit   = true;
+    lineGeneral = true;
+    lineTma     = true;
 }
 
 // PoissonOp::checkForNullSpace (PoissonOp.cpp:670-696): L[1] == 0 to smallReal?
@@ -775,15 +810,23 @@ void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUncha
             SB_CUDA(cudaMemsetAsync(q, 0, slay.n * sizeof(double), ctx->st));
         }
         splitResSrc = nullptr;
+        tmaMapsReady = false;
+    }
+    if (lineTma && !tmaMapsReady) {
+        for (int c2 = 0; c2 < 2; ++c2) k::vertline_tma_make_maps(slay, sp[c2], sp[2 + c2], &tmaOth[c2], &tmaRhs[c2]);
+        tmaMapsReady = true;
     }
     cudaEvent_t e0;
     ctx->profBegin("linesplit_convert", depth, &e0);
+    // the right-hand side is divided by beta J on the way: level by level (shared matrix: J = J(z)) or cell by cell
+    const double* scaleK = lineGeneral ? nullptr : lineTab;   // s_k = 1 / (beta J_k) = lineTab[0..nz)
+    const double* scaleJ = lineGeneral ? J : nullptr;
     if (pre == RELAX_PRE_PRECOND) {
-        k::split_precond(st(), lay, slay, res, Dinv, lineTab, sp[0], sp[1], sp[2], sp[3]);
+        k::split_precond(st(), lay, slay, res, Dinv, scaleK, sp[0], sp[1], sp[2], sp[3], scaleJ, beta);
         splitResSrc = res;
     } else {
         if (!(resUnchanged && splitResSrc == res)) {
-            k::split_field(st(), lay, slay, res, sp[2], sp[3], lineTab);  // rhs_k * s_k, s_k = 1 / (beta J_k) = lineTab[0..nz)
+            k::split_field(st(), lay, slay, res, sp[2], sp[3], scaleK, nullptr, scaleJ, beta);
             splitResSrc = res;
         }
         k::split_field(st(), lay, slay, cor, sp[0], sp[1], nullptr, pre == RELAX_PRE_SHIFT ? shiftBuf : nullptr);
@@ -810,14 +853,14 @@ void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUncha
             else SB_CUDA(cudaStreamWaitEvent(st(), ctx->evHalo, 0));
             ctx->profBegin("vertline", depth, &e0);
             if (nbMask && n < last) {
-                k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass, 1, nbMask);
+                linePass(pass, 1, nbMask);
                 SB_CUDA(cudaEventRecord(ctx->evEdge, st()));
                 SB_CUDA(cudaStreamWaitEvent(ctx->commSt, ctx->evEdge, 0));
                 ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1], ctx->commSt);
                 SB_CUDA(cudaEventRecord(ctx->evHalo, ctx->commSt));
-                k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass, 2, nbMask);
+                linePass(pass, 2, nbMask);
             } else {
-                k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass);
+                linePass(pass);
                 if (n < last) SB_CUDA(cudaEventRecord(ctx->evHalo, st()));
             }
             ctx->profEnd("vertline", depth, e0);
@@ -849,7 +892,7 @@ void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUncha
                 for (int pass = 0; pass < 2; ++pass) {
                     k::fill_ghosts_split(st(), slay, sp[0], sp[1], side, dim, pass == 0);
                     ctx->profBegin("vertline", depth, &e0);
-                    k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass);
+                    linePass(pass);
                     ctx->profEnd("vertline", depth, e0);
                 }
         }
@@ -901,12 +944,28 @@ void Op::relaxGsrbSplit(double* cor, const double* res, int iters, bool resUncha
     k::unsplit_field(st(), lay, slayG, cor, sg[0], sg[1]);
 }
 
+void Op::linePass(int pass, int region, int nbMask)
+{
+    if (lineTma) {
+        LineTmaArgs a;
+        const Coef  c = coef();
+        a.mx = c.mxl; a.my = c.myl;
+        a.tab = lineGeneral ? lineTabG : lineTabS;
+        a.own = sp[pass];
+        a.gstart = gstart;
+        a.aob = alpha / beta; a.sLo = lineSLo; a.sHi = lineSHi;
+        a.pass = pass; a.region = region; a.nbMask = nbMask; a.nbx = a.ntiles = 0;
+        k::vertline_tma_pass(st(), slay, tmaOth[1 - pass], tmaRhs[pass], a, lineGeneral);
+        return;
+    }
+    k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass, region, nbMask);
+}
 void Op::linePasses(int iters)
 {
     for (int it = 0; it < iters; ++it)
         for (int pass = 0; pass < 2; ++pass) {
             k::fill_ghosts_split(st(), slay, sp[0], sp[1], side, dim, pass == 0);
-            k::vertline_split_pass(st(), slay, coef(), lineTabS, sp[pass], sp[1 - pass], sp[2 + pass], pass);
+            linePass(pass);
         }
 }
 

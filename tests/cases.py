@@ -18,6 +18,9 @@ CASES = {
     "s_line64_zstretch": dict(nx=(64, 32, 64), L=(1.0, 0.5, 1.0), max_box=(32, 32, 0), bf=16, periodic=(0, 0, 0), relax=6, map="stretched", ampl=(0, 0, -0.1)),
     "s_line128": dict(nx=(128, 128, 128), L=(2.0, 2.0, 1.0), max_box=(64, 64, 0), bf=16, periodic=(0, 0, 0), relax=6, map="cartesian", ampl=(0, 0, 0)),
     "s_line256": dict(nx=(128, 128, 256), L=(2.0, 2.0, 1.0), max_box=(0, 0, 0), bf=16, periodic=(0, 0, 0), relax=6, map="cartesian", ampl=(0, 0, 0)),
+    # horizontally stretched maps at depths the mapped-grid line kernel (vertline_tma_k<GENERAL>) takes: nz a multiple of 32
+    "s_line64_xystretch": dict(nx=(64, 32, 64), L=(1.0, 0.5, 1.0), max_box=(32, 32, 0), bf=16, periodic=(0, 0, 0), relax=6, map="stretched", ampl=(0.05, 0.03, -0.1)),
+    "s_line256_xystretch": dict(nx=(64, 64, 256), L=(1.0, 1.0, 1.0), max_box=(32, 32, 0), bf=16, periodic=(0, 0, 0), relax=6, map="stretched", ampl=(0.05, 0.03, -0.1)),
     "onebox": dict(nx=(16, 16, 8), L=(1.0, 1.0, 1.0), max_box=(0, 0, 0), bf=4, periodic=(0, 0, 0), relax=6, map="cartesian", ampl=(0, 0, 0)),
 }
 

@@ -102,7 +102,7 @@ def test_solve(ctx, name, optset):
     op.free()
 
 
-@pytest.mark.parametrize("name", ["line_cart", "line_stretch", "line_aniso", "gsrb_stretch", "line_perx", "s_line64", "s_line128", "s_line256"])
+@pytest.mark.parametrize("name", ["line_cart", "line_stretch", "line_aniso", "gsrb_stretch", "line_perx", "s_line64", "s_line128", "s_line256", "s_line64_xystretch"])
 def test_project(ctx, name):
     c = CASES[name]
     op = make_op(ctx, c)

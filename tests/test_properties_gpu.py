@@ -205,3 +205,85 @@ def test_gsrb_split_storage_is_bitwise_the_natural_kernel(ctx, nx, periodic, box
         out[kind] = phi.download()
         op.free()
     assert np.array_equal(out["natural"], out["split"])
+
+
+@pytest.mark.parametrize("nx,periodic,box", [((512, 256, 64), (0, 0, 0), (128, 128, 0)), ((640, 128, 128), (1, 0, 0), (0, 0, 0)),
+                                              ((500, 200, 32), (0, 1, 0), (0, 0, 0))])
+def test_tma_line_kernel_is_bitwise_the_fused_kernel(ctx, nx, periodic, box, monkeypatch):
+    """vertline_tma_k (persistent, warp-specialised, operands by TMA) runs vertline_fused_k's arithmetic operation for
+    operation: identical bits, including a ragged last tile in x (TMA zero fill), periodic sides and several boxes."""
+    nxa = np.array(nx)
+    L = np.array([8.0, 4.0, 1.0])
+    dXi = L / nxa
+    lo = np.array([0, 0, -nx[2]])
+    hi = lo + nxa - 1
+    blo, bhi = (sb.make_base_grids(lo, hi, box, (1, 1, 0), 4) if any(box) else (lo[None, :], hi[None, :]))
+    rng = np.random.default_rng(21)
+    phi0, rhs0 = rng.standard_normal(nx), rng.standard_normal(nx)
+    out = {}
+    for tma in ("0", "1"):
+        monkeypatch.setenv("SB_LINE_TMA", tma)
+        xmin = lo * dXi
+        op = sb.PoissonOp(ctx, lo, hi, dXi, blo, bhi, periodic=periodic, relax_method=sb.RELAX_VERTLINE, map_kind=sb.MAP_STRETCHED,
+                          map_xmin=xmin, map_xmax=xmin + L, map_ampl=(0.0, 0.0, -0.1))
+        phi, rhs = op.field(data=phi0), op.field(data=rhs0)
+        op.relax(phi, rhs, 3)
+        out[tma] = phi.download()
+        op.free()
+    assert np.array_equal(out["0"], out["1"])
+
+
+@pytest.mark.parametrize("nx,periodic,ampl", [((128, 64, 64), (0, 0, 0), (0.05, 0.03, -0.1)), ((96, 40, 32), (1, 0, 0), (0.0, 0.04, 0.0)),
+                                               ((130, 34, 128), (0, 0, 0), (0.06, 0.0, -0.05)), ((64, 64, 256), (0, 1, 0), (0.05, 0.0, -0.1))])
+def test_mapped_grid_line_kernel_agrees_with_the_dgtsv_order_kernel(ctx, nx, periodic, ampl, monkeypatch):
+    """Horizontally stretched maps: vertline_tma_k<GENERAL> (per-column factorisation recomputed in the kernel, chunked
+    sweeps) against vertline_k (dgtsv's operation order, one thread per column) -- agreement to rounding."""
+    nxa = np.array(nx)
+    L = np.array([4.0, 2.0, 1.0])
+    dXi = L / nxa
+    lo = np.array([0, 0, -nx[2]])
+    hi = lo + nxa - 1
+    rng = np.random.default_rng(22)
+    phi0, rhs0 = rng.standard_normal(nx), rng.standard_normal(nx)
+    out = {}
+    for kind in ("general", "auto"):
+        if kind == "auto":
+            monkeypatch.delenv("SB_LINE_KERNEL", raising=False)
+        else:
+            monkeypatch.setenv("SB_LINE_KERNEL", kind)
+        xmin = lo * dXi
+        if periodic[0] or periodic[1]:
+            amp = tuple(0.0 if periodic[d] else ampl[d] for d in range(3))   # a periodic direction keeps its uniform map
+        else:
+            amp = ampl
+        op = sb.PoissonOp(ctx, lo, hi, dXi, lo[None, :], hi[None, :], periodic=periodic, relax_method=sb.RELAX_VERTLINE,
+                          map_kind=sb.MAP_STRETCHED, map_xmin=xmin, map_xmax=xmin + L, map_ampl=amp)
+        phi, rhs = op.field(data=phi0), op.field(data=rhs0)
+        op.relax(phi, rhs, 3)
+        out[kind] = phi.download()
+        op.free()
+    scale = np.max(np.abs(out["general"]))
+    assert np.max(np.abs(out["auto"] - out["general"])) <= 1e-12 * scale
+
+
+def test_mapped_kernel_on_a_uniform_grid_agrees_with_the_shared_matrix_kernel(ctx, monkeypatch):
+    """SB_LINE_KERNEL=mapped forces the per-column kernel where all columns do share one matrix: same mathematics."""
+    nx = (256, 128, 64)
+    nxa = np.array(nx)
+    L = np.array([4.0, 2.0, 1.0])
+    dXi = L / nxa
+    lo = np.array([0, 0, -nx[2]])
+    hi = lo + nxa - 1
+    rng = np.random.default_rng(23)
+    phi0, rhs0 = rng.standard_normal(nx), rng.standard_normal(nx)
+    out = {}
+    for kind in ("split", "mapped"):
+        monkeypatch.setenv("SB_LINE_KERNEL", kind)
+        xmin = lo * dXi
+        op = sb.PoissonOp(ctx, lo, hi, dXi, lo[None, :], hi[None, :], relax_method=sb.RELAX_VERTLINE, map_kind=sb.MAP_STRETCHED,
+                          map_xmin=xmin, map_xmax=xmin + L, map_ampl=(0.0, 0.0, -0.1))
+        phi, rhs = op.field(data=phi0), op.field(data=rhs0)
+        op.relax(phi, rhs, 4)
+        out[kind] = phi.download()
+        op.free()
+    assert np.max(np.abs(out["mapped"] - out["split"])) <= 1e-13 * np.max(np.abs(out["split"]))
