@@ -19,6 +19,7 @@ struct Context {
     cudaEvent_t  evEdge = nullptr, evHalo = nullptr;
     cudaStream_t copySt[2] = {nullptr, nullptr};  // SB_STREAM_H2D, SB_STREAM_D2H (asynchronous uploads / downloads)
     cudaStream_t stream(int which);               // SB_STREAM_*; the copy streams are created on first use
+    int*         fault  = nullptr;  // pinned, mapped: a kernel watchdog's last words (sb_line_tma.cu), readable after a failed launch
     double*      hpin   = nullptr;  // pinned host scratch (scalars coming back from reductions)
     size_t       hpinLen = 0;
     void*        scratch = nullptr;  // device scratch shared by all depths (line-relax workspace)
@@ -40,7 +41,7 @@ struct Context {
     explicit Context(Context& parent);  // single-rank view on the parent's device and stream
     ~Context();
     void* getScratch(size_t bytes);
-    void  sync() { SB_CUDA(cudaStreamSynchronize(st)); }
+    void  sync();
     // Comm::reduce (BaseTools/Comm.cpp:14-50)
     void allreduceSum(double* v, int n);
     void allreduceMax(double* v, int n);
@@ -151,7 +152,7 @@ struct Op {
     // TMA-staged persistent line kernel (sb_line_tma.cu).  lineTma: use it for the shared-matrix case on this depth (large
     // enough, aligned); lineGeneral: horizontally varying metric -- the per-column factorisation is recomputed in the kernel
     // (tables [MzL | MzR], gstart) and the right-hand side is scaled by 1 / (beta J) cell by cell.
-    bool    lineTma = false, lineGeneral = false, lineTmaAllowed = true, tmaMapsReady = false;
+    bool    lineTma = false, lineGeneral = false, lineTmaAllowed = true, lineTmaForce = false, tmaMapsReady = false;
     LineTmaMap tmaOth[2], tmaRhs[2];   // tensor maps of sp[0], sp[1] (as the other colour) and sp[2], sp[3] (right-hand sides)
     double* lineTabG = nullptr;         // general: [MzL | MzR]
     double* gstart = nullptr;           // general: [NW - 1][ny][nx]

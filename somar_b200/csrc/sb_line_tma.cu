@@ -8,7 +8,7 @@
 // reaches 0.68 of the copy bandwidth: its loads are held in registers (128 per thread, 2 CTAs per SM) and
 // stop while a CTA resolves its carries and streams its backward sweep out (profiles/r1_v4_summary.md).
 // Here one CTA per SM walks over tiles (32 columns of one colour in one grid row, all levels):
-//   * a producer thread issues 3-D tensor-map loads -- the other colour's rows j-1, j, j+1 (34 wide: west
+//   * a producer thread issues 3-D tensor-map loads -- the other colour's rows j-1, j, j+1 (36 wide: west
 //     and east neighbours come out of the same box) and this colour's right-hand side -- KZ levels per box,
 //     one ring of S stages per consumer warp, completion on mbarriers.  Bytes in flight cost shared memory,
 //     not registers, and the ring runs ahead across tile boundaries, so HBM requests never stop;
@@ -48,7 +48,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 }
 // Blocks until the phase with the given parity has completed.  A watchdog turns a protocol error (a load that never
 // lands) into a launch failure instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* fault = nullptr, int code = 0)
 {
     const uint32_t a = smem_u32(bar);
     uint32_t       done = 0;
@@ -60,21 +60,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
             : "=r"(done)
             : "r"(a), "r"(parity)
             : "memory");
-        if (spin > (1u << 22)) __trap();
+        if (spin > (1u << 22)) {
+            if (fault) {  // mapped host memory: readable after the launch has failed
+                fault[1] = code; fault[2] = (int)blockIdx.x; fault[3] = (int)threadIdx.x; fault[4] = (int)parity;
+                fault[0] = 1;
+                __threadfence_system();
+            }
+            __trap();
+        }
     }
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar)
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar)
 {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void consumer_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
-constexpr int OTHW = 34;  // box width of the other colour's rows: cells m0 - 1 .. m0 + 32
-__host__ __device__ constexpr int othBytes(int KZ) { return ((OTHW * 3 * KZ * 8 + 127) / 128) * 128; }
-__host__ __device__ constexpr int rhsBytes(int KZ) { return ((32 * KZ * 8 + 127) / 128) * 128; }
+constexpr int OTHW = 36;  // box width of the other colour's rows: cells m0 - 2 .. m0 + 33 (the innermost TMA coordinate must be
+                          // 16-byte aligned, i.e. even for doubles -- measured: an odd start is an illegal instruction)
+// One stage holds the boxes of ALL chunks: the tensor maps view z as (level in chunk, chunk), so a single 4-D box
+// [NW chunks][KZ levels][3 rows][36] (and [NW][KZ][1][32] of the right-hand side) serves the eight consumer warps at
+// once -- 16 bulk copies per tile instead of 128 (one issuing thread could not keep up with the small ones: measured).
+__host__ __device__ constexpr int othBytes(int KZ, int NW) { return ((OTHW * 3 * KZ * NW * 8 + 127) / 128) * 128; }
+__host__ __device__ constexpr int rhsBytes(int KZ, int NW) { return ((32 * KZ * NW * 8 + 127) / 128) * 128; }
 }  // namespace
 
 // tab (shared matrix): {a', g}[N] | {P', c}[N] | R[N] | Pend[NW] | T[NW] | Rend[NW]   (Op::buildLineTables)
@@ -86,17 +97,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     extern __shared__ __align__(128) unsigned char smraw[];
     const int N  = Sl.nz;
     const int CL = N / NW;
-    constexpr int OB = othBytes(KZ), RB = rhsBytes(KZ), SB = OB + RB;
-    unsigned char* const stages = smraw;                                   // [S][NW][SB]
-    double* const  sy  = reinterpret_cast<double*>(smraw + (size_t)S * NW * SB);  // [N][32]
+    constexpr int OB = othBytes(KZ, NW), RB = rhsBytes(KZ, NW), SB = OB + RB;
+    unsigned char* const stages = smraw;                                   // [S][SB]
+    double* const  sy  = reinterpret_cast<double*>(smraw + (size_t)S * SB);  // [N][32]
     double* const  sg  = sy + (size_t)N * 32;                              // [N][32] (GENERAL)
     double* const  sum = sg + (GENERAL ? (size_t)N * 32 : 0);              // [2 sets][NSUM][NW][32]
     constexpr int  NSUM = GENERAL ? 5 : 2;
     double* const  ts  = sum + 2 * NSUM * NW * 32;                         // tables
     const int      ntab = GENERAL ? 2 * N : 5 * N + 3 * NW;
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(ts + ((ntab + 1) & ~1));  // full[S][NW], empty[S][NW]
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(ts + ((ntab + 1) & ~1));  // full[S], empty[S]
     uint64_t* const full = bars;
-    uint64_t* const empt = bars + S * NW;
+    uint64_t* const empt = bars + S;
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nbx = A.nbx, ntiles = A.ntiles, nby = Sl.ny;
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 
     for (int k = threadIdx.x; k < ntab; k += (NW + 1) * 32) ts[k] = A.tab[k];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * S * NW; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < S; ++i) { mbar_init(full + i, 1); mbar_init(empt + i, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -126,16 +137,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             uint32_t phase = 0;
             for (int t = t0; t < ntiles; t = next_tile(t)) {
                 const int bx = t % nbx, j = t / nbx;
-                const int x0 = SOX + bx * 32 - 1;  // element of cell m0 - 1 in a row of a colour array
+                const int x0 = SOX + bx * 32 - 2;  // element of cell m0 - 2 in a row of a colour array (even)
                 for (int sl = 0; sl < nslab; ++sl) {
-                    for (int v = 0; v < NW; ++v) {
-                        uint64_t* fb = full + stage * NW + v;
-                        mbar_wait(empt + stage * NW + v, phase ^ 1);
-                        unsigned char* dst = stages + (size_t)(stage * NW + v) * SB;
-                        mbar_expect_tx(fb, OTHW * 3 * KZ * 8 + 32 * KZ * 8);
-                        tma_load_3d(dst, &mapOth, x0, j, v * CL + sl * KZ, fb);             // rows j-1 .. j+1 (array rows j .. j+2)
-                        tma_load_3d(dst + OB, &mapRhs, x0 + 1, j + 1, v * CL + sl * KZ, fb);  // row j
-                    }
+                    uint64_t* fb = full + stage;
+                    mbar_wait(empt + stage, phase ^ 1, A.fault, 1000 + stage);
+                    unsigned char* dst = stages + (size_t)stage * SB;
+                    mbar_expect_tx(fb, (OTHW * 3 + 32) * KZ * NW * 8);
+                    tma_load_4d(dst, &mapOth, x0, j, sl * KZ, 0, fb);               // rows j-1 .. j+1 (array rows j .. j+2), every chunk
+                    tma_load_4d(dst + OB, &mapRhs, x0 + 2, j + 1, sl * KZ, 0, fb);  // row j
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
@@ -175,20 +184,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
         }
         // P1: right-hand sides, local forward sweep, the chunk's contribution to its first unknown
         for (int sl = 0; sl < nslab; ++sl) {
-            const double* const bo = reinterpret_cast<const double*>(stages + (size_t)(stage * NW + w) * SB);
-            const double* const br = bo + OB / 8;
-            mbar_wait(full + stage * NW + w, phase);
+            const double* const bo = reinterpret_cast<const double*>(stages + (size_t)stage * SB) + (size_t)w * KZ * 3 * OTHW;
+            const double* const br = reinterpret_cast<const double*>(stages + (size_t)stage * SB + OB) + (size_t)w * KZ * 32;
+            mbar_wait(full + stage, phase, A.fault, 2000 + stage * 16 + w);
             double a[KZ][5];
 #pragma unroll
             for (int u = 0; u < KZ; ++u) {
-                a[u][0] = bo[(u * 3 + 1) * OTHW + lane + i0];      // west
-                a[u][1] = bo[(u * 3 + 1) * OTHW + lane + i0 + 1];  // east
-                a[u][2] = bo[(u * 3 + 0) * OTHW + lane + 1];       // south
-                a[u][3] = bo[(u * 3 + 2) * OTHW + lane + 1];       // north
+                a[u][0] = bo[(u * 3 + 1) * OTHW + lane + i0 + 1];  // west  (box element 0 is cell m0 - 2)
+                a[u][1] = bo[(u * 3 + 1) * OTHW + lane + i0 + 2];  // east
+                a[u][2] = bo[(u * 3 + 0) * OTHW + lane + 2];       // south
+                a[u][3] = bo[(u * 3 + 2) * OTHW + lane + 2];       // north
                 a[u][4] = br[u * 32 + lane];
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empt + stage * NW + w);  // the box is in registers: hand the slot back
+            if (lane == 0) mbar_arrive(empt + stage);  // this warp's part of the box is in registers: hand the slot back
             if (++stage == S) { stage = 0; phase ^= 1; }
 #pragma unroll
             for (int u = 0; u < KZ; ++u) {
@@ -343,8 +352,8 @@ size_t tma_smem(int nz, bool general, int S)
 {
     const int    nsum = general ? 5 : 2;
     const size_t ntab = general ? 2 * (size_t)nz : 5 * (size_t)nz + 3 * TNW;
-    return (size_t)S * TNW * (othBytes(TKZ) + rhsBytes(TKZ)) + ((size_t)nz * 32 * (general ? 2 : 1) + 2 * nsum * TNW * 32 + ((ntab + 1) & ~(size_t)1)) * 8 +
-           2 * (size_t)S * TNW * 8;
+    return (size_t)S * (othBytes(TKZ, TNW) + rhsBytes(TKZ, TNW)) + ((size_t)nz * 32 * (general ? 2 : 1) + 2 * nsum * TNW * 32 + ((ntab + 1) & ~(size_t)1)) * 8 +
+           2 * (size_t)S * 8;
 }
 }  // namespace
 
@@ -357,11 +366,14 @@ bool vertline_tma_fits(int nz, bool general)
 void vertline_tma_make_map(const SLay& S, const double* array, int boxw, int boxrows, LineTmaMap* out)
 {
     static_assert(sizeof(LineTmaMap) >= sizeof(CUtensorMap), "LineTmaMap too small");
-    const cuuint64_t dims[3]    = {(cuuint64_t)S.px, (cuuint64_t)S.py, (cuuint64_t)(S.nz + 2 * S.zg)};
-    const cuuint64_t strides[2] = {(cuuint64_t)S.sy * 8, (cuuint64_t)S.sz * 8};
-    const cuuint32_t box[3]     = {(cuuint32_t)boxw, (cuuint32_t)boxrows, (cuuint32_t)TKZ};
-    const cuuint32_t estr[3]    = {1, 1, 1};
-    const CUresult   r = encoder()(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(array), dims,
+    // z is viewed as (level inside a chunk, chunk): one box then spans every chunk's KZ levels
+    if (S.zg != 0 || S.nz % TNW != 0) SB_FAIL("vertline_tma: the colour arrays must have no z ghosts and nz a multiple of the chunk count");
+    const int        CL = S.nz / TNW;
+    const cuuint64_t dims[4]    = {(cuuint64_t)S.px, (cuuint64_t)S.py, (cuuint64_t)CL, (cuuint64_t)TNW};
+    const cuuint64_t strides[3] = {(cuuint64_t)S.sy * 8, (cuuint64_t)S.sz * 8, (cuuint64_t)S.sz * 8 * (cuuint64_t)CL};
+    const cuuint32_t box[4]     = {(cuuint32_t)boxw, (cuuint32_t)boxrows, (cuuint32_t)TKZ, (cuuint32_t)TNW};
+    const cuuint32_t estr[4]    = {1, 1, 1, 1};
+    const CUresult   r = encoder()(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(array), dims,
                                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) SB_FAIL("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");

@@ -15,6 +15,7 @@ struct LineTmaArgs {
     double        aob, sLo, sHi;  // general: alpha / beta and the vertical BC factors (PoissonOpF.ChF:676-688)
     int           pass, region, nbMask;
     int           nbx, ntiles;    // filled by the launcher
+    int*          fault;          // mapped host record written before a watchdog trap (may be null)
 };
 
 namespace k {

@@ -21,7 +21,19 @@ Context::Context(int dev, int rank_, int nranks_) : device(dev), rank(rank_), nr
     SB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     hpinLen = 1 << 16;
     SB_CUDA(cudaMallocHost((void**)&hpin, hpinLen * sizeof(double)));
+    SB_CUDA(cudaHostAlloc((void**)&fault, 16 * sizeof(int), cudaHostAllocMapped));
+    std::memset(fault, 0, 16 * sizeof(int));
     launches0 = k::launch_count();
+}
+void Context::sync()
+{
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) return;
+    const int* f = parent ? parent->fault : fault;
+    std::string why = std::string("cudaStreamSynchronize(st): ") + cudaGetErrorString(e);
+    if (f && f[0]) why += " [kernel watchdog: code " + std::to_string(f[1]) + ", block " + std::to_string(f[2]) + ", thread " + std::to_string(f[3]) +
+                          ", parity " + std::to_string(f[4]) + "]";
+    SB_FAIL(why);
 }
 Context::Context(Context& p) : device(p.device), rank(0), nranks(1), st(p.st), parent(&p)
 {
@@ -34,6 +46,7 @@ Context::~Context()
     delete comm;
     if (scratch) cudaFree(scratch);
     if (hpin) cudaFreeHost(hpin);
+    if (fault) cudaFreeHost(fault);
     if (evEdge) cudaEventDestroy(evEdge);
     if (evHalo) cudaEventDestroy(evHalo);
     if (commSt) cudaStreamDestroy(commSt);
@@ -191,7 +204,7 @@ Op::Op(Context* c, const sb_level_desc& d) : ctx(c)
     map.kind = d.map_kind; map.fn = d.map_fn; map.user = d.map_user;
     alpha = d.alpha; beta = d.beta; relaxMethod = d.relax_method;
     { const char* gk = getenv("SB_GSRB_KERNEL"); gsrbNatural = gk && std::string(gk) == "natural"; }  // test knob, read at creation
-    { const char* tk = getenv("SB_LINE_TMA"); lineTmaAllowed = !(tk && std::string(tk) == "0"); }     // "0": keep vertline_fused_k (tests)
+    { const char* tk = getenv("SB_LINE_TMA"); lineTmaAllowed = !(tk && std::string(tk) == "0"); lineTmaForce = tk && std::string(tk) == "force"; }  // "0": keep vertline_fused_k, "force": no size threshold (tests)
     if (d.num_boxes <= 0) SB_FAIL("empty box list");
     boxes.resize(d.num_boxes); boxRank.resize(d.num_boxes);
     for (int b = 0; b < d.num_boxes; ++b) {
@@ -405,7 +418,7 @@ void Op::fillMetricFromMap()
 Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
 {
     dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth + 1; flatZ = f.flatZ;
-    gsrbNatural = f.gsrbNatural; lineTmaAllowed = f.lineTmaAllowed;
+    gsrbNatural = f.gsrbNatural; lineTmaAllowed = f.lineTmaAllowed; lineTmaForce = f.lineTmaForce;
     refined = f.refined;  // the coarse-fine sides stay (coarsened CFRegion, PoissonOp.cpp:392-396), with homogeneous ghosts only
     std::memcpy(amrCrseDXi, f.amrCrseDXi, sizeof(amrCrseDXi));  // not scaled (PoissonOp.cpp:345)
     std::memcpy(periodic, f.periodic, sizeof(periodic));
@@ -439,7 +452,7 @@ Op::Op(const Op& f, const int ref[3]) : ctx(f.ctx)
 Op::Op(Context* single, const Op& f) : ctx(single)
 {
     dim = f.dim; alpha = f.alpha; beta = f.beta; relaxMethod = f.relaxMethod; map = f.map; depth = f.depth; flatZ = f.flatZ;
-    refined = f.refined; gsrbNatural = f.gsrbNatural; lineTmaAllowed = f.lineTmaAllowed;
+    refined = f.refined; gsrbNatural = f.gsrbNatural; lineTmaAllowed = f.lineTmaAllowed; lineTmaForce = f.lineTmaForce;
     std::memcpy(amrCrseDXi, f.amrCrseDXi, sizeof(amrCrseDXi));
     std::memcpy(periodic, f.periodic, sizeof(periodic));
     std::memcpy(bcAlpha, f.bcAlpha, sizeof(bcAlpha));
@@ -670,7 +683,7 @@ void Op::buildLineTables(double sLo, double sHi)
     if (!nsm) { int dv = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dv); }
     const long long ntiles = (long long)(((lay.nx + 1) / 2 + 31) / 32) * lay.ny;
     lineTma = lineTmaAllowed && k::vertline_split_fused() && k::vertline_split_nw() == k::vertline_tma_nw() && k::vertline_tma_fits(N, false) &&
-              ntiles >= 2LL * nsm;
+              (ntiles >= 2LL * nsm || lineTmaForce);
 }
 
 // Line relaxation for a horizontally varying metric (any map with x / y stretching): the columns no longer share one
@@ -955,6 +968,7 @@ void Op::linePass(int pass, int region, int nbMask)
         a.gstart = gstart;
         a.aob = alpha / beta; a.sLo = lineSLo; a.sHi = lineSHi;
         a.pass = pass; a.region = region; a.nbMask = nbMask; a.nbx = a.ntiles = 0;
+        a.fault = ctx->parent ? ctx->parent->fault : ctx->fault;
         k::vertline_tma_pass(st(), slay, tmaOth[1 - pass], tmaRhs[pass], a, lineGeneral);
         return;
     }
