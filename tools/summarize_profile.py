@@ -75,8 +75,24 @@ def rep_table(path):
     return "\n".join(out)
 
 
+def traffic_entry(path):
+    """dram bytes (read + write) and duration per captured launch of one ncu --set full report."""
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+    ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    num = lambda v: float(v.replace(",", ""))
+    tot = [num(d[ir]) * scale[units[ir]] + num(d[iw]) * scale[units[iw]] for d in data]
+    dur = [num(d[it]) * tscale[units[it]] for d in data]
+    return short(data[0][hdr.index("Kernel Name")]), {"dram_bytes_per_launch": sum(tot) / len(tot), "duration_us_under_ncu": sum(dur) / len(dur),
+                                                       "launches_captured": len(data), "report": path}
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--traffic", help="also write {kernel: dram bytes per launch} of the --rep reports to this json (bench.py reads it)")
     ap.add_argument("--launches")
     ap.add_argument("--last", type=int, default=0)
     ap.add_argument("--rep", nargs="*", default=[])
@@ -91,6 +107,12 @@ def main():
         parts += [launches_table(a.launches, a.last), ""]
     for r in a.rep:
         parts += [rep_table(r), ""]
+    if a.traffic:
+        import json
+        kernels = dict(traffic_entry(r) for r in a.rep)
+        with open(a.traffic, "w") as f:
+            json.dump({"source": a.out, "metric": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full --clock-control none)",
+                       "kernels": kernels}, f, indent=1)
     with open(a.out, "w") as f:
         f.write("\n".join(parts))
     print("\n".join(parts))
