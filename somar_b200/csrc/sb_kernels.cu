@@ -1029,6 +1029,7 @@ __global__ void reduce1_k(Lay L, BoxList bl, int op, const double* __restrict__ 
         else { const double s = w * dv; a = a + s * v; b = b + s; }  // IntegralF.ChF:37-58
     };
     const bool two = op >= 3;
+    const bool masked = mlo0 <= mhi0;
     for (long long r0 = ch + (long long)RCH * ty; r0 < rows; r0 += (long long)RCH * by * 4) {
         for (int i = tx; i < n0; i += bxw) {
             double v[4], w[4];
@@ -1041,7 +1042,7 @@ __global__ void reduce1_k(Lay L, BoxList bl, int op, const double* __restrict__ 
                     const long long q  = L.idx(lo0 + i, jj, kk);
                     v[u] = x[q];
                     if (two) w[u] = y[q];
-                    if (lo0 + i >= mlo0 && lo0 + i <= mhi0 && jj >= mlo1 && jj <= mhi1 && kk >= mlo2 && kk <= mhi2) v[u] = 0.0;
+                    if (masked && lo0 + i >= mlo0 && lo0 + i <= mhi0 && jj >= mlo1 && jj <= mhi1 && kk >= mlo2 && kk <= mhi2) v[u] = 0.0;
                 }
             }
 #pragma unroll

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                     if (k == N - 1) diag += -mr * A.sHi;
                     double d = diag;
                     if (k > 0) d = diag - (ml * g) * zr_[k - 1];
-                    g = 1.0 / d;
+                    g = __drcp_rn(d);  // correctly rounded, as 1.0 / d
                     const double aa = k > 0 ? -(ml * g) : 0.0;
                     const double cc = k < N - 1 ? -(mr * g) : 0.0;
                     zl  = fma(aa, zl, g * b);
