@@ -56,3 +56,21 @@ if ! link "" > "$OUT/link1.log"; then
   link "$OBJ/_fort_stubs.o" > "$OUT/link2.log" || { cat "$OUT/link2.log" | head -50; exit 1; }
 fi
 echo "built $OUT/somar_ref"
+
+# 6. the same driver with SOMAR's `using PoissonOp / LevelProjSolver` lines swapped for the B200 drop-ins of integration/
+#    (compiled against the reference's headers, linked to libsomar_b200.so): somar_ref_b200.  Needs the product library.
+ROOT="$(cd "$HERE/.." && pwd)"
+LIBDIR="$ROOT/somar_b200/lib"
+if [ -f "$LIBDIR/libsomar_b200.so" ]; then
+  SHIMINC="$INC -I$ROOT/include -I$ROOT/integration"
+  g++ $CXXFLAGS $SHIMINC -c "$ROOT/integration/B200PoissonOp.cpp" -o "$OBJ/_b200_poissonop.o"
+  g++ $CXXFLAGS $SHIMINC -c "$ROOT/integration/B200LevelHybridSolver.cpp" -o "$OBJ/_b200_hybrid.o"
+  g++ $CXXFLAGS $SHIMINC -DSB_SHIM -c "$HERE/ref_driver.cpp" -o "$OBJ/_ref_driver_b200.o"
+  STUBS=""; [ -f "$OBJ/_fort_stubs.o" ] && STUBS="$OBJ/_fort_stubs.o"
+  g++ -o "$OUT/somar_ref_b200" $OBJS "$OBJ/_fort_leaves.o" "$OBJ/_dgtsv.o" "$OBJ/_ref_driver_b200.o" "$OBJ/_b200_poissonop.o" \
+      "$OBJ/_b200_hybrid.o" $STUBS -L"$LIBDIR" -lsomar_b200 -Wl,-rpath,'$ORIGIN/../../../somar_b200/lib' -lpthread > "$OUT/link_b200.log" 2>&1 \
+      || { head -40 "$OUT/link_b200.log"; exit 1; }
+  echo "built $OUT/somar_ref_b200"
+else
+  echo "libsomar_b200.so not built yet: skipping somar_ref_b200"
+fi

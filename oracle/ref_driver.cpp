@@ -50,21 +50,33 @@
 using Elliptic::PoissonOp;
 typedef LevelData<FArrayBox> LDFAB;
 
+// -DSB_SHIM: the same driver with the two `using` lines of Grade5_SOMAR/AMRNSLevel.H:1448-1450 swapped -- the operator and the
+// level solver are the B200 drop-ins of integration/ (C++ API -> C ABI -> CUDA); everything else, including the
+// reference's own MGSolver when drv.useMGSolver=1, is the reference's code.  Built as somar_ref_b200.
+#ifdef SB_SHIM
+#include "B200LevelHybridSolver.H"
+typedef somar_b200::B200PoissonOp         BasePoissonOp;
+typedef somar_b200::B200LevelHybridSolver LevelSolverType;
+#else
+typedef Elliptic::PoissonOp         BasePoissonOp;
+typedef Elliptic::LevelHybridSolver LevelSolverType;
+#endif
+
 static std::vector<double> g_norms;  // every depth-0 norm() result, in call order
 static long g_relaxCalls = 0, g_relaxIters = 0, g_residualCalls = 0;
 
 // Depth-0 tap.  MGSolver::define clones its top operator with newMGOperator(Unit)
 // (MGSolverI.H:188), so the clone must be a TapOp too.
-class TapOp : public PoissonOp
+class TapOp : public BasePoissonOp
 {
 public:
-    using PoissonOp::PoissonOp;
-    TapOp(const PoissonOp& a_src) : PoissonOp(a_src) {}
+    using BasePoissonOp::BasePoissonOp;
+    TapOp(const TapOp& a_src) : BasePoissonOp(a_src) {}
 
     Real
     norm(const LDFAB& a_x, const int a_p, const Real a_powScale = 1.0) const override
     {
-        const Real v = PoissonOp::norm(a_x, a_p, a_powScale);
+        const Real v = BasePoissonOp::norm(a_x, a_p, a_powScale);
         g_norms.push_back(v);
         return v;
     }
@@ -74,14 +86,14 @@ public:
     {
         ++g_relaxCalls;
         g_relaxIters += a_iters;
-        PoissonOp::relax(a_cor, a_res, a_time, a_iters);
+        BasePoissonOp::relax(a_cor, a_res, a_time, a_iters);
     }
 
     Elliptic::MGOperator<LDFAB>*
     newMGOperator(const IntVect& a_refRatio) const override
     {
         if (a_refRatio == IntVect::Unit) return new TapOp(*this);
-        return PoissonOp::newMGOperator(a_refRatio);
+        return BasePoissonOp::newMGOperator(a_refRatio);
     }
 
     const LDFAB&   J() const { return m_J; }
@@ -673,7 +685,7 @@ main(int argc, char* argv[])
     // Solver.
     // LevelHybridSolver keeps its residual-norm history (initial, then one entry per leptic order /
     // V-cycle, LevelHybridSolver.cpp:312-400) in a protected member; expose it.
-    struct HybridPeek : Elliptic::LevelHybridSolver {
+    struct HybridPeek : LevelSolverType {
         const std::vector<Real>& resNorms() const { return m_resNorms; }
     } hybrid;
     Elliptic::MGSolver<LDFAB>            mg;
@@ -694,7 +706,9 @@ main(int argc, char* argv[])
         struct Peek : Elliptic::LevelHybridSolver { using Elliptic::LevelHybridSolver::computeSolveMode; };
         std::shared_ptr<const Elliptic::MGOperator<LDFAB>> mgOpPtr = opPtr;
         out.kv("solveMode", (int)Peek::computeSolveMode(mgOpPtr, hopt));  // 1 MG, 2 Leptic, 3 Leptic_MG
+#ifndef SB_SHIM
         out.kv("maxDepth", hybrid.getOptions().mgOptions.maxDepth);
+#endif
     }
 
     LDFAB rhs(grids, 1), phi(grids, 1, IntVect::Unit);
@@ -741,7 +755,7 @@ main(int argc, char* argv[])
             off += fcDom.numPts();
         }
         opPtr->levelDivergence(rhs, vel);
-        initDivNorm = opPtr->PoissonOp::norm(rhs, ctx->proj.normType);
+        initDivNorm = opPtr->BasePoissonOp::norm(rhs, ctx->proj.normType);
         out.put("div", gather(rhs, domBox));
         out.kv("initDivNorm", initDivNorm);
     } else if (mode == "solve") {
@@ -773,6 +787,10 @@ main(int argc, char* argv[])
     out.kv("status", status.getSolverStatus());
     out.kv("initResNorm", status.getInitResNorm());
     out.kv("finalResNorm", status.getFinalResNorm());
+#ifdef SB_SHIM
+    if (!useMGSolver) { out.kv("maxDepth", hybrid.maxDepth()); out.kv("deviceSolveMs", hybrid.deviceMilliseconds()); }
+    out.kv("impl", "b200-shim");
+#endif
     out.kv("relaxCallsDepth0", g_relaxCalls);
     out.kv("relaxItersDepth0", g_relaxIters);
 
@@ -792,7 +810,7 @@ main(int argc, char* argv[])
             out.put(std::string("grad") + char('0' + d), g);
         }
         opPtr->levelDivergence(rhs, vel);
-        out.kv("finalDivNorm", opPtr->PoissonOp::norm(rhs, ctx->proj.normType));
+        out.kv("finalDivNorm", opPtr->BasePoissonOp::norm(rhs, ctx->proj.normType));
         out.put("divAfter", gather(rhs, domBox));
     }
     return 0;

@@ -86,6 +86,12 @@ void Comm::allreduceHost(double* v, int n, bool isMax)
     ctx->sync();
 }
 
+void Comm::allreduceDevice(double* dev, int n, bool isMax, cudaStream_t st)
+{
+    if (!st) st = ctx->st;
+    SB_NCCL(api().AllReduce(dev, dev, n, kNcclFloat64, isMax ? kNcclMax : kNcclSum, comm, st));
+}
+
 // One ghost layer, faces only, all neighbour sides in one NCCL group.  Sends are issued lo then
 // hi and receives hi then lo, so that two ranks that are each other's neighbour on both sides
 // (2 ranks along a periodic direction) pair the messages correctly.

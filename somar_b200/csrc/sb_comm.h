@@ -15,6 +15,7 @@ struct Comm {
     ~Comm();
     static void getUniqueId(void* id128);
     void allreduceHost(double* v, int n, bool isMax);
+    void allreduceDevice(double* dev, int n, bool isMax, cudaStream_t st = nullptr);  // in place, stream-ordered, no host sync
     void exchangeFaces(Op& op, double* phi);
     void exchangeDir(Op& op, double* phi, int dir, int ext0, int ext1);
     void exchangeFacesSplit(Op& op, double* s0, double* s1, cudaStream_t st = nullptr, const SLay* S = nullptr);  // same, on colour-split storage (x and y sides); st: default ctx->st; S: default op.slay

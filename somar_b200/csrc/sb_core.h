@@ -269,6 +269,7 @@ void add_vertical_extrusion(cudaStream_t st, const Lay& L, const Lay& F, double*
 void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, const double* x, const double* y,
                   double dv, double* partial, double* out, const Box3* mask = nullptr);
 int  reduce_partial_len(int nboxes);
+void sum_boxes(cudaStream_t st, const double* in, int nboxes, int ncomp, double* out);
 }  // namespace k
 
 }  // namespace sb

@@ -1073,6 +1073,21 @@ __global__ void reduce2_k(int op, const double* __restrict__ partial, double* __
         else out[bx] = a;
     }
 }
+// out[c] = sum over boxes of in[ncomp * b + c], boxes in ascending order (the order of the reference's loop over the
+// DataIterator, Integral.cpp:249-266): one thread, a handful of adds -- what used to be a round trip to the host.
+__global__ void sum_boxes_k(const double* __restrict__ in, int nboxes, int ncomp, double* __restrict__ out)
+{
+    const int c = threadIdx.x;
+    if (c >= ncomp) return;
+    double s = 0.0;
+    for (int b = 0; b < nboxes; ++b) s += in[ncomp * b + c];
+    out[c] = s;
+}
+void sum_boxes(cudaStream_t st, const double* in, int nboxes, int ncomp, double* out)
+{
+    sum_boxes_k<<<1, 32, 0, st>>>(in, nboxes, ncomp, out);
+    LAUNCHED();
+}
 int  reduce_partial_len(int nboxes) { return 2 * RCH * nboxes; }
 void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, const double* x, const double* y, double dv,
                   double* partial, double* out, const Box3* mask)

@@ -859,25 +859,49 @@ void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUncha
             for (int s = 0; s < 2; ++s)
                 if (side[d][s].kind == SIDE_NEIGHBOR) nbMask |= 1 << (2 * d + s);
         const int last = 2 * iters - 1;
-        for (int n = 0; n <= last; ++n) {
-            const int pass = n & 1;
-            k::fill_ghosts_split(st(), slay, sp[0], sp[1], side, dim, pass == 0);
-            if (n == 0) ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1]);
-            else SB_CUDA(cudaStreamWaitEvent(st(), ctx->evHalo, 0));
-            ctx->profBegin("vertline", depth, &e0);
-            if (nbMask && n < last) {
-                linePass(pass, 1, nbMask);
-                SB_CUDA(cudaEventRecord(ctx->evEdge, st()));
-                SB_CUDA(cudaStreamWaitEvent(ctx->commSt, ctx->evEdge, 0));
-                ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1], ctx->commSt);
-                SB_CUDA(cudaEventRecord(ctx->evHalo, ctx->commSt));
-                linePass(pass, 2, nbMask);
-            } else {
-                linePass(pass);
-                if (n < last) SB_CUDA(cudaEventRecord(ctx->evHalo, st()));
+        auto passes = [&](bool prof) {
+            for (int n = 0; n <= last; ++n) {
+                const int pass = n & 1;
+                k::fill_ghosts_split(st(), slay, sp[0], sp[1], side, dim, pass == 0);
+                if (n == 0) ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1]);
+                else SB_CUDA(cudaStreamWaitEvent(st(), ctx->evHalo, 0));
+                if (prof) ctx->profBegin("vertline", depth, &e0);
+                if (nbMask && n < last) {
+                    linePass(pass, 1, nbMask);
+                    SB_CUDA(cudaEventRecord(ctx->evEdge, st()));
+                    SB_CUDA(cudaStreamWaitEvent(ctx->commSt, ctx->evEdge, 0));
+                    ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1], ctx->commSt);
+                    SB_CUDA(cudaEventRecord(ctx->evHalo, ctx->commSt));
+                    linePass(pass, 2, nbMask);
+                } else {
+                    linePass(pass);
+                    if (n < last) SB_CUDA(cudaEventRecord(ctx->evHalo, st()));
+                }
+                if (prof) ctx->profEnd("vertline", depth, e0);
             }
-            ctx->profEnd("vertline", depth, e0);
-        }
+        };
+        // The whole pass loop -- kernels on two streams, the NCCL face exchanges between them -- is captured once per
+        // iteration count and replayed: at N > 1 every depth is launch-bound otherwise (five launches, a grouped
+        // send/recv and two events per colour pass).  SB_MR_GRAPH=0 keeps the plain launches.
+        static const bool mrGraph = [] { const char* e = getenv("SB_MR_GRAPH"); return !(e && std::string(e) == "0"); }();
+        if (mrGraph && !ctx->isProfiling()) {
+            RelaxGraph& g = relaxGraphs[iters];
+            if (!g.exec && ++relaxCallsSeen >= 2) {
+                cudaGraph_t     graph = nullptr;
+                const long long l0    = k::launch_count();
+                SB_CUDA(cudaStreamBeginCapture(st(), cudaStreamCaptureModeThreadLocal));
+                passes(false);
+                SB_CUDA(cudaStreamEndCapture(st(), &graph));
+                g.kernels = k::launch_count() - l0;
+                k::note_launches(-g.kernels);  // captured, not launched
+                SB_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+                SB_CUDA(cudaGraphDestroy(graph));
+            }
+            if (g.exec) {
+                SB_CUDA(cudaGraphLaunch(g.exec, st()));
+                k::note_launches(g.kernels);
+            } else passes(false);
+        } else passes(ctx->isProfiling());
     } else {
         // Small depths: replay the pass loop as a CUDA graph (captured on the second call with this
         // iteration count, once every kernel has been configured by a plain run).
@@ -1061,18 +1085,11 @@ bool Op::removeKernel(double* phi, bool defer)
     if (!hasNullSpace) return false;
     const double dv = dXi[0] * dXi[1] * dXi[2];
     k::reduce_boxes(st(), lay, boxlist(), 4, phi, J, dim == 2 ? dXi[0] * dXi[2] : dv, redPartial, redOut);
-    const int nl = nlocal();
-    if (ctx->nranks == 1 && nl == 1) {
-        SB_CUDA(cudaMemcpyAsync(shiftBuf, redOut, 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->st));
-    } else {
-        SB_CUDA(cudaMemcpyAsync(ctx->hpin, redOut, 2 * nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
-        ctx->sync();
-        double sv[2] = {0.0, 0.0};
-        for (int b = 0; b < nl; ++b) { sv[0] += ctx->hpin[2 * b]; sv[1] += ctx->hpin[2 * b + 1]; }
-        ctx->allreduceSum(sv, 2);
-        ctx->hpin[0] = sv[0]; ctx->hpin[1] = sv[1];
-        SB_CUDA(cudaMemcpyAsync(shiftBuf, ctx->hpin, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
-        SB_CUDA(cudaStreamSynchronize(ctx->st));  // hpin is reused by the next reduction
+    // (sum, vol) over the boxes of this rank, then over the ranks: all on the stream, the host is not involved
+    k::sum_boxes(st(), redOut, nlocal(), 2, shiftBuf);
+    if (ctx->nranks > 1) {
+        if (!ctx->comm) SB_FAIL("nranks > 1 but sb_comm_init was not called");
+        ctx->comm->allreduceDevice(shiftBuf, 2, false, st());
     }
     if (defer) return true;
     k::add_scalar_valid(st(), lay, phi, shiftBuf);

@@ -11,12 +11,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DECK = os.path.join(ROOT, "oracle", "decks", "base3d.inputs")
 
 
-def ref_binary(dim=3):
-    return os.path.join(ROOT, "oracle", "_ref", f"d{dim}", "somar_ref")
+def ref_binary(dim=3, shim=False):
+    """shim: the same driver built with SOMAR's `using PoissonOp / LevelProjSolver` lines swapped for the B200 drop-ins of
+    integration/ (somar_ref_b200: reference C++ API -> C ABI -> CUDA)."""
+    return os.path.join(ROOT, "oracle", "_ref", f"d{dim}", "somar_ref_b200" if shim else "somar_ref")
 
 
-def have_ref(dim=3):
-    return os.path.exists(ref_binary(dim))
+def have_ref(dim=3, shim=False):
+    return os.path.exists(ref_binary(dim, shim))
 
 
 class RefResult:
@@ -46,7 +48,7 @@ class RefResult:
 
 
 def run_ref(mode, nx, L, inp=None, max_box=(0, 0, 0), block_factor=None, offset=None, periodic=(0, 0, 0), relax=6,
-            mapname="cartesian", ampl=(0, 0, 0), extra=None, timeout=600, dim=3, split_dirs=None):
+            mapname="cartesian", ampl=(0, 0, 0), extra=None, timeout=600, dim=3, split_dirs=None, shim=False):
     """Run the reference driver.  nx, L, offset: 3-vectors (2-D: dim=2 and 2-vectors)."""
     nx = list(nx)
     D = len(nx)
@@ -63,7 +65,7 @@ def run_ref(mode, nx, L, inp=None, max_box=(0, 0, 0), block_factor=None, offset=
     split = list(split_dirs) if split_dirs is not None else [1] * (D - 1) + [0]
     vec = lambda v: " ".join(str(x) for x in v)
     with tempfile.TemporaryDirectory() as td:
-        args = [ref_binary(dim), DECK,
+        args = [ref_binary(dim, shim), DECK,
                 f"base.nx={vec(nx)}", f"base.L={vec(L)}", f"base.nxOffset={vec(offset)}",
                 f"base.isPeriodic={vec(list(periodic)[:D])}", f"base.splitDirs={vec(split)}",
                 f"base.maxBaseGridSize={vec(list(max_box)[:D])}", f"base.blockFactor={block_factor}",
