@@ -67,7 +67,10 @@ Elliptic::SolverStatus B200LevelHybridSolver::solve(StateType& a_phi, const Stat
     m_solverStatus.setSolverStatus(st.status);
     m_solverStatus.setInitResNorm(st.init_res_norm);
     m_solverStatus.setFinalResNorm(st.final_res_norm);
-    m_resNorms.assign(st.res_norms, st.res_norms + st.num_norms);
+    // m_resNorms of the reference: in MG mode the initial and the final norm (LevelHybridSolver.cpp:392-400), in the leptic
+    // modes one entry per leptic order / V-cycle
+    if (st.solve_mode == SB_MODE_MG) m_resNorms = {st.init_res_norm, st.final_res_norm};
+    else m_resNorms.assign(st.res_norms, st.res_norms + st.num_norms);
     m_mode = st.solve_mode; m_maxDepth = st.max_depth; m_ms = st.device_ms;
     return m_solverStatus;
 }

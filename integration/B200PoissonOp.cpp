@@ -177,11 +177,16 @@ sb_field* B200PoissonOp::flux(const int a_set, const int a_dir) const
 }
 void B200PoissonOp::upload(sb_field* a_dst, const StateType& a_src) const
 {
+    // Valid cells only.  On the device the boxes of a rank are fused into one array, where the ghost cells of an
+    // interior box side ARE the neighbouring box's valid cells: a box's (stale) host ghosts must not land there.
+    // Every ghost the operator reads is refilled on the device by applyBCs.
+    const DisjointBoxLayout& grids = a_src.getBoxes();
     for (DataIterator dit = a_src.dataIterator(); dit.ok(); ++dit) {
-        const FArrayBox& fab = a_src[dit];
+        FArrayBox tmp(grids[dit], 1);
+        tmp.copy(a_src[dit], grids[dit], 0, grids[dit], 0, 1);
         int l[3], h[3];
-        to3(l, fab.box().smallEnd(), 0); to3(h, fab.box().bigEnd(), 0);
-        check(sb_field_upload(a_dst, fab.dataPtr(0), l, h), "sb_field_upload");
+        to3(l, tmp.box().smallEnd(), 0); to3(h, tmp.box().bigEnd(), 0);
+        check(sb_field_upload(a_dst, tmp.dataPtr(0), l, h), "sb_field_upload");
     }
 }
 void B200PoissonOp::download(StateType& a_dst, sb_field* a_src) const
