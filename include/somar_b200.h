@@ -282,6 +282,22 @@ int sb_solver_vcycle(sb_solver* s, sb_field* cor, sb_field* res);
  * with the preconditioning pass fused into the first relaxation. */
 int sb_solver_precond_vcycle(sb_solver* s, sb_field* cor, sb_field* res);
 
+/* ---- the projection bracket on device-resident fields (any number of ranks) ------------------ */
+/* AMRNSLevel::projectCorrect (AMRNSLevelProject.cpp:247-373) between the level's own BC fills: [vel -> advecting],
+ * div = levelDivergence(vel), solve L[phi] = div (homogeneous BCs, phi from zero), vel -= levelGradient(phi),
+ * p += phi / proj_dt (p may be NULL; skipped for proj_dt = 0), diagnostic divergence, [vel -> Cartesian].
+ * vel_ghost >= 0: vel is the Cartesian face velocity of a FluxBox with that ghost width and is transformed on the way
+ * in and out as the reference does (sb_op_send_to_*_velocity); vel_ghost < 0: vel is the advecting velocity already.
+ * phi_out (may be NULL) receives the correction.  Nothing leaves the device but the two norms and the status. */
+int sb_project_correct(sb_solver* s, sb_field* const vel[3], sb_field* p, double proj_dt, int vel_ghost, sb_field* phi_out,
+                       double* init_div_norm, double* final_div_norm, sb_solver_status* status);
+/* AMRNSLevel::projectPredict (AMRNSLevelProject.cpp:63-243): vel -= proj_dt * levelGradient(p, ..., false, false) with the
+ * lagged pressure; if that raised |Div[vel]|, one quick-and-dirty projectCorrect (LevelHybridSolver::
+ * getQuickAndDirtyOptions switched on around it, :176-182).  norms = {initial, lagged, corrected (-1 without the
+ * fallback)}; status describes the fallback's solve (UNDEFINED if there was none). */
+int sb_project_predict(sb_solver* s, sb_field* const vel[3], sb_field* p, double proj_dt, int vel_ghost, double norms[3], int* used_fallback,
+                       sb_solver_status* status);
+
 /* ---- the projection bracket, host buffers in and out --------------------------------------- */
 /* AMRNSLevel::projectCorrect, single level (AMRNSLevelProject.cpp:247-373): vel is the advecting
  * (J-scaled) face velocity, D host arrays over the face-centred *domain* box in global Fortran

@@ -744,6 +744,69 @@ main(int argc, char* argv[])
         return 0;
     }
 
+    if (mode == "predict") {
+        // AMRNSLevel::projectPredict (Grade5_SOMAR/AMRNSLevelProject.cpp:63-243) between the level's own BC fills, restated
+        // around the reference's operator and solver calls (Grade5 is not part of this build): lagged-pressure correction,
+        // and, if it raised |Div[vel]|, one projectCorrect (:247-373) under LevelHybridSolver's quick-and-dirty options.
+        //   drv.in: the D face fields of the advecting velocity, then p over the domain box;  drv.projDt
+        if (useMGSolver) MayDay::Error("drv.mode=predict uses the LevelHybridSolver");
+        Real projDt = 0.5;
+        drv.query("projDt", projDt);
+        vel.define(grids, 1);
+        gradPhi.define(grids, 1);
+        LDFAB  p(grids, 1, IntVect::Unit), divVel(grids, 1);
+        size_t off = 0;
+        for (int d = 0; d < SpaceDim; ++d) {
+            const Box fcDom = surroundingNodes(domBox, d);
+            for (DataIterator dit(grids); dit.ok(); ++dit) scatterFAB(vel[dit][d], grids[dit], in.data() + off, fcDom);
+            off += fcDom.numPts();
+        }
+        for (DataIterator dit(grids); dit.ok(); ++dit) p[dit].setVal(0.0);
+        scatter(p, in.data() + off, domBox);
+        const int normType = ctx->proj.normType;
+        opPtr->levelDivergence(divVel, vel);
+        const Real n0 = opPtr->BasePoissonOp::norm(divVel, normType);
+        opPtr->levelGradient(gradPhi, p, nullptr, 0.0, false, false);
+        for (DataIterator dit(grids); dit.ok(); ++dit)
+            for (int d = 0; d < SpaceDim; ++d) vel[dit][d].plus(gradPhi[dit][d], -projDt);
+        opPtr->levelDivergence(divVel, vel);
+        const Real n1 = opPtr->BasePoissonOp::norm(divVel, normType);
+        Real       n2 = -1.0;
+        int        fallback = 0, fbStatus = -1;
+        if (n1 > n0) {
+            fallback = 1;
+            const auto saveOpts = hybrid.getOptions();
+            hybrid.modifyOptionsExceptMaxDepth(LevelSolverType::getQuickAndDirtyOptions());
+            {   // projectCorrect
+                LDFAB phiC(grids, 1, IntVect::Unit);
+                opPtr->levelDivergence(divVel, vel);
+                Elliptic::SolverStatus st = hybrid.solve(phiC, nullptr, divVel, 0.0, true, true);
+                fbStatus = st.getSolverStatus();
+                opPtr->levelGradient(gradPhi, phiC, nullptr, 0.0, true, true);
+                for (DataIterator dit(grids); dit.ok(); ++dit) {
+                    for (int d = 0; d < SpaceDim; ++d) vel[dit][d].plus(gradPhi[dit][d], -1.0);
+                    p[dit].plus(phiC[dit], 1.0 / projDt);
+                }
+            }
+            hybrid.modifyOptionsExceptMaxDepth(saveOpts);
+            opPtr->levelDivergence(divVel, vel);
+            n2 = opPtr->BasePoissonOp::norm(divVel, normType);
+        }
+        for (int d = 0; d < SpaceDim; ++d) {
+            const Box           fcDom = surroundingNodes(domBox, d);
+            std::vector<double> v(fcDom.numPts(), 0.0);
+            for (DataIterator dit(grids); dit.ok(); ++dit) gatherFAB(v, vel[dit][d], grids[dit], fcDom);
+            out.put(std::string("vel") + char('0' + d), v);
+        }
+        out.put("p", gather(p, domBox));
+        out.kv("initDivNorm", n0);
+        out.kv("laggedDivNorm", n1);
+        out.kv("correctedDivNorm", n2);
+        out.kv("usedFallback", fallback);
+        out.kv("status", fbStatus);
+        return 0;
+    }
+
     if (mode == "project") {
         vel.define(grids, 1);
         gradPhi.define(grids, 1);

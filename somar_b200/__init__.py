@@ -530,6 +530,19 @@ class _SolverBase:
     def set_options(self, opt):
         capi.check(self.lib.sb_solver_set_options(self.h, C.byref(opt)))
 
+    def project_correct(self, vel, p=None, proj_dt=1.0, vel_ghost=-1, phi_out=None):
+        """AMRNSLevel::projectCorrect on device-resident fields: returns (initDivNorm, finalDivNorm, status)."""
+        n0, n1, st = C.c_double(), C.c_double(), SolverStatus()
+        capi.check(self.lib.sb_project_correct(self.h, PoissonOp._f3(vel), p.h if p else None, proj_dt, vel_ghost,
+                                               phi_out.h if phi_out else None, C.byref(n0), C.byref(n1), C.byref(st)))
+        return n0.value, n1.value, st
+
+    def project_predict(self, vel, p, proj_dt=1.0, vel_ghost=-1):
+        """AMRNSLevel::projectPredict on device-resident fields: returns ((initial, lagged, corrected) norms, used_fallback, status)."""
+        norms, fb, st = (C.c_double * 3)(), C.c_int(), SolverStatus()
+        capi.check(self.lib.sb_project_predict(self.h, PoissonOp._f3(vel), p.h, proj_dt, vel_ghost, norms, C.byref(fb), C.byref(st)))
+        return tuple(norms), bool(fb.value), st
+
     def project_host(self, vel, proj_dt=1.0, p=None):
         """AMRNSLevel::projectCorrect with host arrays: returns (vel_out, phi, initDivNorm, finalDivNorm, status)."""
         op = self.op

@@ -171,6 +171,8 @@ PROTOTYPES = {
     "sb_context_stream_sync": (C.c_int, [P, C.c_int]),
     "sb_field_upload_async": (C.c_int, [P, DP, IP, IP]),
     "sb_field_download_async": (C.c_int, [P, DP, IP, IP]),
+    "sb_project_correct": (C.c_int, [P, F3, P, C.c_double, C.c_int, P, DP, DP, C.POINTER(SolverStatus)]),
+    "sb_project_predict": (C.c_int, [P, F3, P, C.c_double, C.c_int, DP, IP, C.POINTER(SolverStatus)]),
     "sb_project_host": (C.c_int, [P, DP * 3, DP, DP, C.c_double, DP, DP, C.POINTER(SolverStatus)]),
 }
 

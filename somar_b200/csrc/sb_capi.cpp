@@ -716,6 +716,45 @@ int sb_solver_precond_vcycle(sb_solver* s, sb_field* cor, sb_field* res)
     SB_END
 }
 
+// The projection bracket on device-resident fields, any number of ranks (every call inside is collective).
+int sb_project_correct(sb_solver* s, sb_field* const vel[3], sb_field* p, double proj_dt, int vel_ghost, sb_field* phi_out,
+                       double* init_div_norm, double* final_div_norm, sb_solver_status* status)
+{
+    SB_TRY DEVG(s) REQ(s); REQ(vel);
+    Op& o = *s->s.op;
+    if (!s->s.isHybrid && s->s.mg.ops.empty()) SB_FAIL("solver not defined");
+    sb_op tmp{&o, false};
+    double* v[3]; fluxPtrs(&tmp, vel, v);
+    if (p && p->f.op != &o) SB_FAIL("p does not live on the solver's operator");
+    if (phi_out && phi_out->f.op != &o) SB_FAIL("phi_out does not live on the solver's operator");
+    cudaEvent_t e0, e1;
+    SB_CUDA(cudaEventCreate(&e0)); SB_CUDA(cudaEventCreate(&e1));
+    SB_CUDA(cudaEventRecord(e0, o.st()));
+    SolverStatus st = s->s.projectCorrect(v, p ? D(p) : nullptr, proj_dt, vel_ghost, phi_out ? D(phi_out) : nullptr, init_div_norm, final_div_norm);
+    SB_CUDA(cudaEventRecord(e1, o.st()));
+    o.ctx->sync();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    fillStatus(s, st, status, ms);
+    SB_END
+}
+int sb_project_predict(sb_solver* s, sb_field* const vel[3], sb_field* p, double proj_dt, int vel_ghost, double norms[3], int* used_fallback,
+                       sb_solver_status* status)
+{
+    SB_TRY DEVG(s) REQ(s); REQ(vel); REQ(p); REQ(norms);
+    Op& o = *s->s.op;
+    sb_op tmp{&o, false};
+    double* v[3]; fluxPtrs(&tmp, vel, v);
+    if (p->f.op != &o) SB_FAIL("p does not live on the solver's operator");
+    bool fb = false;
+    SolverStatus st = s->s.projectPredict(v, D(p), proj_dt, vel_ghost, norms, &fb);
+    o.ctx->sync();
+    if (used_fallback) *used_fallback = fb ? 1 : 0;
+    fillStatus(s, st, status, 0.0f);
+    SB_END
+}
+
 // AMRNSLevel::projectCorrect, single level (Grade5_SOMAR/AMRNSLevelProject.cpp:247-373).
 int sb_project_host(sb_solver* s, double* const vel[3], double* phi, double* p, double proj_dt, double* init_div_norm,
                     double* final_div_norm, sb_solver_status* status)

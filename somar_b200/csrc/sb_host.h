@@ -356,6 +356,20 @@ struct HybridSolver {
     double *            cor = nullptr, *res = nullptr, *localRes = nullptr;
     std::vector<double> resNorms;
     sb_mg_options       opt;
+    // LevelHybridSolver::getQuickAndDirtyOptions (LevelHybridSolver.cpp:47-60) switched on / off around the fallback
+    // projection of AMRNSLevel::projectPredict (AMRNSLevelProject.cpp:176-182): hybrid relTol 1e-2, one solver swap, the
+    // MGSolver's quick-and-dirty options (MGSolverI.H:56-74); the leptic options stay (LevelLepticSolver.cpp:67-84)
+    sb_mg_options       optDefine, savedOpt, savedMgOpt;
+    int                 savedSwaps = 10;
+    bool                quickAndDirty = false;
+    void setQuickAndDirty(bool on);
+    // the projection bracket on device-resident fields (sb_project_correct / sb_project_predict): persistent temporaries
+    double *            pDiv = nullptr, *pPhi = nullptr, *pGrad[3] = {nullptr, nullptr, nullptr};
+    void   projectTemps();
+    // AMRNSLevel::projectCorrect (AMRNSLevelProject.cpp:247-373) / projectPredict (:63-243) without the level's own BC fills
+    SolverStatus projectCorrect(double* const vel[3], double* p, double projDt, int velGhost, double* phiOut, double* initDivNorm,
+                                double* finalDivNorm);
+    SolverStatus projectPredict(double* const vel[3], double* p, double projDt, int velGhost, double norms[3], bool* usedFallback);
     static int computeSolveMode(const Op& op);  // LevelHybridSolver.cpp:457-498
     void define(Op& top, const sb_mg_options& o);
     ~HybridSolver();

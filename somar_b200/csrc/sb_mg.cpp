@@ -514,6 +514,7 @@ void HybridSolver::define(Op& top, const sb_mg_options& o)
 {
     op   = &top;
     opt  = o;
+    optDefine = o;
     mode = isHybrid ? computeSolveMode(top) : SB_MODE_MG;
     const bool useLeptic = mode == SB_MODE_LEPTIC || mode == SB_MODE_LEPTIC_MG;
     const bool useMG     = mode == SB_MODE_MG || mode == SB_MODE_LEPTIC_MG;
@@ -537,6 +538,85 @@ HybridSolver::~HybridSolver()
     if (cor) cudaFree(cor);
     if (res) cudaFree(res);
     if (localRes) cudaFree(localRes);
+    if (pDiv) cudaFree(pDiv);
+    if (pPhi) cudaFree(pPhi);
+    for (double* q : pGrad) if (q) cudaFree(q);
+}
+void HybridSolver::setQuickAndDirty(bool on)
+{
+    if (on == quickAndDirty) return;
+    if (on) {
+        savedOpt = opt; savedMgOpt = mg.opt; savedSwaps = maxSolverSwaps;
+        sb_mg_options q = optDefine;  // getDefaultOptions(): the proj.* values this solver was defined with
+        q.absTol = 1.0e-300; q.relTol = 1.0e-300; q.numCycles = -1; q.maxIters = 1; q.verbosity = 0;
+        q.bottom.absTol = 1.0e-300; q.bottom.relTol = 1.0e-300; q.bottom.verbosity = 0;
+        if (!mg.ops.empty()) mg.modifyOptionsExceptMaxDepth(q);
+        const int md = opt.maxDepth;
+        opt = optDefine; opt.maxDepth = md;
+        opt.absTol = 1.0e-300; opt.relTol = 1.0e-2;
+        maxSolverSwaps = 1;
+    } else {
+        if (!mg.ops.empty()) mg.modifyOptionsExceptMaxDepth(savedMgOpt);
+        opt = savedOpt;
+        maxSolverSwaps = savedSwaps;
+    }
+    quickAndDirty = on;
+}
+void HybridSolver::projectTemps()
+{
+    if (pDiv) return;
+    pDiv = op->alloc(); pPhi = op->alloc();
+    for (int d = 0; d < 3; ++d)
+        if (!(op->dim == 2 && d == 1)) pGrad[d] = op->alloc();
+}
+SolverStatus HybridSolver::projectCorrect(double* const vel[3], double* p, double projDt, int velGhost, double* phiOut, double* initDivNorm,
+                                          double* finalDivNorm)
+{
+    Op& o = *op;
+    projectTemps();
+    if (velGhost >= 0) o.scaleVelocity(vel, velGhost, true);                  // sendToAdvectingVelocity      :290
+    o.levelDivergence(pDiv, vel);                                             //                              :293
+    const double n0 = o.norm(pDiv, opt.normType);                             //                              :297
+    if (initDivNorm) *initDivNorm = n0;
+    SolverStatus st = solve(pPhi, pDiv, true, true, -1.0);                    //                              :316
+    o.levelGradient(pGrad, pPhi, true);                                       //                              :328
+    for (int d = 0; d < 3; ++d)
+        if (pGrad[d]) k::incr_valid(o.st(), o.lay, vel[d], pGrad[d], -1.0, d);  // vel.plus(gradPhi, -1.0)     :331-336
+    const double smallReal = 1.0e4 * std::numeric_limits<double>::epsilon();
+    if (p && !(std::abs(projDt) < smallReal)) o.incr(p, pPhi, 1.0 / projDt);  // p.plus(phi, 1 / projDt)      :340-347
+    if (finalDivNorm) {                                                       //                              :354-357
+        o.levelDivergence(pDiv, vel);
+        *finalDivNorm = o.norm(pDiv, opt.normType);
+    }
+    if (phiOut) o.assignLocal(phiOut, pPhi);
+    if (velGhost >= 0) o.scaleVelocity(vel, velGhost, false);                 // sendToCartesianVelocity      :372
+    return st;
+}
+SolverStatus HybridSolver::projectPredict(double* const vel[3], double* p, double projDt, int velGhost, double norms[3], bool* usedFallback)
+{
+    Op& o = *op;
+    projectTemps();
+    SolverStatus st;
+    if (velGhost >= 0) o.scaleVelocity(vel, velGhost, true);                  //                              :126
+    o.levelDivergence(pDiv, vel);                                             //                              :137
+    norms[0] = o.norm(pDiv, opt.normType);
+    o.levelGradient(pGrad, p, false);                                         // levelGradient(gradP, p, crseP, t, false, false) :147
+    for (int d = 0; d < 3; ++d)
+        if (pGrad[d]) k::incr_valid(o.st(), o.lay, vel[d], pGrad[d], -projDt, d);  // vel.plus(gradP, -projDt)  :155-160
+    o.levelDivergence(pDiv, vel);                                             //                              :170
+    norms[1] = o.norm(pDiv, opt.normType);
+    norms[2] = -1.0;
+    if (usedFallback) *usedFallback = false;
+    if (norms[1] > norms[0]) {                                                // the lagged pressure made it worse :176-186
+        setQuickAndDirty(true);
+        st = projectCorrect(vel, p, projDt, -1, nullptr, nullptr, nullptr);
+        setQuickAndDirty(false);
+        o.levelDivergence(pDiv, vel);
+        norms[2] = o.norm(pDiv, opt.normType);
+        if (usedFallback) *usedFallback = true;
+    }
+    if (velGhost >= 0) o.scaleVelocity(vel, velGhost, false);                 //                              :241
+    return st;
 }
 SolverStatus HybridSolver::solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double metric)
 {
