@@ -316,6 +316,18 @@ def run_ours(args):
     k_ms, k_n = ctx.profile_get("vertline@0")
     r_ms, r_n = ctx.profile_get("residual@0")
     tot_line = sum(ctx.profile_get(f"vertline@{d}")[0] for d in range(len(sched)))
+    # where a step spends its time, phase by phase, on the production launch path (rank 0's stream; at N > 1 the waits for
+    # neighbouring tiles and for the agglomerated depths are inside these numbers)
+    ctx.profile(2)
+    step()
+    ctx.profile(0)
+    phases = {}
+    for d in range(len(sched)):
+        for key in ("relax_down", "residual_restrict", "prolong", "relax_up", "bottom", "agglomerated",
+                    "agg.relax_down", "agg.residual_restrict", "agg.prolong", "agg.relax_up", "agg.bottom"):
+            p_ms, p_n = ctx.profile_get(f"{key}@{d}")
+            if p_n:
+                phases[f"{key}@{d}"] = round(p_ms, 4)
 
     # the whole level solve the reference reports as "Solve time" (AMRNSLevelProject.cpp:315-324): MGSolver::solve with
     # the deck defaults (FMG outer iterations to relTol 1e-6) on the synthetic residual
@@ -369,6 +381,8 @@ def run_ours(args):
                                   "what": "same bytes per step, independent inputs double-buffered: upload of step n+1 and "
                                           "download of step n-1 overlap the V-cycle of step n (sb_field_*_async)"}},
             "gpu_launches": launches,
+            "phases_ms": phases,
+            "halo": op.halo_mode(),
             "solve": solve_info,
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"bound": "hbm", "kernel": LINE_KERNEL + " (one colour pass of vertical line relaxation, depth 0)",

@@ -167,6 +167,11 @@ int sb_op_set_metric(sb_op* op, int centering, int box_id, const double* host, c
 int sb_op_finalize(sb_op* op);
 int sb_op_destroy(sb_op* op);
 int sb_op_has_null_space(sb_op* op, int* out);
+/* How the relaxations of this operator exchange face ghosts with neighbouring tiles (LevelData::exchange between the
+ * colours, PoissonOp.cpp:1957-1965): SB_HALO_NONE one rank; SB_HALO_NCCL grouped ncclSend / ncclRecv; SB_HALO_PEER stores
+ * into the neighbour's arrays over NVLink (CUDA IPC).  Meaningful once a relaxation has run. */
+enum { SB_HALO_NONE = 0, SB_HALO_NCCL = 1, SB_HALO_PEER = 2 };
+int sb_op_halo_mode(sb_op* op, int* out);
 /* MGOperator::newMGOperator(refRatio) (PoissonOp.cpp:970-985, coarsening ctor :334-405). */
 int sb_op_new_mg_operator(sb_op* op, const int ref[3], sb_op** crse);
 int sb_op_get_info(sb_op* op, int domain_lo[3], int domain_hi[3], double dXi[3], int* num_local_boxes);

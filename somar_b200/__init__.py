@@ -354,6 +354,12 @@ class PoissonOp:
         capi.check(self.lib.sb_op_has_null_space(self.h, C.byref(v)))
         return bool(v.value)
 
+    def halo_mode(self):
+        """How relaxations exchange face ghosts with neighbouring tiles: 'none', 'nccl' or 'peer' (sb_op_halo_mode)."""
+        v = C.c_int()
+        capi.check(self.lib.sb_op_halo_mode(self.h, C.byref(v)))
+        return ("none", "nccl", "peer")[v.value]
+
     def coefficient(self, which):
         """0 J, 1 Dinv, 2..4 M_d (2*N_d), 5..7 Jgup_d over the (face) domain box."""
         n = np.array(self.domain_hi) - np.array(self.domain_lo) + 1

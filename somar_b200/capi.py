@@ -114,6 +114,7 @@ PROTOTYPES = {
     "sb_op_finalize": (C.c_int, [P]),
     "sb_op_destroy": (C.c_int, [P]),
     "sb_op_has_null_space": (C.c_int, [P, IP]),
+    "sb_op_halo_mode": (C.c_int, [P, IP]),
     "sb_op_new_mg_operator": (C.c_int, [P, IP, PP]),
     "sb_op_get_info": (C.c_int, [P, IP, IP, DP, IP]),
     "sb_op_get_coefficient": (C.c_int, [P, C.c_int, DP, C.c_longlong]),

@@ -89,7 +89,8 @@ int sb_context_profile(sb_context* ctx, int enable)
     SB_TRY DEVG(ctx) REQ(ctx);
     ctx->c.profResolve();
     if (enable) ctx->c.prof.clear();
-    ctx->c.profiling = enable != 0;
+    ctx->c.profiling = enable == 1;   // per launch (plain launches, no graph replay)
+    ctx->c.phases    = enable == 2;   // per V-cycle phase, production launch path
     SB_END
 }
 int sb_context_profile_get(sb_context* ctx, const char* key, double* total_ms, long long* count)
@@ -244,6 +245,14 @@ int sb_op_set_metric(sb_op* op, int centering, int box_id, const double* host, c
 }
 int sb_op_finalize(sb_op* op) { SB_TRY DEVG(op) REQ(op); op->op->finalize(); op->op->ctx->sync(); SB_END }
 int sb_op_has_null_space(sb_op* op, int* out) { SB_TRY DEVG(op) REQ(op); REQ(out); *out = op->op->hasNullSpace; SB_END }
+int sb_op_halo_mode(sb_op* op, int* out)
+{
+    SB_TRY DEVG(op) REQ(op); REQ(out);
+    const Op& o = *op->op;
+    const PeerHalo* h = o.haloLine ? o.haloLine.get() : o.haloGsrb.get();
+    *out = o.ctx->nranks <= 1 ? SB_HALO_NONE : (h && h->ready) ? SB_HALO_PEER : SB_HALO_NCCL;
+    SB_END
+}
 int sb_op_new_mg_operator(sb_op* op, const int ref[3], sb_op** crse)
 {
     SB_TRY DEVG(op) REQ(op); REQ(crse);

@@ -6,6 +6,7 @@
 #include <map>
 
 #include "sb_core.h"
+#include "sb_halo.h"
 #include "sb_line_tma.h"
 
 namespace sb {
@@ -25,16 +26,22 @@ struct Context {
     void*        scratch = nullptr;  // device scratch shared by all depths (line-relax workspace)
     size_t       scratchBytes = 0;
     Comm*        comm = nullptr;
+    bool         peerHalo = true;   // SB_PEER_HALO=0 at creation: keep the NCCL face exchange inside the relaxations
+    cudaEvent_t  evPost = nullptr;  // last peer post of a pass loop (joins commSt back into st)
     Context*     parent = nullptr;  // set on the single-rank view used by agglomerated MG depths: stream and profile are the parent's
     long long    launches0 = 0;
     // optional per-kernel timing (CUDA events on `st` around selected launches)
     bool         profiling = false;
+    bool         phases = false;     // coarse profile: one record per phase of a V-cycle (relax / residual+restrict / prolong / agglomerated
+                                     // depths), production launch path (CUDA graphs stay on)
     struct ProfRec { std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; double ms = 0; long long count = 0; };
     std::map<std::string, ProfRec> prof;
     cudaEvent_t  tm0 = nullptr, tm1 = nullptr;  // sb_context_timer_start/stop
     void profBegin(const char* key, int depth, cudaEvent_t* e0);
     void profEnd(const char* key, int depth, cudaEvent_t e0);
     void profResolve();
+    void phaseBegin(cudaEvent_t* e0);
+    void phaseEnd(const char* key, int depth, cudaEvent_t e0);
     bool isProfiling() const { return parent ? parent->profiling : profiling; }
 
     Context(int dev, int rank, int nranks);
@@ -157,7 +164,9 @@ struct Op {
     double* lineTabG = nullptr;         // general: [MzL | MzR]
     double* gstart = nullptr;           // general: [NW - 1][ny][nx]
     double  lineSLo = 0.0, lineSHi = 0.0;
-    void    linePass(int pass, int region = 0, int nbMask = 0);  // one colour pass on sp[], whichever kernel applies
+    // one colour pass on sp[], whichever kernel applies; fusedHalo (vertline_tma_k only): the pass also delivers its face
+    // layers to the neighbouring tiles (haloLine) and publishes their arrival
+    void    linePass(int pass, int region = 0, int nbMask = 0, bool fusedHalo = false);
     const double* splitResSrc = nullptr;  // natural-layout field whose split copy sp[2], sp[3] hold
     // point GSRB on colour-split storage with z ghosts (sb_line.cu: gsrb_split_k): cor, rhs, J, Dinv x 2 colours
     SLay    slayG;
@@ -173,6 +182,9 @@ struct Op {
     void linePasses(int iters);  // the (ghost fill, colour pass) x 2 x iters loop on sp[]
     std::vector<double> hM[3];  // host copies of the 1-D tables over the whole domain (2*N_d)
     double* xbuf[3][2][2] = {};  // exchange buffers [dir][side][send/recv]
+    // neighbour exchange of the split fields by stores into the neighbour's arrays (sb_halo.cu); null: NCCL send / recv.
+    // haloLine owns sp[0], sp[1]; haloGsrb owns sg[0], sg[1].
+    std::unique_ptr<PeerHalo> haloLine, haloGsrb;
 
     Op(Context* ctx, const sb_level_desc& d);
     Op(const Op& fine, const int ref[3]);  // coarsening ctor, PoissonOp.cpp:334-405

@@ -79,6 +79,53 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
 }
 __device__ __forceinline__ void consumer_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Schedule slot u -> tile (bx, j).  Plain order without a fused exchange; otherwise the tiles touching an exchanged side
+// first: row 0 (nA), row ny-1 (nB), column 0 (nC), column nbx-1 (nD), then the interior rectangle.
+__device__ __forceinline__ void tile_of(const LineTmaArgs& A, int ny, int u, int& bx, int& j)
+{
+    if (!A.halo) { bx = u % A.nbx; j = u / A.nbx; return; }
+    if (u < A.nA) { bx = u; j = 0; return; }
+    u -= A.nA;
+    if (u < A.nB) { bx = u; j = ny - 1; return; }
+    u -= A.nB;
+    if (u < A.nC) { bx = 0; j = A.jlo + u; return; }
+    u -= A.nC;
+    if (u < A.nD) { bx = A.nbx - 1; j = A.jlo + u; return; }
+    u -= A.nD;
+    bx = A.bxlo + u % A.nbxi;
+    j  = A.jlo + u / A.nbxi;
+}
+// sides of the tile an exchanged face layer lies on: bit 2 * dir + side
+__device__ __forceinline__ int tile_touch(const LineTmaArgs& A, int ny, int bx, int j)
+{
+    if (!A.halo) return 0;
+    return (((A.nbMask & 1) && bx == 0) ? 1 : 0) | (((A.nbMask & 2) && bx == A.nbx - 1) ? 2 : 0) | (((A.nbMask & 4) && j == 0) ? 4 : 0) |
+           (((A.nbMask & 8) && j == ny - 1) ? 8 : 0);
+}
+// One CTA has finished a tile on the sides in `touch` (its stores fenced, its threads past a barrier): count it, and
+// publish the side's arrival counter in the neighbour's memory when it was the last one.
+__device__ __forceinline__ void halo_signal(const LineTmaArgs& A, int ny, int touch)
+{
+    const HaloDev& H = *A.halo;
+    for (int s = 0; s < 4; ++s) {
+        if (!((touch >> s) & 1)) continue;
+        const unsigned int count = s < 2 ? (unsigned int)ny : (unsigned int)A.nbx;  // tiles along an x side / a y side
+        __threadfence_system();
+        const unsigned int old = atomicAdd(H.done + s, 1u);
+        if (old == count - 1) {
+            H.done[s] = 0;
+            const unsigned long long e = H.posted[s] + 1;
+            H.posted[s] = e;
+            __threadfence_system();
+            st_release_sys_u64(H.side[s].rflag, e);
+        }
+    }
+}
+
 constexpr int OTHW = 36;  // box width of the other colour's rows: cells m0 - 2 .. m0 + 33 (the innermost TMA coordinate must be
                           // 16-byte aligned, i.e. even for doubles -- measured: an odd start is an illegal instruction)
 // One stage holds the boxes of ALL chunks: the tensor maps view z as (level in chunk, chunk), so a single 4-D box
@@ -136,7 +183,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             int      stage = 0;
             uint32_t phase = 0;
             for (int t = t0; t < ntiles; t = next_tile(t)) {
-                const int bx = t % nbx, j = t / nbx;
+                int bx, j;
+                tile_of(A, nby, t, bx, j);
                 const int x0 = SOX + bx * 32 - 2;  // element of cell m0 - 2 in a row of a colour array (even)
                 for (int sl = 0; sl < nslab; ++sl) {
                     uint64_t* fb = full + stage;
@@ -166,8 +214,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     int             stage = 0;
     uint32_t        phase = 0;
     int             set = 0;
+    int             pending = 0;  // sides of the previous tile still to be counted (done after the next barrier)
     for (int t = t0; t < ntiles; t = next_tile(t)) {
-        const int  bx = t % nbx, j = t / nbx;
+        int bx, j;
+        tile_of(A, nby, t, bx, j);
+        const int  touch = tile_touch(A, nby, bx, j);
         const int  i0 = (A.pass + Sl.par + j) & 1;  // own cells of this row: i = 2 m + i0
         const int  m  = bx * 32 + lane;
         const bool act = 2 * m + i0 < Sl.nx;
@@ -237,6 +288,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             cz[(4 * NW + w) * 32 + lane] = R;
         }
         consumer_bar(NW * 32);
+        if (pending) {
+            if (threadIdx.x == 0) halo_signal(A, nby, pending);
+            pending = 0;
+        }
 
         // Carries.  Zs[v]: true z just below chunk v; X: true x just above this warp's chunk.
         double Zs[NW];
@@ -257,10 +312,29 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                 X = fma(re, X, fma(Zs[v], tv, ca[v * 32 + lane]));
             }
 
-        // P2: true backward sweep of this chunk, straight to HBM.
+        // P2: true backward sweep of this chunk, straight to HBM -- and, for cells of an exchanged face layer, into the
+        // neighbour's ghost cell as well (rq[0]: across a y side, rq[1]: across an x side; a corner cell feeds both).
         const long long base = (long long)(SOX + (act ? m : 0)) + Sl.sy * (long long)(1 + j);
         double* po = A.own + base + (long long)(k1 - 1) * szl;
         double  xl = X;
+        double*   rq[2]  = {nullptr, nullptr};
+        long long rqs[2] = {0, 0};
+        if (touch && act) {
+            const HaloDev& H = *A.halo;
+            if (touch & 12) {
+                const HaloPeerSide& Pq = H.side[(touch & 4) ? 2 : 3];
+                rq[0]  = Pq.rs[A.pass] + (long long)(SOX + m) + Pq.rsy * (long long)Pq.rrow + Pq.rsz * (long long)(k1 - 1);
+                rqs[0] = Pq.rsz;
+            }
+            const int sx = ((touch & 1) && ii == 0) ? 0 : ((touch & 2) && ii == Sl.nx - 1) ? 1 : -1;
+            if (sx >= 0) {
+                const HaloPeerSide& Pq = H.side[sx];
+                rq[1]  = Pq.rs[A.pass] + (long long)Pq.rx + Pq.rsy * (long long)(1 + j) + Pq.rsz * (long long)(k1 - 1);
+                rqs[1] = Pq.rsz;
+            }
+        }
+        // warp-uniform choice of the loop: a lane with a neighbour-bound cell drags its warp through the predicated stores
+        const bool remote = touch && __any_sync(0xffffffffu, rq[0] || rq[1]);
         if (GENERAL) {
             // true forward values first: z_k = zl_k + P'_k Z (P'_k recomputed exactly as in P1)
             double Pp = 1.0;
@@ -275,6 +349,18 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                 xl = fma(cc, xl, sy[k * 32 + lane]);
                 if (act) *po = xl;
                 po -= szl;
+                if (remote) {
+                    if (rq[0]) { *rq[0] = xl; rq[0] -= rqs[0]; }
+                    if (rq[1]) { *rq[1] = xl; rq[1] -= rqs[1]; }
+                }
+            }
+        } else if (!remote) {
+#pragma unroll 4
+            for (int k = k1 - 1; k >= k0; --k) {
+                const double2 tt = T2[k];
+                xl = fma(tt.y, xl, fma(tt.x, Zm, sy[k * 32 + lane]));
+                if (act) *po = xl;
+                po -= szl;
             }
         } else {
 #pragma unroll 4
@@ -283,9 +369,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                 xl = fma(tt.y, xl, fma(tt.x, Zm, sy[k * 32 + lane]));
                 if (act) *po = xl;
                 po -= szl;
+                if (rq[0]) { *rq[0] = xl; rq[0] -= rqs[0]; }
+                if (rq[1]) { *rq[1] = xl; rq[1] -= rqs[1]; }
             }
         }
+        // the tile is counted after the next barrier: thread 0's system-scope fence there covers every consumer's stores
+        if (touch) pending = touch;
         set ^= 1;
+    }
+    if (pending) {
+        consumer_bar(NW * 32);
+        if (threadIdx.x == 0) halo_signal(A, nby, pending);
     }
 }
 
@@ -392,6 +486,22 @@ void vertline_tma_pass(cudaStream_t st, const SLay& S, const LineTmaMap& mapOth,
     LineTmaArgs A = args;
     A.nbx    = ((S.nx + 1) / 2 + 31) / 32;
     A.ntiles = A.nbx * S.ny;
+    A.nA = A.nB = A.nC = A.nD = A.jlo = A.bxlo = 0;
+    A.nbxi = A.nbx;
+    if (A.halo) {
+        if (A.region != 0 || S.ny < 2 || S.nx < 2) SB_FAIL("vertline_tma: the fused exchange needs region 0 and a tile of at least 2 x 2 columns");
+        const bool xlo = A.nbMask & 1, xhi = A.nbMask & 2, ylo = A.nbMask & 4, yhi = A.nbMask & 8;
+        A.nA  = ylo ? A.nbx : 0;
+        A.nB  = yhi ? A.nbx : 0;
+        A.jlo = ylo ? 1 : 0;
+        const int jhi = yhi ? S.ny - 2 : S.ny - 1, nrows = jhi - A.jlo + 1 > 0 ? jhi - A.jlo + 1 : 0;
+        A.nC   = xlo ? nrows : 0;
+        A.nD   = xhi && !(xlo && A.nbx == 1) ? nrows : 0;
+        A.bxlo = A.nC ? 1 : 0;
+        const int bxhi = A.nD ? A.nbx - 2 : A.nbx - 1;
+        A.nbxi = bxhi - A.bxlo + 1 > 0 ? bxhi - A.bxlo + 1 : 0;
+        if (A.nA + A.nB + A.nC + A.nD + A.nbxi * nrows != A.ntiles) SB_FAIL("vertline_tma: tile schedule does not cover the tile");
+    }
     const int grid = A.ntiles < nsm ? A.ntiles : nsm;
     const CUtensorMap& mo = reinterpret_cast<const CUtensorMap&>(mapOth);
     const CUtensorMap& mr = reinterpret_cast<const CUtensorMap&>(mapRhs);

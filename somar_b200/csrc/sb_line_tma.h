@@ -1,6 +1,7 @@
 // sb_line_tma.h -- host interface of the TMA-staged line relaxation kernel (sb_line_tma.cu).
 #pragma once
 #include "sb_core.h"
+#include "sb_halo.h"
 
 namespace sb {
 
@@ -16,6 +17,12 @@ struct LineTmaArgs {
     int           pass, region, nbMask;
     int           nbx, ntiles;    // filled by the launcher
     int*          fault;          // mapped host record written before a watchdog trap (may be null)
+    // Neighbouring tiles, fused exchange (halo != null, region == 0): the tiles that touch an exchanged side (nbMask) run
+    // first, their backward sweeps also store the face layer into the neighbour's ghost cells (peer memory), and the CTA
+    // that completes the last tile of a side publishes the side's arrival counter (sb_halo.cu: same protocol as
+    // halo_post_k).  The schedule below (filled by the launcher) enumerates: row 0, row ny-1, column 0, column nbx-1, interior.
+    const HaloDev* halo;
+    int           nA, nB, nC, nD, jlo, bxlo, nbxi;
 };
 
 namespace k {

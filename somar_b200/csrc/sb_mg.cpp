@@ -443,33 +443,47 @@ SolverStatus MGSolver::cycle(bool fmgMode, double* phi, const double* rhs, bool 
 void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth, bool corIsPreCond)
 {
     const int pre = corIsPreCond ? Op::RELAX_PRE_PRECOND : Op::RELAX_PRE_NONE;
+    cudaEvent_t e0;
+    Context*    pc = ops[depth]->ctx;
     if (depth == aggDepth) {  // the rest of the hierarchy runs on rank 0
         Op& dist = *ops[depth];
+        pc->phaseBegin(&e0);
         aggGather(a_res, aggRes, SB_CELL, dist);
         if (!corIsPreCond) aggGather(a_cor, aggCor, SB_CELL, dist);
         if (agg) agg->vCycle_residualEq(aggCor, aggRes, 0, corIsPreCond);
         aggScatter(a_cor, aggCor, dist);
+        pc->phaseEnd("agglomerated", depth, e0);
         return;
     }
     Op& op = *ops[depth];
     if (depth == opt.maxDepth) {
+        pc->phaseBegin(&e0);
         op.relax(a_cor, a_res, opt.numSmoothBottom, false, pre);
         if (bottom) bottom->solve(a_cor, a_res, true, false);
+        pc->phaseEnd("bottom", depth, e0);
         return;
     }
     Op&     crseOp  = *ops[depth + 1];
     double* crseCor = cor[depth + 1];
     double* crseRes = res[depth + 1];
     double* tmp     = tmpRes[depth];
+    pc->phaseBegin(&e0);
     op.relax(a_cor, a_res, opt.numSmoothDown, false, pre);
+    pc->phaseEnd("relax_down", depth, e0);
+    pc->phaseBegin(&e0);
     op.residual(tmp, a_cor, a_res, true);
     op.MGRestrict(crseOp, crseRes, tmp);
+    pc->phaseEnd("residual_restrict", depth, e0);
     const int numCycles = std::abs(opt.numCycles);
     if (numCycles == 0) crseOp.preCond(crseCor, crseRes, 0);
     for (int i = 0; i < numCycles; ++i) vCycle_residualEq(crseCor, crseRes, depth + 1, /*crseOp.preCond(crseCor, crseRes, 0)*/ i == 0);
+    pc->phaseBegin(&e0);
     const bool shiftPending = op.MGProlong(crseOp, a_cor, crseCor, opt.prolongOrder, /*deferKernel*/ true);
+    pc->phaseEnd("prolong", depth, e0);
+    pc->phaseBegin(&e0);
     op.relax(a_cor, a_res, opt.numSmoothUp, /*resUnchanged since the down-relax*/ opt.numSmoothDown >= 2,
              shiftPending ? Op::RELAX_PRE_SHIFT : Op::RELAX_PRE_NONE);
+    pc->phaseEnd("relax_up", depth, e0);
 }
 
 // MGSolver<T>::fmg_residualEq (MGSolverI.H:758-820)

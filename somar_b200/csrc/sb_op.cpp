@@ -24,6 +24,7 @@ Context::Context(int dev, int rank_, int nranks_) : device(dev), rank(rank_), nr
     SB_CUDA(cudaHostAlloc((void**)&fault, 16 * sizeof(int), cudaHostAllocMapped));
     std::memset(fault, 0, 16 * sizeof(int));
     launches0 = k::launch_count();
+    { const char* e = getenv("SB_PEER_HALO"); peerHalo = !(e && std::string(e) == "0"); }
 }
 void Context::sync()
 {
@@ -49,6 +50,7 @@ Context::~Context()
     if (fault) cudaFreeHost(fault);
     if (evEdge) cudaEventDestroy(evEdge);
     if (evHalo) cudaEventDestroy(evHalo);
+    if (evPost) cudaEventDestroy(evPost);
     if (commSt) cudaStreamDestroy(commSt);
     for (cudaStream_t q : copySt) if (q) cudaStreamDestroy(q);
     if (st && !parent) cudaStreamDestroy(st);
@@ -73,6 +75,23 @@ void Context::profEnd(const char* key, int depth, cudaEvent_t e0)
 {
     if (parent) { parent->profEnd(key, depth, e0); return; }
     if (!profiling || !e0) return;
+    cudaEvent_t e1;
+    SB_CUDA(cudaEventCreate(&e1));
+    SB_CUDA(cudaEventRecord(e1, st));
+    prof[std::string(key) + "@" + std::to_string(depth)].ev.emplace_back(e0, e1);
+}
+void Context::phaseBegin(cudaEvent_t* e0)
+{
+    if (parent) { parent->phaseBegin(e0); return; }
+    *e0 = nullptr;
+    if (!phases) return;
+    SB_CUDA(cudaEventCreate(e0));
+    SB_CUDA(cudaEventRecord(*e0, st));
+}
+void Context::phaseEnd(const char* key, int depth, cudaEvent_t e0)
+{
+    if (parent) { parent->phaseEnd((std::string("agg.") + key).c_str(), depth, e0); return; }  // depths of the agglomerated hierarchy count from its top
+    if (!phases || !e0) return;
     cudaEvent_t e1;
     SB_CUDA(cudaEventCreate(&e1));
     SB_CUDA(cudaEventRecord(e1, st));
@@ -354,8 +373,8 @@ Op::~Op()
     cudaFree(J); cudaFree(Dinv);
     for (int i = 0; i < 3; ++i) cudaFree(Jgup[i]);
     cudaFree(lineTab); cudaFree(lineTabS); cudaFree(lineTabG); cudaFree(gstart);
-    for (double* q : sp) cudaFree(q);
-    for (double* q : sg) cudaFree(q);
+    for (int q = 0; q < 4; ++q) if (q >= 2 || !haloLine) cudaFree(sp[q]);   // sp[0], sp[1] live in haloLine's block
+    for (int q = 0; q < 8; ++q) if (q >= 2 || !haloGsrb) cudaFree(sg[q]);
     for (auto& kv : relaxGraphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     cudaFree(mtab); cudaFree(loBC); cudaFree(hiBC); cudaFree(boxLoHi); cudaFree(redPartial); cudaFree(redOut); cudaFree(shiftBuf); cudaFree(pivotFlag);
     for (int d = 0; d < 3; ++d)
@@ -818,9 +837,14 @@ void Op::checkPivot()
 void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUnchanged, int pre)
 {
     if (!sp[0]) {
-        for (double*& q : sp) {
-            SB_CUDA(cudaMalloc((void**)&q, slay.n * sizeof(double)));
-            SB_CUDA(cudaMemsetAsync(q, 0, slay.n * sizeof(double), ctx->st));
+        // with neighbouring tiles the two colour arrays of the correction live in a block the neighbours can write
+        if (ctx->nranks > 1 && ctx->peerHalo) {
+            haloLine.reset(new PeerHalo);
+            haloLine->setup(*this, slay, &sp[0], &sp[1]);
+        }
+        for (int q = haloLine ? 2 : 0; q < 4; ++q) {
+            SB_CUDA(cudaMalloc((void**)&sp[q], slay.n * sizeof(double)));
+            SB_CUDA(cudaMemsetAsync(sp[q], 0, slay.n * sizeof(double), ctx->st));
         }
         splitResSrc = nullptr;
         tmaMapsReady = false;
@@ -853,31 +877,59 @@ void Op::relaxLineSplit(double* cor, const double* res, int iters, bool resUncha
             SB_CUDA(cudaStreamCreateWithFlags(&ctx->commSt, cudaStreamNonBlocking));
             SB_CUDA(cudaEventCreateWithFlags(&ctx->evEdge, cudaEventDisableTiming));
             SB_CUDA(cudaEventCreateWithFlags(&ctx->evHalo, cudaEventDisableTiming));
+            SB_CUDA(cudaEventCreateWithFlags(&ctx->evPost, cudaEventDisableTiming));
         }
         int nbMask = 0;
         for (int d = 0; d < 2; ++d)
             for (int s = 0; s < 2; ++s)
                 if (side[d][s].kind == SIDE_NEIGHBOR) nbMask |= 1 << (2 * d + s);
-        const int last = 2 * iters - 1;
+        const int  last = 2 * iters - 1;
+        const bool peer = haloLine && haloLine->ready;
+        // peer posts run on the compute stream between the edge and the interior part of a pass (SB_HALO_FORK=1: on
+        // the second stream, which relies on the two streams making progress concurrently)
+        static const bool haloFork = [] { const char* e = getenv("SB_HALO_FORK"); return e && std::string(e) == "1"; }();
+        static const bool haloFuse = [] { const char* e = getenv("SB_HALO_FUSED"); return !(e && std::string(e) == "0"); }();
+        const bool fused = peer && haloFuse && lineTma && nbMask && slay.nx >= 2 && slay.ny >= 2;
         auto passes = [&](bool prof) {
+            bool forked = false;
+            // both sides are done with the ghosts of the previous relaxation on this depth
+            if (peer) { haloLine->post(st(), slay, sp[0], sp[1], 0); haloLine->wait(st()); }
             for (int n = 0; n <= last; ++n) {
                 const int pass = n & 1;
                 k::fill_ghosts_split(st(), slay, sp[0], sp[1], side, dim, pass == 0);
-                if (n == 0) ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1]);
+                if (peer) {
+                    if (n == 0) haloLine->post(st(), slay, sp[0], sp[1], 3);
+                    haloLine->wait(st());
+                } else if (n == 0) ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1]);
                 else SB_CUDA(cudaStreamWaitEvent(st(), ctx->evHalo, 0));
                 if (prof) ctx->profBegin("vertline", depth, &e0);
-                if (nbMask && n < last) {
+                if (fused) {
+                    // one kernel: the tiles along the exchanged sides first, their results stored into the neighbours' ghost
+                    // cells by the sweep that computes them, the arrival published by the last such tile (sb_line_tma.cu)
+                    linePass(pass, 0, nbMask, /*fusedHalo*/ n < last);
+                } else if (nbMask && n < last) {
                     linePass(pass, 1, nbMask);
-                    SB_CUDA(cudaEventRecord(ctx->evEdge, st()));
-                    SB_CUDA(cudaStreamWaitEvent(ctx->commSt, ctx->evEdge, 0));
-                    ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1], ctx->commSt);
-                    SB_CUDA(cudaEventRecord(ctx->evHalo, ctx->commSt));
+                    if (peer && !haloFork) {
+                        haloLine->post(st(), slay, sp[0], sp[1], 1 << pass);
+                    } else {
+                        SB_CUDA(cudaEventRecord(ctx->evEdge, st()));
+                        SB_CUDA(cudaStreamWaitEvent(ctx->commSt, ctx->evEdge, 0));
+                        if (peer) { haloLine->post(ctx->commSt, slay, sp[0], sp[1], 1 << pass); forked = true; }
+                        else {
+                            ctx->comm->exchangeFacesSplit(*this, sp[0], sp[1], ctx->commSt);
+                            SB_CUDA(cudaEventRecord(ctx->evHalo, ctx->commSt));
+                        }
+                    }
                     linePass(pass, 2, nbMask);
                 } else {
                     linePass(pass);
-                    if (n < last) SB_CUDA(cudaEventRecord(ctx->evHalo, st()));
+                    if (!peer && n < last) SB_CUDA(cudaEventRecord(ctx->evHalo, st()));
                 }
                 if (prof) ctx->profEnd("vertline", depth, e0);
+            }
+            if (forked) {  // join the second stream
+                SB_CUDA(cudaEventRecord(ctx->evPost, ctx->commSt));
+                SB_CUDA(cudaStreamWaitEvent(st(), ctx->evPost, 0));
             }
         };
         // The whole pass loop -- kernels on two streams, the NCCL face exchanges between them -- is captured once per
@@ -946,9 +998,13 @@ void Op::relaxGsrbSplit(double* cor, const double* res, int iters, bool resUncha
 {
     if (!sg[0]) {
         slayG = makeSLay(lay, 1);
-        for (double*& q : sg) {
-            SB_CUDA(cudaMalloc((void**)&q, slayG.n * sizeof(double)));
-            SB_CUDA(cudaMemsetAsync(q, 0, slayG.n * sizeof(double), ctx->st));
+        if (ctx->nranks > 1 && ctx->peerHalo) {
+            haloGsrb.reset(new PeerHalo);
+            haloGsrb->setup(*this, slayG, &sg[0], &sg[1]);
+        }
+        for (int q = haloGsrb ? 2 : 0; q < 8; ++q) {
+            SB_CUDA(cudaMalloc((void**)&sg[q], slayG.n * sizeof(double)));
+            SB_CUDA(cudaMemsetAsync(sg[q], 0, slayG.n * sizeof(double), ctx->st));
         }
         splitResSrcG  = nullptr;
         gsrbCoefSplit = false;
@@ -968,20 +1024,28 @@ void Op::relaxGsrbSplit(double* cor, const double* res, int iters, bool resUncha
     const double* const Jc[2] = {sg[4], sg[5]};
     const double* const Dc[2] = {sg[6], sg[7]};
     cudaEvent_t e0;
+    // neighbouring tiles: the cells a pass has updated go straight into the neighbour's ghost cells (sb_halo.cu); the
+    // bare post / wait pair first says that both sides are done with the ghosts of the previous call
+    const bool peer = haloGsrb && haloGsrb->ready;
+    if (peer) { haloGsrb->post(st(), slayG, sg[0], sg[1], 0); haloGsrb->wait(st()); }
     for (int it = 0; it < iters; ++it)
         for (int pass = 0; pass < 2; ++pass) {
             const bool physToo = pass == 0;
             k::fill_ghosts_split(st(), slayG, sg[0], sg[1], side, dim, physToo);
             k::fill_ghosts_split_z(st(), slayG, sg[0], sg[1], side[2][0], side[2][1], physToo);
-            if (ctx->nranks > 1) ctx->comm->exchangeFacesSplit(*this, sg[0], sg[1], nullptr, &slayG);
+            if (peer) {
+                if (it == 0 && pass == 0) haloGsrb->post(st(), slayG, sg[0], sg[1], 3);
+                haloGsrb->wait(st());
+            } else if (ctx->nranks > 1) ctx->comm->exchangeFacesSplit(*this, sg[0], sg[1], nullptr, &slayG);
             ctx->profBegin("gsrb", depth, &e0);
             k::gsrb_split_pass(st(), slayG, coef(), p, r, Jc, Dc, pass);
             ctx->profEnd("gsrb", depth, e0);
+            if (peer && !(it == iters - 1 && pass == 1)) haloGsrb->post(st(), slayG, sg[0], sg[1], 0, pass);
         }
     k::unsplit_field(st(), lay, slayG, cor, sg[0], sg[1]);
 }
 
-void Op::linePass(int pass, int region, int nbMask)
+void Op::linePass(int pass, int region, int nbMask, bool fusedHalo)
 {
     if (lineTma) {
         LineTmaArgs a;
@@ -993,6 +1057,7 @@ void Op::linePass(int pass, int region, int nbMask)
         a.aob = alpha / beta; a.sLo = lineSLo; a.sHi = lineSHi;
         a.pass = pass; a.region = region; a.nbMask = nbMask; a.nbx = a.ntiles = 0;
         a.fault = ctx->parent ? ctx->parent->fault : ctx->fault;
+        a.halo  = fusedHalo ? haloLine->devCopy : nullptr;
         k::vertline_tma_pass(st(), slay, tmaOth[1 - pass], tmaRhs[pass], a, lineGeneral);
         return;
     }
