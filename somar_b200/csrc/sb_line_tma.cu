@@ -79,6 +79,16 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
 }
 __device__ __forceinline__ void consumer_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
+__device__ __forceinline__ unsigned int ld_acquire_cta_shared(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_cta_shared_add(unsigned int* p, unsigned int v)
+{
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -138,7 +148,7 @@ __host__ __device__ constexpr int rhsBytes(int KZ, int NW) { return ((32 * KZ * 
 // tab (shared matrix): {a', g}[N] | {P', c}[N] | R[N] | Pend[NW] | T[NW] | Rend[NW]   (Op::buildLineTables)
 // tab (general):       MzL[N] | MzR[N]
 template <int NW, int KZ, int S, bool GENERAL>
-__global__ void __launch_bounds__((NW + 1) * 32, 1)
+__global__ void __launch_bounds__((NW + 2) * 32, 1)
     vertline_tma_k(const __grid_constant__ CUtensorMap mapOth, const __grid_constant__ CUtensorMap mapRhs, SLay Sl, LineTmaArgs A)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -155,6 +165,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     uint64_t* const bars = reinterpret_cast<uint64_t*>(ts + ((ntab + 1) & ~1));  // full[S], empty[S]
     uint64_t* const full = bars;
     uint64_t* const empt = bars + S;
+    unsigned int* const tilesDone = reinterpret_cast<unsigned int*>(bars + 2 * S);  // consumer warps that have finished an exchanged tile
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nbx = A.nbx, ntiles = A.ntiles, nby = Sl.ny;
@@ -169,8 +180,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     int t0 = blockIdx.x;
     while (t0 < ntiles && !in_region(t0)) t0 += gridDim.x;
 
-    for (int k = threadIdx.x; k < ntab; k += (NW + 1) * 32) ts[k] = A.tab[k];
+    for (int k = threadIdx.x; k < ntab; k += (NW + 2) * 32) ts[k] = A.tab[k];
     if (threadIdx.x == 0) {
+        *tilesDone = 0;
         for (int i = 0; i < S; ++i) { mbar_init(full + i, 1); mbar_init(empt + i, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -199,6 +211,31 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
         }
         return;
     }
+    if (w == NW + 1) {
+        // ===== signaller (fused exchange): counts this CTA's tiles on exchanged sides as the consumers finish them and
+        // publishes a side's arrival counter in the neighbour's memory when its last tile is in.  The system-scope fences
+        // this takes (they wait for the SM's outstanding stores) stay off the consumer warps.
+        if (lane == 0 && A.halo) {
+            unsigned int seen = 0;
+            for (int t = t0; t < ntiles; t = next_tile(t)) {
+                int bx, j;
+                tile_of(A, nby, t, bx, j);
+                const int touch = tile_touch(A, nby, bx, j);
+                if (!touch) continue;
+                seen += NW;
+                unsigned int spin = 0;
+                while (ld_acquire_cta_shared(tilesDone) < seen) {
+                    __nanosleep(100);
+                    if (++spin > (1u << 24)) {
+                        if (A.fault) { A.fault[1] = 4000; A.fault[2] = (int)blockIdx.x; A.fault[3] = (int)seen; A.fault[4] = 0; A.fault[0] = 1; __threadfence_system(); }
+                        __trap();
+                    }
+                }
+                halo_signal(A, nby, touch);
+            }
+        }
+        return;
+    }
 
     // ===== consumers =====
     const double2* const T1 = reinterpret_cast<const double2*>(ts);          // shared: {a', g}
@@ -214,7 +251,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     int             stage = 0;
     uint32_t        phase = 0;
     int             set = 0;
-    int             pending = 0;  // sides of the previous tile still to be counted (done after the next barrier)
     for (int t = t0; t < ntiles; t = next_tile(t)) {
         int bx, j;
         tile_of(A, nby, t, bx, j);
@@ -288,10 +324,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
             cz[(4 * NW + w) * 32 + lane] = R;
         }
         consumer_bar(NW * 32);
-        if (pending) {
-            if (threadIdx.x == 0) halo_signal(A, nby, pending);
-            pending = 0;
-        }
 
         // Carries.  Zs[v]: true z just below chunk v; X: true x just above this warp's chunk.
         double Zs[NW];
@@ -373,13 +405,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                 if (rq[1]) { *rq[1] = xl; rq[1] -= rqs[1]; }
             }
         }
-        // the tile is counted after the next barrier: thread 0's system-scope fence there covers every consumer's stores
-        if (touch) pending = touch;
+        // hand the tile to the signaller: release at CTA scope, so that its system-scope fence covers this warp's stores
+        if (touch) {
+            __syncwarp();
+            if (lane == 0) red_release_cta_shared_add(tilesDone, 1u);
+        }
         set ^= 1;
-    }
-    if (pending) {
-        consumer_bar(NW * 32);
-        if (threadIdx.x == 0) halo_signal(A, nby, pending);
     }
 }
 
@@ -447,7 +478,7 @@ size_t tma_smem(int nz, bool general, int S)
     const int    nsum = general ? 5 : 2;
     const size_t ntab = general ? 2 * (size_t)nz : 5 * (size_t)nz + 3 * TNW;
     return (size_t)S * (othBytes(TKZ, TNW) + rhsBytes(TKZ, TNW)) + ((size_t)nz * 32 * (general ? 2 : 1) + 2 * nsum * TNW * 32 + ((ntab + 1) & ~(size_t)1)) * 8 +
-           2 * (size_t)S * 8;
+           2 * (size_t)S * 8 + 16;
 }
 }  // namespace
 
@@ -513,7 +544,7 @@ void vertline_tma_pass(cudaStream_t st, const SLay& S, const LineTmaMap& mapOth,
             SB_CUDA(cudaFuncSetAttribute(vertline_tma_k<TNW, TKZ, STG, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); \
             configured = sh;                                                                                                     \
         }                                                                                                                        \
-        vertline_tma_k<TNW, TKZ, STG, GEN><<<grid, (TNW + 1) * 32, sh, st>>>(mo, mr, S, A);                                       \
+        vertline_tma_k<TNW, TKZ, STG, GEN><<<grid, (TNW + 2) * 32, sh, st>>>(mo, mr, S, A);                                       \
     }
     // as deep a ring as the 227 KB of shared memory allow
     if (!general) {
