@@ -347,6 +347,40 @@ def run_ours(args):
               "solve_iters": int(st_solve.num_iters), "solve_status": int(st_solve.status)}
     tmp.free()
 
+    # The same grid and step with a horizontally stretched map (StretchedMap, maps/StretchedMap.cpp:9-38, amplitudes
+    # 0.05, 0.03, -0.1): every column has its own tridiagonal matrix, the line relaxation runs vertline_tma_k<GENERAL>
+    # (per-column factorisation recomputed in the kernel).  N = 1 only; a second line of evidence, not the headline.
+    mapped = None
+    if world == 1 and not args.no_mapped:
+        xmin = lo * dXi
+        op_m = sb.PoissonOp(ctx, lo, hi, dXi, blo, bhi, box_rank=ranks, relax_method=sb.RELAX_VERTLINE, map_kind=sb.MAP_STRETCHED,
+                            map_xmin=xmin, map_xmax=xmin + np.array(LDOM), map_ampl=(0.05, 0.03, -0.1))
+        solver_m = sb.MGSolver(op_m, opt)
+        res_m, cor_m = op_m.field(), op_m.field()
+        res_m.upload_ptr(res_h.data_ptr(), tlo, thi)
+
+        def step_m():
+            solver_m.precond_vcycle(cor_m, res_m)
+        for _ in range(2):
+            step_m()
+        m_ms, _, _ = timed(step_m, 3)
+        ctx.profile(True)
+        step_m()
+        ctx.profile(False)
+        mk_ms, mk_n = ctx.profile_get("vertline@0")
+        m_launch = mk_ms / max(mk_n, 1)
+        tmp_m = op_m.field()
+        op_m.residual(tmp_m, cor_m, res_m)
+        mapped = {"map": "StretchedMap ampl (0.05, 0.03, -0.1)", "ms_per_step": m_ms / 3, "value": ncell / (m_ms / 3 * 1e-3), "unit": UNIT,
+                  "line_kernel": "vertline_tma_k<8,4,S,true> (per-column factorisation, no J / Dinv operands)",
+                  "line_launch_ms": m_launch, "line_launches_timed": mk_n,
+                  "line_achieved_gbs": (RELAX_BYTES_PER_CELL_ITER / 2.0) * ncell_tile / (m_launch * 1e-3) / 1e9 if m_launch > 0 else None,
+                  "res_norm_init": op_m.norm(res_m, 2), "res_norm_after_step": op_m.norm(tmp_m, 2)}
+        for f in (tmp_m, res_m, cor_m):
+            f.free()
+        solver_m.free()
+        op_m.free()
+
     # end to end with host buffers
     step_e2e()
     e_ms, e_wall, _ = timed(step_e2e, max(1, min(args.steps, 3)))
@@ -382,6 +416,7 @@ def run_ours(args):
                                           "download of step n-1 overlap the V-cycle of step n (sb_field_*_async)"}},
             "gpu_launches": launches,
             "phases_ms": phases,
+            "mapped": (dict(mapped, line_frac=mapped["line_achieved_gbs"] / peak) if mapped and mapped["line_achieved_gbs"] else mapped),
             "halo": op.halo_mode(),
             "solve": solve_info,
             "wall_ms_per_step": wall_ms / args.steps,
@@ -510,6 +545,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mapped", action="store_true", help="skip the second measurement on the horizontally stretched map (N = 1)")
     ap.add_argument("--no-verify", action="store_true", help="report the decomposition-independent checks without failing on a mismatch")
     ap.add_argument("--write-checks", action="store_true", help="N = 1 only: (re)write tests/golden/bench_s5_checks.json from this run")
     ap.add_argument("--profile-mode", action="store_true",

@@ -164,6 +164,9 @@ struct Coef {
     const double* mzl; const double* mzr;  // [nz]
     const double* loBC; const double* hiBC;  // [py*px] slabs (index = OX+i + sy*(1+j))
     double beta;
+    // J and Dinv as functions of the level only ([nz] each), set when every column of the tile holds the same values
+    // BIT FOR BIT (Op::detectColumnCoefficients): kernels then read the two tables instead of the two arrays
+    const double* tabJ; const double* tabD;
 };
 
 struct BoxList {  // boxes of this rank in tile-local coordinates, on the device
@@ -213,8 +216,10 @@ void vertline_smem_pass(cudaStream_t st, const Lay& L, const Coef& c, const doub
 // scale (per level) or scaleJ / beta (per cell: value / (beta * scaleJ)) may be given, not both
 void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat, double* s0, double* s1, const double* scale,
                  const double* shift = nullptr, const double* scaleJ = nullptr, double beta = 1.0);
+// tabD (may be null): Dinv as a function of the level only, read instead of the array
 void split_precond(cudaStream_t st, const Lay& L, const SLay& S, const double* res, const double* Dinv, const double* scale,
-                   double* c0, double* c1, double* r0, double* r1, const double* scaleJ = nullptr, double beta = 1.0);
+                   double* c0, double* c1, double* r0, double* r1, const double* scaleJ = nullptr, double beta = 1.0,
+                   const double* tabD = nullptr);
 void unsplit_field(cudaStream_t st, const Lay& L, const SLay& S, double* nat, const double* s0, const double* s1);
 void fill_ghosts_split(cudaStream_t st, const SLay& S, double* s0, double* s1, const SideBC bc[3][2], int dim, bool physToo);
 // vertical sides of a split field with z ghosts (S.zg = 1): Robin / periodic, as fill_ghosts_dir_k
@@ -266,8 +271,9 @@ void add_vertical_extrusion(cudaStream_t st, const Lay& L, const Lay& F, double*
 // Reductions.  op: 0 max|x|, 1 sum|x|, 2 sum x^2, 3 sum x*y, 4 sum (J*dv)*x and sum J*dv (2 outputs).
 // One result per box (or 2 for op 4) lands in out[] (device); partial is scratch.
 // mask (may be null): a box in tile-local indices whose cells count as zero (AMRNormLevel).
+// ytab (may be null): y as a function of the level only, read instead of the array y
 void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, const double* x, const double* y,
-                  double dv, double* partial, double* out, const Box3* mask = nullptr);
+                  double dv, double* partial, double* out, const Box3* mask = nullptr, const double* ytab = nullptr);
 int  reduce_partial_len(int nboxes);
 void sum_boxes(cudaStream_t st, const double* in, int nboxes, int ncomp, double* out);
 }  // namespace k

@@ -149,6 +149,9 @@ struct Op {
     double* redOut = nullptr;
     double* shiftBuf = nullptr;  // (sum, vol) of the last removeKernel
     int*    pivotFlag = nullptr;
+    double* colTab = nullptr;    // [J(k) | Dinv(k)] when both are functions of the level only, bit for bit (coefUniform)
+    bool    coefUniform = false;
+    void    detectColumnCoefficients();
     double* lineTab = nullptr;   // [4][nz] tables of the shared-matrix line relaxation (s, f, g, MzR)
     bool    lineFast = false;
     // colour-split line relaxation (sb_line.cu): layout, tables [6][nz], scratch (cor0, cor1, res0, res1)

@@ -257,7 +257,9 @@ __global__ void apply_op_k(Lay L, Coef c, double* __restrict__ out, const double
     if (i >= L.nx || j >= L.ny) return;
     const long long q   = L.idx(i, j, k);
     const double    lap = stencil7(L, c, phi, q, i, j, k);
-    const double    lhs = c.beta * c.J[q] * lap + phi[q] / c.Dinv[q];
+    const double    Jq  = c.tabJ ? c.tabJ[k] : c.J[q];        // the same bits either way (Op::detectColumnCoefficients)
+    const double    Dq  = c.tabD ? c.tabD[k] : c.Dinv[q];
+    const double    lhs = c.beta * Jq * lap + phi[q] / Dq;
     out[q]              = rhs ? rhs[q] - lhs : lhs;
 }
 void apply_op(cudaStream_t st, const Lay& L, const Coef& c, double* lhs, const double* phi)
@@ -1012,7 +1014,8 @@ __device__ __forceinline__ double block_reduce(double v, int op, double* sm)
 // mlo / mhi: a box (tile-local indices, empty if mlo0 > mhi0) whose cells count as zero -- the cells
 // covered by the finer AMR level in PoissonOp::AMRNormLevel (PoissonOp.cpp:1250-1276).
 __global__ void reduce1_k(Lay L, BoxList bl, int op, const double* __restrict__ x, const double* __restrict__ y, double dv,
-                          double* __restrict__ partial, int bxw, int mlo0, int mlo1, int mlo2, int mhi0, int mhi1, int mhi2)
+                          double* __restrict__ partial, int bxw, int mlo0, int mlo1, int mlo2, int mhi0, int mhi1, int mhi2,
+                          const double* __restrict__ ytab)
 {
     __shared__ double sm[32];
     const int bx = blockIdx.y, ch = blockIdx.x;
@@ -1041,7 +1044,7 @@ __global__ void reduce1_k(Lay L, BoxList bl, int op, const double* __restrict__ 
                     const int       jj = lo1 + (int)(r % n1), kk = lo2 + (int)(r / n1);
                     const long long q  = L.idx(lo0 + i, jj, kk);
                     v[u] = x[q];
-                    if (two) w[u] = y[q];
+                    if (two) w[u] = ytab ? ytab[kk] : y[q];
                     if (masked && lo0 + i >= mlo0 && lo0 + i <= mhi0 && jj >= mlo1 && jj <= mhi1 && kk >= mlo2 && kk <= mhi2) v[u] = 0.0;
                 }
             }
@@ -1090,14 +1093,14 @@ void sum_boxes(cudaStream_t st, const double* in, int nboxes, int ncomp, double*
 }
 int  reduce_partial_len(int nboxes) { return 2 * RCH * nboxes; }
 void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, const double* x, const double* y, double dv,
-                  double* partial, double* out, const Box3* mask)
+                  double* partial, double* out, const Box3* mask, const double* ytab)
 {
     int bxw = 32;
     while (bxw < 256 && bxw < boxes.maxnx) bxw <<= 1;
     const Box3 none{{1, 1, 1}, {0, 0, 0}};
     const Box3& m = mask ? *mask : none;
     reduce1_k<<<dim3(RCH, boxes.n), 256, 0, st>>>(L, boxes, op, x, y, dv, partial, bxw, m.lo[0], m.lo[1], m.lo[2], m.hi[0], m.hi[1],
-                                                  m.hi[2]);
+                                                  m.hi[2], ytab);
     LAUNCHED();
     reduce2_k<<<boxes.n, 64, 0, st>>>(op, partial, out);
     LAUNCHED();

@@ -76,7 +76,8 @@ __global__ void split_field_k(Lay L, SLay S, const double* __restrict__ nat, dou
 // res and Dinv.
 __global__ void split_precond_k(Lay L, SLay S, const double* __restrict__ res, const double* __restrict__ Dinv,
                                 const double* __restrict__ scale, double* __restrict__ c0, double* __restrict__ c1,
-                                double* __restrict__ r0, double* __restrict__ r1, const double* __restrict__ scaleJ, double beta)
+                                double* __restrict__ r0, double* __restrict__ r1, const double* __restrict__ scaleJ, double beta,
+                                const double* __restrict__ tabD)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -90,9 +91,10 @@ __global__ void split_precond_k(Lay L, SLay S, const double* __restrict__ res, c
     const bool      two = i + 1 < L.nx;
     if (two) {
         const double2 v = *reinterpret_cast<const double2*>(res + q);
-        const double2 w = *reinterpret_cast<const double2*>(Dinv + q);
-        re = v.x; ro = v.y; de = w.x; dd = w.y;
-    } else { re = res[q]; de = Dinv[q]; }
+        re = v.x; ro = v.y;
+        if (tabD) de = dd = tabD[k];
+        else { const double2 w = *reinterpret_cast<const double2*>(Dinv + q); de = w.x; dd = w.y; }
+    } else { re = res[q]; de = tabD ? tabD[k] : Dinv[q]; }
     const int       ce = S.colour(i, j);
     const long long d  = S.idx(i, j, k);
     (ce ? c1 : c0)[d] = re * de;
@@ -125,11 +127,11 @@ void split_field(cudaStream_t st, const Lay& L, const SLay& S, const double* nat
     note_launch();
 }
 void split_precond(cudaStream_t st, const Lay& L, const SLay& S, const double* res, const double* Dinv, const double* scale,
-                   double* c0, double* c1, double* r0, double* r1, const double* scaleJ, double beta)
+                   double* c0, double* c1, double* r0, double* r1, const double* scaleJ, double beta, const double* tabD)
 {
     const dim3 b(64, 4, 1);
     const dim3 g(((L.nx + 1) / 2 + 63) / 64, (L.ny + 3) / 4, L.nz);
-    split_precond_k<<<g, b, 0, st>>>(L, S, res, Dinv, scale, c0, c1, r0, r1, scaleJ, beta);
+    split_precond_k<<<g, b, 0, st>>>(L, S, res, Dinv, scale, c0, c1, r0, r1, scaleJ, beta, tabD);
     note_launch();
 }
 void unsplit_field(cudaStream_t st, const Lay& L, const SLay& S, double* nat, const double* s0, const double* s1)
@@ -246,8 +248,10 @@ __global__ void gsrb_split_k(SLay S, Coef c, double* __restrict__ p0, double* __
     const double mzl = c.mzl[k], mzr = c.mzr[k], myl = c.myl[j], myr = c.myr[j], beta = c.beta;
     const double2 dn = *reinterpret_cast<const double2*>(own + q - S.sz), up = *reinterpret_cast<const double2*>(own + q + S.sz);
     const double2 so = *reinterpret_cast<const double2*>(oth + q - S.sy), no = *reinterpret_cast<const double2*>(oth + q + S.sy);
-    const double2 rv = *reinterpret_cast<const double2*>(rr + q), Jv = *reinterpret_cast<const double2*>(JJ + q),
-                  Dv = *reinterpret_cast<const double2*>(DD + q);
+    const double2 rv = *reinterpret_cast<const double2*>(rr + q);
+    // J / Dinv of the level from the [nz] tables when they are functions of the level only (the same bits, Coef::tabJ)
+    const double2 Jv = c.tabJ ? make_double2(c.tabJ[k], c.tabJ[k]) : *reinterpret_cast<const double2*>(JJ + q);
+    const double2 Dv = c.tabD ? make_double2(c.tabD[k], c.tabD[k]) : *reinterpret_cast<const double2*>(DD + q);
     // horizontal neighbours in the other array: elements m + i0 - 1, m + i0, m + i0 + 1
     double w0, e0, e1;
     if (i0) { const double2 t = *reinterpret_cast<const double2*>(oth + q); w0 = t.x; e0 = t.y; e1 = oth[q + 2]; }

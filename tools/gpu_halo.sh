@@ -28,5 +28,6 @@ for v in ${VARIANTS:-fused post nccl}; do
         post)  run_bench post SB_HALO_FUSED=0 ;;
         fork)  run_bench fork SB_HALO_FUSED=0 SB_HALO_FORK=1 ;;
         nccl)  run_bench nccl SB_PEER_HALO=0 ;;
+        agg*)  run_bench $v SB_AGG_CELLS=${v#agg} ;;   # agglomeration threshold in cells, e.g. agg1048576
     esac
 done
