@@ -325,10 +325,13 @@ void pack_faces_split(cudaStream_t st, const SLay& S, double* s0, double* s1, do
 //  * vertline_split_k (SB_LINE_VARIANT=1): the earlier three-phase form (local forward, local
 //    backward, correction), tab = [6][N]: s, a, P, g, c, Q.
 // ------------------------------------------------------------------------------------------
-// Launch shape (development knob SB_LINE_VARIANT, read once).
+// Launch shape.  The shipped library has one: 8 warps, 4 levels per load batch, 2 CTAs per SM (measured best on B200,
+// profiles/r1_v4_summary.md).  Building with -DSB_DIAG_KERNELS adds the development knob SB_LINE_VARIANT (read once) and
+// the diagnostic / rejected kernels it selects (vertline_split_k, vertline_pers_k, vertline_probe_k).
 struct LineVariant { int nw, u, minb, fused, pers; };
 static LineVariant line_variant()
 {
+#ifdef SB_DIAG_KERNELS
     static int v = -1;
     if (v < 0) { const char* e = getenv("SB_LINE_VARIANT"); v = e ? atoi(e) : 0; }
     switch (v) {
@@ -339,8 +342,10 @@ static LineVariant line_variant()
         case 5: return {8, 4, 1, 1, 0};
         case 7: return {8, 4, 2, 2, 0};
         case 8: return {8, 4, 2, 1, 1};   // persistent CTAs with cross-tile prefetch: measured slower (0.776 ms, see header of vertline_pers_k)
-        default: return {8, 4, 2, 1, 0};  // measured best on B200 (profiles/r1_v4_summary.md)
+        default: break;
     }
+#endif
+    return {8, 4, 2, 1, 0};
 }
 int  vertline_split_chunk(int nz) { const int nw = line_variant().nw; return (nz + nw - 1) / nw; }
 int  vertline_split_nw() { return line_variant().nw; }
@@ -501,6 +506,7 @@ __global__ void __launch_bounds__(NW * 32, MINB)
     }
 }
 
+#ifdef SB_DIAG_KERNELS
 // Persistent form of vertline_fused_k for aligned shapes (nz = NW * CL, CL a multiple of 2 U): a
 // CTA walks over tiles (32 columns of one row) with stride gridDim.x.  The tables are staged once per
 // CTA instead of once per tile, and the first 2 U levels of the NEXT tile are requested before the
@@ -791,6 +797,8 @@ __global__ void __launch_bounds__(NW * 32, MINB)
     }
 }
 
+#endif  // SB_DIAG_KERNELS
+
 void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const double* tab, double* own, const double* oth,
                          const double* rhs, int pass, int region, int nbMask)
 {
@@ -809,6 +817,7 @@ void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const do
     }
     if ((long long)S.sz * S.nz >= (1LL << 31)) SB_FAIL("colour-split field too large for 32-bit element offsets");
     const bool al = S.nz == v.nw * CL && CL % (2 * v.u) == 0;
+#ifdef SB_DIAG_KERNELS
     if (v.fused == 1 && v.pers && al && v.nw == 8 && v.u == 4) {
         static int    nsm = 0;
         static size_t configured = 0;
@@ -834,7 +843,9 @@ void vertline_split_pass(cudaStream_t st, const SLay& S, const Coef& c, const do
     else if (v.nw == 16 && v.u == 4 && al) SB_LAUNCH((vertline_fused_k<16, 4, 1, true>))
     else if (v.nw == 16 && v.u == 4) SB_LAUNCH((vertline_fused_k<16, 4, 1, false>))
     else if (v.nw == 8 && v.u == 4 && v.minb == 1 && al) SB_LAUNCH((vertline_fused_k<8, 4, 1, true>))
-    else if (al && v.nw == 8) SB_LAUNCH((vertline_fused_k<8, 4, 2, true>))
+    else
+#endif
+    if (al && v.nw == 8) SB_LAUNCH((vertline_fused_k<8, 4, 2, true>))
     else if (v.nw == 8) SB_LAUNCH((vertline_fused_k<8, 4, 2, false>))
     else SB_FAIL("SB_LINE_VARIANT: no kernel instance for this shape");
 #undef SB_LAUNCH
