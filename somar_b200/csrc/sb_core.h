@@ -275,6 +275,27 @@ void add_vertical_extrusion(cudaStream_t st, const Lay& L, const Lay& F, double*
 void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, const double* x, const double* y,
                   double dv, double* partial, double* out, const Box3* mask = nullptr, const double* ytab = nullptr);
 int  reduce_partial_len(int nboxes);
+
+// The deepest depth of a V-cycle in one launch (sb_tiny.cu): relax(numSmoothBottom) + BiCGStabSolver::solve on a grid of at
+// most 4096 cells owned by one rank.
+struct TinyBottomArgs {
+    Lay               L;
+    Coef              c;
+    SideBC            side[3][2];
+    int               dim, relaxMethod;
+    const int*        boxLo;   // [nboxes][3], tile-local
+    const int*        boxHi;
+    int               nboxes;
+    sb_bottom_options opt;
+    int               numSmoothBottom, corIsPreCond, useBottomSolver;
+    double*           phi;
+    const double*     rhs;
+    double*           w[8];    // r, r_tilde, e, p, p_tilde, s_tilde, t, v
+    double*           out;     // status, initResNorm, finalResNorm, iterations, restarts (may be null)
+    int*              pivotFlag;
+};
+bool tiny_bottom_fits(const Lay& L, int nboxes);
+void tiny_bottom(cudaStream_t st, const TinyBottomArgs& args);
 void sum_boxes(cudaStream_t st, const double* in, int nboxes, int ncomp, double* out);
 }  // namespace k
 

@@ -330,6 +330,7 @@ struct MGSolver {
     // corIsPreCond: cor still has to be set to preCond(res) -- the caller skipped that pass so that
     // the first relaxation can fuse it
     void vCycle_residualEq(double* cor, const double* res, int depth, bool corIsPreCond = false);
+    bool tinyBottom(Op& op, double* cor, const double* res, bool corIsPreCond);  // sb_tiny.cu; false: not applicable
     void fmg_residualEq(double* cor, const double* res, int depth);
     void modifyOptionsExceptMaxDepth(const sb_mg_options& o);
 };

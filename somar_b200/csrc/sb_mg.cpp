@@ -458,8 +458,10 @@ void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth, 
     Op& op = *ops[depth];
     if (depth == opt.maxDepth) {
         pc->phaseBegin(&e0);
-        op.relax(a_cor, a_res, opt.numSmoothBottom, false, pre);
-        if (bottom) bottom->solve(a_cor, a_res, true, false);
+        if (!tinyBottom(op, a_cor, a_res, corIsPreCond)) {
+            op.relax(a_cor, a_res, opt.numSmoothBottom, false, pre);
+            if (bottom) bottom->solve(a_cor, a_res, true, false);
+        }
         pc->phaseEnd("bottom", depth, e0);
         return;
     }
@@ -484,6 +486,40 @@ void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth, 
     op.relax(a_cor, a_res, opt.numSmoothUp, /*resUnchanged since the down-relax*/ opt.numSmoothDown >= 2,
              shiftPending ? Op::RELAX_PRE_SHIFT : Op::RELAX_PRE_NONE);
     pc->phaseEnd("relax_up", depth, e0);
+}
+
+// The bottom smooths and the bottom solve as one single-CTA kernel (sb_tiny.cu) when the deepest grid is tiny and wholly on
+// this rank: the host-driven path costs ~40 launches and six host round trips per BiCGStab iteration.  SB_TINY_BOTTOM=0
+// keeps the host-driven solver.
+bool MGSolver::tinyBottom(Op& op, double* a_cor, const double* a_res, bool corIsPreCond)
+{
+    static const bool allowed = [] { const char* e = getenv("SB_TINY_BOTTOM"); return !(e && std::string(e) == "0"); }();
+    if (!allowed || !bottom || op.ctx->nranks != 1 || op.ctx->isProfiling()) return false;
+    if (op.relaxMethod != SB_RELAX_VERTLINE && op.relaxMethod != SB_RELAX_GSRB) return false;
+    if (!k::tiny_bottom_fits(op.lay, op.nlocal())) return false;
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s) {
+            const int kind = op.side[d][s].kind;
+            if (!(kind < 0 || sideIsBC(kind) || kind == SIDE_PERIODIC_SELF)) return false;
+        }
+    k::TinyBottomArgs a;
+    a.L = op.lay; a.c = op.coef();
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s) a.side[d][s] = op.side[d][s];
+    a.dim = op.dim; a.relaxMethod = op.relaxMethod;
+    const BoxList bl = op.boxlist();
+    a.boxLo = bl.lo; a.boxHi = bl.hi; a.nboxes = bl.n;
+    a.opt = bottom->opt;
+    a.numSmoothBottom = opt.numSmoothBottom; a.corIsPreCond = corIsPreCond ? 1 : 0; a.useBottomSolver = 1;
+    a.phi = a_cor; a.rhs = a_res;
+    BiCGStabSolver& b = *bottom;
+    double* w[8] = {b.r, b.r_tilde, b.e, b.p, b.p_tilde, b.s_tilde, b.t, b.v};
+    for (int i = 0; i < 8; ++i) a.w[i] = w[i];
+    a.out = op.redOut;  // 2 * nlocal doubles >= 5 whenever the op has three boxes; else no status record
+    if (2 * op.nlocal() < 5) a.out = nullptr;
+    a.pivotFlag = op.pivotFlag;
+    k::tiny_bottom(op.st(), a);
+    return true;
 }
 
 // MGSolver<T>::fmg_residualEq (MGSolverI.H:758-820)
