@@ -323,8 +323,8 @@ def run_ours(args):
     ctx.profile(0)
     phases = {}
     for d in range(len(sched)):
-        for key in ("relax_down", "residual_restrict", "prolong", "relax_up", "bottom", "agglomerated",
-                    "agg.relax_down", "agg.residual_restrict", "agg.prolong", "agg.relax_up", "agg.bottom"):
+        for key in ("relax_down", "residual_restrict", "prolong", "relax_up", "bottom", "tail", "agglomerated",
+                    "agg.relax_down", "agg.residual_restrict", "agg.prolong", "agg.relax_up", "agg.bottom", "agg.tail"):
             p_ms, p_n = ctx.profile_get(f"{key}@{d}")
             if p_n:
                 phases[f"{key}@{d}"] = round(p_ms, 4)

@@ -276,26 +276,36 @@ void reduce_boxes(cudaStream_t st, const Lay& L, const BoxList& boxes, int op, c
                   double dv, double* partial, double* out, const Box3* mask = nullptr, const double* ytab = nullptr);
 int  reduce_partial_len(int nboxes);
 
-// The deepest depth of a V-cycle in one launch (sb_tiny.cu): relax(numSmoothBottom) + BiCGStabSolver::solve on a grid of at
-// most 4096 cells owned by one rank.
-struct TinyBottomArgs {
-    Lay               L;
-    Coef              c;
-    SideBC            side[3][2];
-    int               dim, relaxMethod;
-    const int*        boxLo;   // [nboxes][3], tile-local
-    const int*        boxHi;
-    int               nboxes;
-    sb_bottom_options opt;
-    int               numSmoothBottom, corIsPreCond, useBottomSolver;
-    double*           phi;
-    const double*     rhs;
-    double*           w[8];    // r, r_tilde, e, p, p_tilde, s_tilde, t, v
-    double*           out;     // status, initResNorm, finalResNorm, iterations, restarts (may be null)
-    int*              pivotFlag;
+// The tail of a V-cycle in one launch (sb_tiny.cu): vCycle_residualEq over the deepest depths (as many as fit a shared-memory
+// arena together, owned by one rank), bottom smooths and BiCGStab solve included.
+struct TinyLevel {
+    Lay           L;
+    Coef          c;
+    SideBC        side[3][2];
+    int           dim, relaxMethod;
+    const int*    boxLo;   // [nboxes][3], tile-local
+    const int*    boxHi;
+    int           nboxes;
+    int           hasNullSpace;
+    double        dv;      // cell volume in index space (removeKernel's weights are J dv)
+    int           ref[3];  // refinement ratio to the next (coarser) level of the tail
+    double *      cor, *res, *tmp;
+    int*          pivotFlag;
+    const double* lineTab;  // [4][nz] factorisation tables of the shared-matrix line relaxation (Op::lineTab), or null
 };
-bool tiny_bottom_fits(const Lay& L, int nboxes);
-void tiny_bottom(cudaStream_t st, const TinyBottomArgs& args);
+constexpr int TINY_MAXLEV = 4;
+struct TinyTailArgs {
+    int               nlev;            // lev[nlev - 1] is the bottom of the hierarchy
+    TinyLevel         lev[TINY_MAXLEV];
+    sb_bottom_options opt;
+    int               numSmoothDown, numSmoothUp, numSmoothBottom, prolongOrder, corIsPreCond;
+    double*           w[8];            // BiCGStab work vectors on the bottom level: r, r_tilde, e, p, p_tilde, s_tilde, t, v
+    double*           out;             // status, initResNorm, finalResNorm, iterations, restarts of the bottom solve (may be null)
+};
+bool   tiny_level_fits(const Lay& L, int nboxes);
+size_t tiny_level_bytes(const Lay& L, int nboxes, bool nonBottom, bool bottom);  // shared memory its staged copy takes
+size_t tiny_arena_limit();
+void   tiny_tail(cudaStream_t st, const TinyTailArgs& args, size_t arenaBytes);
 void sum_boxes(cudaStream_t st, const double* in, int nboxes, int ncomp, double* out);
 }  // namespace k
 

@@ -330,7 +330,11 @@ struct MGSolver {
     // corIsPreCond: cor still has to be set to preCond(res) -- the caller skipped that pass so that
     // the first relaxation can fuse it
     void vCycle_residualEq(double* cor, const double* res, int depth, bool corIsPreCond = false);
-    bool tinyBottom(Op& op, double* cor, const double* res, bool corIsPreCond);  // sb_tiny.cu; false: not applicable
+    // sb_tiny.cu: depths >= tinyTailStart() run as one single-CTA kernel; false: not applicable here
+    int  tailStart = -2;
+    double* tailOut = nullptr;  // device record of the last tail launch (bottom-solve status, time split)
+    int  tinyTailStart();
+    bool tinyTail(int depth, double* cor, const double* res, bool corIsPreCond);
     void fmg_residualEq(double* cor, const double* res, int depth);
     void modifyOptionsExceptMaxDepth(const sb_mg_options& o);
 };

@@ -4,6 +4,7 @@
 // (Elliptic/MGCoarseningStrategy.cpp) and LevelHybridSolver (Elliptic/LevelHybridSolver.cpp).
 // Fields live on the device; only scalars (norms, dot products) come back to the host, exactly
 // where the reference performs an MPI_Allreduce.
+#include <cstdio>
 #include <algorithm>
 #include <cmath>
 #include <limits>
@@ -241,6 +242,7 @@ SolverStatus BiCGStabSolver::solve(double* phi, const double* rhs, bool homog, b
 void MGSolver::define(Op& top, const sb_mg_options& a_opt, std::vector<IV> sched, bool useBottomSolver)
 {
     opt = a_opt;
+    tailStart = -2;
     if (sched.empty()) {
         if (top.relaxMethod == SB_RELAX_VERTLINE) refSchedule = createMGRefSchedule(top, opt.maxDepth, true, true);
         else refSchedule = createMGRefSchedule(top, opt.maxDepth, false, false);
@@ -358,6 +360,7 @@ void MGSolver::checkPivotAll()
 }
 MGSolver::~MGSolver()
 {
+    if (tailOut) cudaFree(tailOut);
     for (auto* q : tmpRes) if (q) cudaFree(q);
     for (auto* q : cor) if (q) cudaFree(q);
     for (auto* q : res) if (q) cudaFree(q);
@@ -376,7 +379,8 @@ void MGSolver::modifyOptionsExceptMaxDepth(const sb_mg_options& o)
     opt           = o;
     opt.maxDepth  = old;
     if (bottom) bottom->opt = o.bottom;
-    if (agg) { sb_mg_options a = o; a.maxDepth = agg->opt.maxDepth; agg->opt = a; agg->bottom->opt = o.bottom; }
+    tailStart = -2;  // numCycles / prolongOrder decide whether the single-kernel tail applies
+    if (agg) { sb_mg_options a = o; a.maxDepth = agg->opt.maxDepth; agg->opt = a; agg->bottom->opt = o.bottom; agg->tailStart = -2; }
 }
 
 SolverStatus MGSolver::solve(double* phi, const double* rhs, bool homog, bool setPhiToZero, double metric)
@@ -456,12 +460,14 @@ void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth, 
         return;
     }
     Op& op = *ops[depth];
+    pc->phaseBegin(&e0);
+    if (tinyTail(depth, a_cor, a_res, corIsPreCond)) {
+        pc->phaseEnd("tail", depth, e0);
+        return;
+    }
     if (depth == opt.maxDepth) {
-        pc->phaseBegin(&e0);
-        if (!tinyBottom(op, a_cor, a_res, corIsPreCond)) {
-            op.relax(a_cor, a_res, opt.numSmoothBottom, false, pre);
-            if (bottom) bottom->solve(a_cor, a_res, true, false);
-        }
+        op.relax(a_cor, a_res, opt.numSmoothBottom, false, pre);
+        if (bottom) bottom->solve(a_cor, a_res, true, false);
         pc->phaseEnd("bottom", depth, e0);
         return;
     }
@@ -469,8 +475,7 @@ void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth, 
     double* crseCor = cor[depth + 1];
     double* crseRes = res[depth + 1];
     double* tmp     = tmpRes[depth];
-    pc->phaseBegin(&e0);
-    op.relax(a_cor, a_res, opt.numSmoothDown, false, pre);
+    op.relax(a_cor, a_res, opt.numSmoothDown, false, pre);   // (phase opened above)
     pc->phaseEnd("relax_down", depth, e0);
     pc->phaseBegin(&e0);
     op.residual(tmp, a_cor, a_res, true);
@@ -488,37 +493,86 @@ void MGSolver::vCycle_residualEq(double* a_cor, const double* a_res, int depth, 
     pc->phaseEnd("relax_up", depth, e0);
 }
 
-// The bottom smooths and the bottom solve as one single-CTA kernel (sb_tiny.cu) when the deepest grid is tiny and wholly on
-// this rank: the host-driven path costs ~40 launches and six host round trips per BiCGStab iteration.  SB_TINY_BOTTOM=0
-// keeps the host-driven solver.
-bool MGSolver::tinyBottom(Op& op, double* a_cor, const double* a_res, bool corIsPreCond)
+// The deepest depths of the V-cycle -- as many as fit a shared-memory arena together, wholly on this rank -- as ONE single-CTA
+// kernel (sb_tiny.cu: tiny_tail_k): relaxations, residual, restriction, prolongation, null-space removal, bottom smooths and the
+// whole BiCGStab solve, with the solver's decisions made on the device.  The host-driven path costs ~50 launches per
+// relaxation on such a depth and six host round trips per BiCGStab iteration.  SB_TINY_TAIL=0 keeps the host-driven path.
+int MGSolver::tinyTailStart()
 {
-    static const bool allowed = [] { const char* e = getenv("SB_TINY_BOTTOM"); return !(e && std::string(e) == "0"); }();
-    if (!allowed || !bottom || op.ctx->nranks != 1 || op.ctx->isProfiling()) return false;
-    if (op.relaxMethod != SB_RELAX_VERTLINE && op.relaxMethod != SB_RELAX_GSRB) return false;
-    if (!k::tiny_bottom_fits(op.lay, op.nlocal())) return false;
-    for (int d = 0; d < 3; ++d)
-        for (int s = 0; s < 2; ++s) {
-            const int kind = op.side[d][s].kind;
-            if (!(kind < 0 || sideIsBC(kind) || kind == SIDE_PERIODIC_SELF)) return false;
-        }
-    k::TinyBottomArgs a;
-    a.L = op.lay; a.c = op.coef();
-    for (int d = 0; d < 3; ++d)
-        for (int s = 0; s < 2; ++s) a.side[d][s] = op.side[d][s];
-    a.dim = op.dim; a.relaxMethod = op.relaxMethod;
-    const BoxList bl = op.boxlist();
-    a.boxLo = bl.lo; a.boxHi = bl.hi; a.nboxes = bl.n;
+    if (tailStart != -2) return tailStart;
+    tailStart = -1;
+    static const bool allowed = [] { const char* e = getenv("SB_TINY_TAIL"); return !(e && std::string(e) == "0"); }();
+    if (!allowed || !bottom || aggDepth >= 0 || std::abs(opt.numCycles) != 1 || opt.prolongOrder > 1) return tailStart;
+    auto ok = [&](const Op& op) {
+        if (op.ctx->nranks != 1) return false;
+        if (op.relaxMethod != SB_RELAX_VERTLINE && op.relaxMethod != SB_RELAX_GSRB) return false;
+        if (!k::tiny_level_fits(op.lay, op.nlocal())) return false;
+        for (int d = 0; d < 3; ++d)
+            for (int s = 0; s < 2; ++s) {
+                const int kind = op.side[d][s].kind;
+                if (!(kind < 0 || sideIsBC(kind) || kind == SIDE_PERIODIC_SELF)) return false;
+            }
+        return true;
+    };
+    static const long long maxCells = [] { const char* e = getenv("SB_TINY_CELLS"); return e ? atoll(e) : (1LL << 40); }();
+    auto cells = [](const Op& op) { return (long long)op.lay.nx * op.lay.ny * op.lay.nz; };
+    int d = opt.maxDepth;
+    if (d < 0 || d >= (int)ops.size() || !ok(*ops[d]) || cells(*ops[d]) > maxCells) return tailStart;
+    size_t bytes = k::tiny_level_bytes(ops[d]->lay, ops[d]->nlocal(), false, true);
+    if (bytes > k::tiny_arena_limit()) return tailStart;
+    // grow upwards while the staged copies of all levels fit the arena together
+    while (d > 0 && opt.maxDepth - (d - 1) + 1 <= k::TINY_MAXLEV && ok(*ops[d - 1]) && cells(*ops[d - 1]) <= maxCells) {
+        const size_t more = k::tiny_level_bytes(ops[d - 1]->lay, ops[d - 1]->nlocal(), true, false);
+        if (bytes + more > k::tiny_arena_limit()) break;
+        bytes += more;
+        --d;
+    }
+    tailStart = d;
+    return tailStart;
+}
+bool MGSolver::tinyTail(int depth, double* a_cor, const double* a_res, bool corIsPreCond)
+{
+    const int start = tinyTailStart();
+    if (start < 0 || depth < start || ops[depth]->ctx->isProfiling()) return false;
+    k::TinyTailArgs a;
+    a.nlev = opt.maxDepth - depth + 1;
+    for (int l = 0; l < a.nlev; ++l) {
+        Op&           op = *ops[depth + l];
+        k::TinyLevel& V  = a.lev[l];
+        V.L = op.lay; V.c = op.coef();
+        for (int d = 0; d < 3; ++d)
+            for (int s = 0; s < 2; ++s) V.side[d][s] = op.side[d][s];
+        V.dim = op.dim; V.relaxMethod = op.relaxMethod;
+        const BoxList bl = op.boxlist();
+        V.boxLo = bl.lo; V.boxHi = bl.hi; V.nboxes = bl.n;
+        V.hasNullSpace = op.hasNullSpace ? 1 : 0;
+        V.dv = op.dim == 2 ? op.dXi[0] * op.dXi[2] : op.dXi[0] * op.dXi[1] * op.dXi[2];
+        for (int d = 0; d < 3; ++d) V.ref[d] = l + 1 < a.nlev ? op.domain.size(d) / ops[depth + l + 1]->domain.size(d) : 1;
+        V.cor = l == 0 ? a_cor : cor[depth + l];
+        V.res = l == 0 ? const_cast<double*>(a_res) : res[depth + l];
+        V.tmp = l + 1 < a.nlev ? tmpRes[depth + l] : nullptr;
+        V.pivotFlag = op.pivotFlag;
+        V.lineTab   = op.relaxMethod == SB_RELAX_VERTLINE && op.lineFast ? op.lineTab : nullptr;
+    }
     a.opt = bottom->opt;
-    a.numSmoothBottom = opt.numSmoothBottom; a.corIsPreCond = corIsPreCond ? 1 : 0; a.useBottomSolver = 1;
-    a.phi = a_cor; a.rhs = a_res;
+    a.numSmoothDown = opt.numSmoothDown; a.numSmoothUp = opt.numSmoothUp; a.numSmoothBottom = opt.numSmoothBottom;
+    a.prolongOrder = opt.prolongOrder; a.corIsPreCond = corIsPreCond ? 1 : 0;
     BiCGStabSolver& b = *bottom;
     double* w[8] = {b.r, b.r_tilde, b.e, b.p, b.p_tilde, b.s_tilde, b.t, b.v};
     for (int i = 0; i < 8; ++i) a.w[i] = w[i];
-    a.out = op.redOut;  // 2 * nlocal doubles >= 5 whenever the op has three boxes; else no status record
-    if (2 * op.nlocal() < 5) a.out = nullptr;
-    a.pivotFlag = op.pivotFlag;
-    k::tiny_bottom(op.st(), a);
+    if (!tailOut) SB_CUDA(cudaMalloc((void**)&tailOut, 16 * sizeof(double)));
+    a.out = tailOut;
+    size_t bytes = 0;
+    for (int l = 0; l < a.nlev; ++l) bytes += k::tiny_level_bytes(ops[depth + l]->lay, ops[depth + l]->nlocal(), l + 1 < a.nlev, l + 1 == a.nlev);
+    k::tiny_tail(ops[depth]->st(), a, bytes);
+    static const bool dbg = [] { const char* e = getenv("SB_TINY_DEBUG"); return e && std::string(e) == "1"; }();
+    if (dbg) {
+        double h[10];
+        SB_CUDA(cudaMemcpyAsync(h, tailOut, sizeof(h), cudaMemcpyDeviceToHost, ops[depth]->st()));
+        ops[depth]->ctx->sync();
+        fprintf(stderr, "tiny_tail depth %d levels %d: bottom status %d iters %d restarts %d res %.3e -> %.3e | us: stage %.1f down %.1f smooth %.1f bicgstab %.1f up %.1f\n",
+                depth, a.nlev, (int)h[0], (int)h[3], (int)h[4], h[1], h[2], h[5] * 1e-3, h[6] * 1e-3, h[7] * 1e-3, h[8] * 1e-3, h[9] * 1e-3);
+    }
     return true;
 }
 
