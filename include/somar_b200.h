@@ -142,6 +142,10 @@ int sb_plan_tile(const sb_level_desc* desc, int rank, int nranks, int tile_lo[3]
                  int side_neighbor[6], int* num_local_boxes);
 /* The MG refinement schedule MGSolver::define would create (MGCoarseningStrategy.cpp:62-310):
  * HorizCoarseningStrategy(doVertCoarsening) when relax_method is VERTLINE, else Semicoarsening. */
+/* The order in which one colour pass of the line relaxation walks the tiles (32 columns of one colour x one grid row) of an
+ * nx x ny tile when it delivers its face layers to neighbouring ranks itself (sb_line_tma.cu): the tiles on the exchanged
+ * sides nb_mask (bit 2 * dir + side) first.  order[3 u] = (bx, j, touched sides) of slot u.  Host only. */
+int sb_plan_line_tile_order(int nx, int ny, int nb_mask, int* order, int capacity, int* num_tiles);
 int sb_plan_schedule(const sb_level_desc* desc, int max_depth, int* schedule, int capacity, int* num_sched);
 
 /* Stencil records of the quadratic coarse-fine ghost interpolation (MappedQuadCFStencil::define / buildStencils,

@@ -115,6 +115,7 @@ PROTOTYPES = {
     "sb_op_destroy": (C.c_int, [P]),
     "sb_op_has_null_space": (C.c_int, [P, IP]),
     "sb_op_halo_mode": (C.c_int, [P, IP]),
+    "sb_plan_line_tile_order": (C.c_int, [C.c_int, C.c_int, C.c_int, IP, C.c_int, IP]),
     "sb_op_new_mg_operator": (C.c_int, [P, IP, PP]),
     "sb_op_get_info": (C.c_int, [P, IP, IP, DP, IP]),
     "sb_op_get_coefficient": (C.c_int, [P, C.c_int, DP, C.c_longlong]),

@@ -104,6 +104,13 @@ int sb_context_profile_get(sb_context* ctx, const char* key, double* total_ms, l
 }
 
 // Host-only helpers (no CUDA device needed): decomposition plan and MG schedule.
+int sb_plan_line_tile_order(int nx, int ny, int nb_mask, int* order, int capacity, int* num_tiles)
+{
+    SB_TRY REQ(order); REQ(num_tiles);
+    if (nx < 2 || ny < 2) SB_FAIL("a tile of at least 2 x 2 columns");
+    *num_tiles = k::line_tma_tile_order(nx, ny, nb_mask, order, capacity);
+    SB_END
+}
 int sb_plan_tile(const sb_level_desc* d, int rank, int nranks, int tile_lo[3], int tile_hi[3], int side_kind[6],
                  int side_neighbor[6], int* num_local_boxes)
 {

@@ -95,7 +95,7 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsign
 }
 // Schedule slot u -> tile (bx, j).  Plain order without a fused exchange; otherwise the tiles touching an exchanged side
 // first: row 0 (nA), row ny-1 (nB), column 0 (nC), column nbx-1 (nD), then the interior rectangle.
-__device__ __forceinline__ void tile_of(const LineTmaArgs& A, int ny, int u, int& bx, int& j)
+__host__ __device__ __forceinline__ void tile_of(const LineTmaArgs& A, int ny, int u, int& bx, int& j)
 {
     if (!A.halo) { bx = u % A.nbx; j = u / A.nbx; return; }
     if (u < A.nA) { bx = u; j = 0; return; }
@@ -110,7 +110,7 @@ __device__ __forceinline__ void tile_of(const LineTmaArgs& A, int ny, int u, int
     j  = A.jlo + u / A.nbxi;
 }
 // sides of the tile an exchanged face layer lies on: bit 2 * dir + side
-__device__ __forceinline__ int tile_touch(const LineTmaArgs& A, int ny, int bx, int j)
+__host__ __device__ __forceinline__ int tile_touch(const LineTmaArgs& A, int ny, int bx, int j)
 {
     if (!A.halo) return 0;
     return (((A.nbMask & 1) && bx == 0) ? 1 : 0) | (((A.nbMask & 2) && bx == A.nbx - 1) ? 2 : 0) | (((A.nbMask & 4) && j == 0) ? 4 : 0) |
@@ -509,12 +509,9 @@ void vertline_tma_make_maps(const SLay& S, const double* oth, const double* rhs,
     vertline_tma_make_map(S, rhs, 32, 1, mapRhs);
 }
 
-void vertline_tma_pass(cudaStream_t st, const SLay& S, const LineTmaMap& mapOth, const LineTmaMap& mapRhs, const LineTmaArgs& args,
-                       bool general)
+// Tile count and, for the fused exchange, the edge-first schedule of a pass (see tile_of)
+static void line_tma_schedule(const SLay& S, LineTmaArgs& A)
 {
-    static int nsm = 0;
-    if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
-    LineTmaArgs A = args;
     A.nbx    = ((S.nx + 1) / 2 + 31) / 32;
     A.ntiles = A.nbx * S.ny;
     A.nA = A.nB = A.nC = A.nD = A.jlo = A.bxlo = 0;
@@ -533,6 +530,32 @@ void vertline_tma_pass(cudaStream_t st, const SLay& S, const LineTmaMap& mapOth,
         A.nbxi = bxhi - A.bxlo + 1 > 0 ? bxhi - A.bxlo + 1 : 0;
         if (A.nA + A.nB + A.nC + A.nD + A.nbxi * nrows != A.ntiles) SB_FAIL("vertline_tma: tile schedule does not cover the tile");
     }
+}
+// Host-side view of that schedule (sb_plan_line_tile_order): (bx, j, touched sides) of every slot, in order
+int line_tma_tile_order(int nx, int ny, int nbMask, int* order, int capacity)
+{
+    SLay S{};
+    S.nx = nx; S.ny = ny;
+    LineTmaArgs A{};
+    A.nbMask = nbMask; A.region = 0;
+    static const HaloDev dummy{};
+    A.halo = nbMask ? &dummy : nullptr;
+    line_tma_schedule(S, A);
+    for (int u = 0; u < A.ntiles && u < capacity; ++u) {
+        int bx, j;
+        tile_of(A, ny, u, bx, j);
+        order[3 * u] = bx; order[3 * u + 1] = j; order[3 * u + 2] = tile_touch(A, ny, bx, j);
+    }
+    return A.ntiles;
+}
+
+void vertline_tma_pass(cudaStream_t st, const SLay& S, const LineTmaMap& mapOth, const LineTmaMap& mapRhs, const LineTmaArgs& args,
+                       bool general)
+{
+    static int nsm = 0;
+    if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+    LineTmaArgs A = args;
+    line_tma_schedule(S, A);
     const int grid = A.ntiles < nsm ? A.ntiles : nsm;
     const CUtensorMap& mo = reinterpret_cast<const CUtensorMap&>(mapOth);
     const CUtensorMap& mr = reinterpret_cast<const CUtensorMap&>(mapRhs);

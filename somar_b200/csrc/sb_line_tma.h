@@ -27,6 +27,9 @@ struct LineTmaArgs {
 
 namespace k {
 int  vertline_tma_nw();                      // chunks per column (consumer warps)
+// the order in which a pass with the fused exchange walks its tiles: order[3 u] = (bx, j, touched sides) of slot u; returns the
+// number of tiles (host only; what sb_plan_line_tile_order exports for the CPU tests)
+int  line_tma_tile_order(int nx, int ny, int nbMask, int* order, int capacity);
 bool vertline_tma_fits(int nz, bool general);
 void vertline_tma_make_maps(const SLay& S, const double* oth, const double* rhs, LineTmaMap* mapOth, LineTmaMap* mapRhs);
 void vertline_tma_pass(cudaStream_t st, const SLay& S, const LineTmaMap& mapOth, const LineTmaMap& mapRhs, const LineTmaArgs& args,

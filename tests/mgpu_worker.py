@@ -77,7 +77,7 @@ def main():
         np.save(f"{out_path}.phi.npy", full)
         with open(out_path, "w") as f:
             json.dump({"status": st.status, "norms": st.norms, "max_depth": st.max_depth, "solve_mode": st.solve_mode, "world": world,
-                       "launches": ctx.launch_count()}, f)
+                       "launches": ctx.launch_count(), "halo": op.halo_mode()}, f)
     dist.barrier()
     dist.destroy_process_group()
 

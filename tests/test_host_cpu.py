@@ -199,3 +199,34 @@ def test_cf_stencil_plan(name):
                     assert abs(sm - mixed) <= 1e-12 * (1.0 + abs(mixed))
                     checked += 1
     assert checked > 0
+
+
+@pytest.mark.parametrize("nx,ny", [(2, 2), (64, 2), (65, 3), (128, 7), (512, 256), (1000, 33), (3, 40)])
+def test_fused_halo_tile_schedule_covers_the_tile_once(nx, ny):
+    """vertline_tma_k with the fused neighbour exchange walks the tiles of an exchanged side first (sb_line_tma.cu: tile_of).
+    Whatever the shape and the set of exchanged sides, every tile is visited exactly once, the tiles touching a side come
+    before every interior tile, and each side is touched by as many tiles as the kernel's arrival counters expect
+    (ny along an x side, nbx along a y side)."""
+    import ctypes as C
+    from somar_b200 import capi
+    lib = capi.load()
+    nbx = ((nx + 1) // 2 + 31) // 32
+    for mask in range(16):
+        order = (C.c_int * (3 * nbx * ny))()
+        n = C.c_int()
+        capi.check(lib.sb_plan_line_tile_order(nx, ny, mask, order, nbx * ny, C.byref(n)))
+        assert n.value == nbx * ny
+        tiles = [(order[3 * u], order[3 * u + 1], order[3 * u + 2]) for u in range(n.value)]
+        assert sorted((bx, j) for bx, j, _ in tiles) == [(bx, j) for bx in range(nbx) for j in range(ny)]
+        per_side = [0, 0, 0, 0]
+        seen_interior = False
+        for bx, j, touch in tiles:
+            want = ((mask & 1) and bx == 0) * 1 | ((mask & 2) and bx == nbx - 1) * 2 | ((mask & 4) and j == 0) * 4 | ((mask & 8) and j == ny - 1) * 8
+            assert touch == want
+            if touch:
+                assert not seen_interior
+            else:
+                seen_interior = True
+            for s in range(4):
+                per_side[s] += (touch >> s) & 1
+        assert per_side == [ny if mask & 1 else 0, ny if mask & 2 else 0, nbx if mask & 4 else 0, nbx if mask & 8 else 0]

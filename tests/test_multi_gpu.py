@@ -94,7 +94,7 @@ def _two_rank_solve_2d(name, optset, agg):
     assert rel_err(phi, ref["phi"]) <= 1e-9
 
 
-def _run_worker(name, optset, agg):
+def _run_worker(name, optset, agg, extra_env=None):
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, "res.json")
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={WORLD}", "--master-addr", "127.0.0.1",
@@ -103,11 +103,29 @@ def _run_worker(name, optset, agg):
         env.pop("SB_AGG_CELLS", None)
         if agg is not None:
             env["SB_AGG_CELLS"] = agg
+        env.update(extra_env or {})
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
         res = json.load(open(out))
         phi = np.load(out + ".phi.npy")
     return res, phi
+
+
+@pytest.mark.parametrize("name,optset", [("line_cart", "defaults"), ("gsrb_perxy", "vcycle")])
+def test_peer_halo_is_bitwise_the_nccl_exchange(name, optset):
+    """The relaxations' halo exchange by stores into the neighbour's memory (sb_halo.cu; fused into vertline_tma_k where that
+    kernel runs) moves the same values as the NCCL send / recv it replaces: the solve is bit-identical either way."""
+    import somar_b200 as sb
+    from cases import geometry
+    c = CASES[name]
+    _, _, _, lo, hi = geometry(c)
+    if len(sb.make_base_grids(lo, hi, c["max_box"], (1, 1, 0), c["bf"])[0]) < WORLD:
+        pytest.skip(f"{name} has fewer boxes than ranks ({WORLD})")
+    res_p, phi_p = _run_worker(name, optset, "0")
+    res_n, phi_n = _run_worker(name, optset, "0", {"SB_PEER_HALO": "0"})
+    assert res_n["halo"] == "nccl" and res_p["halo"] in ("peer", "nccl")
+    assert res_p["status"] == res_n["status"] and res_p["norms"] == res_n["norms"]
+    assert np.array_equal(phi_p, phi_n)
 
 
 # ---- AMR hierarchies over several ranks: every level split into tiles, inter-level copies (coarse-fine buffer fill,
