@@ -73,3 +73,23 @@ def test_golden_general_line_kernel(name, monkeypatch):
     assert_norms(st.norms, z["solve_norms"][1:])
     assert rel_err(p.download(), z["solve_phi"]) <= 1e-9
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["cube", "flat"])
+def test_apply_op_matches_the_references_own_python_kit(ctx, name):
+    """The CUDA operator against code the reference's authors wrote independently of their Fortran: PythonScripts/ElliKit.py's
+    sparse Div . Grad Laplacian with mirror (Neumann) ghosts, imported by tests/golden/make_golden_ellikit.py where
+    /root/reference exists.  Cartesian map (J = 1), HomogNeumBC on every side, one box and 2 x 2 boxes."""
+    z = np.load(os.path.join(HERE, "golden", "independent", "ellikit_laplacian.npz"))
+    nx, L = np.array(z[f"{name}_nx"]), np.array(z[f"{name}_L"], dtype=float)
+    phi0, want = z[f"{name}_phi"], z[f"{name}_lap"]
+    dXi = L / nx
+    lo = np.array([0, 0, -nx[2]])
+    hi = lo + nx - 1
+    for max_box in ((0, 0, 0), (int(nx[0]) // 2, int(nx[1]) // 2, 0)):
+        blo, bhi = sb.make_base_grids(lo, hi, max_box, (1, 1, 0), 2)
+        op = sb.PoissonOp(ctx, lo, hi, dXi, blo, bhi, relax_method=sb.RELAX_GSRB)
+        phi, lhs = op.field(data=np.asfortranarray(phi0)), op.field()
+        op.applyOp(lhs, phi)
+        assert rel_err(lhs.download(), want) <= 1e-12
+        op.free()

@@ -156,3 +156,20 @@ def test_div_and_grad_are_second_order_accurate(ampl):
     for q in (0, 1):
         assert e[2][q] < 0.01
         assert 3.3 <= e[0][q] / e[1][q] <= 4.8 and 3.5 <= e[1][q] / e[2][q] <= 4.5
+
+
+@pytest.mark.parametrize("name", ["cube", "flat"])
+def test_oracle_operator_matches_the_references_own_python_kit(name):
+    """The reference ships an independent implementation of the same operator: PythonScripts/ElliKit.py, the sparse
+    Div . Grad Laplacian with mirror (Neumann) ghosts its Python-side solvers use.  tests/golden/independent/ellikit_laplacian.npz holds
+    L[phi] computed by importing that file (tests/golden/make_golden_ellikit.py, run where /root/reference exists).  On a
+    Cartesian map J = 1 and HomogNeumBC gives the same ghosts, so the oracle's applyOp -- i.e. the restated
+    COMPUTEMATRIXELEMENTS / APPLYOP / FILLGHOSTCELLS leaves behind the reference's C++ -- must reproduce it to rounding,
+    with several boxes per direction (the exchange path) as well as with one."""
+    z = np.load(os.path.join(HERE, "golden", "independent", "ellikit_laplacian.npz"))
+    nx, L, phi, want = tuple(int(v) for v in z[f"{name}_nx"]), tuple(float(v) for v in z[f"{name}_L"]), z[f"{name}_phi"], z[f"{name}_lap"]
+    scale = np.max(np.abs(want))
+    for max_box in ((0, 0, 0), (nx[0] // 2, nx[1] // 2, 0)):
+        r = run_ref("applyop", nx=nx, L=L, inp=[phi], max_box=max_box, block_factor=2, relax=5)
+        got = r["lhs"].reshape(nx, order="F")
+        assert np.max(np.abs(got - want)) <= 1e-12 * scale
