@@ -106,14 +106,16 @@ public:
 // Tap on the AMR levels' operators: AMRHybridSolver keeps its residual history private and prints 7 digits, so
 // every AMRNormLevel result is recorded in call order.
 static std::vector<double> g_amrNorms;
-class AmrTapOp : public PoissonOp
+// (-DSB_SHIM: the levels' operators are B200PoissonOps, so the reference's own AMRHybridSolver -- and the LevelHybridSolvers it
+// builds for its level solves -- drive the device operator through the virtual interface.)
+class AmrTapOp : public BasePoissonOp
 {
 public:
-    using PoissonOp::PoissonOp;
+    using BasePoissonOp::BasePoissonOp;
     Real
     AMRNormLevel(const LDFAB& a_res, const LDFAB* a_fineResPtr, const IntVect& a_refRatio, const int a_p) const override
     {
-        const Real v = PoissonOp::AMRNormLevel(a_res, a_fineResPtr, a_refRatio, a_p);
+        const Real v = BasePoissonOp::AMRNormLevel(a_res, a_fineResPtr, a_refRatio, a_p);
         g_amrNorms.push_back(v);
         return v;
     }
